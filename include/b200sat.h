@@ -1,0 +1,201 @@
+/*
+ * b200sat.h -- C ABI of the B200-native batched CDCL engine.
+ *
+ * This is the drop-in boundary for minisat-rust's solver seam.  The reference
+ * has no FFI layer of its own; the seam is `trait Solver` (src/sat.rs:28-36)
+ * with its two implementors CoreSolver (src/sat/minisat.rs:26-103) and
+ * SimpSolver (src/sat/minisat.rs:123-279).  Every entry point below names the
+ * reference item it replaces.  INTEGRATION.md shows the Rust `extern "C"`
+ * block + `impl Solver for B200Solver` a maintainer would add.
+ *
+ * Conventions
+ *   - Lit / Var encodings are the reference's: Var 0-based u32,
+ *     Lit = var<<1 | sign, sign 1 = negative (src/sat/formula.rs:63-75,137-154).
+ *   - bool results keep the reference meaning: 0 == "formula already UNSAT".
+ *   - negative int returns are engine errors (B200SAT_E_*); nothing throws.
+ *   - all solving runs in sm_100a CUDA kernels; there is NO CPU fallback: every
+ *     solving call fails with B200SAT_E_NO_DEVICE when no CUDA device exists.
+ */
+#ifndef B200SAT_H
+#define B200SAT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ settings
+ * One flat POD for the nested settings structs of the reference
+ * (CoreSettings/SimpSettings src/sat/minisat.rs:16-23,106-120).  Field
+ * defaults: SURVEY.md Appendix B.  Layout is identical to oracle_settings. */
+typedef struct b200sat_settings {
+    double   var_decay;               /* decision_heuristic.rs:25   0.95       */
+    double   clause_decay;            /* clause_db.rs:14            0.999      */
+    double   random_seed;             /* decision_heuristic.rs:26   91648253.0 */
+    double   random_var_freq;         /* decision_heuristic.rs:27   0.0        */
+    double   restart_first;           /* search.rs:31               100.0      */
+    double   restart_inc;             /* search.rs:32               2.0        */
+    double   size_factor;             /* search.rs:63               1/3        */
+    double   size_inc;                /* search.rs:64               1.1        */
+    double   size_adjust_inc;         /* search.rs:66               1.5        */
+    double   garbage_frac;            /* search.rs:176              0.20       */
+    double   simp_garbage_frac;       /* simplify.rs:28             0.5        */
+    uint64_t grow;                    /* simplify.rs:25             0          */
+    int32_t  size_adjust_start_confl; /* search.rs:65               100        */
+    int32_t  min_learnts_lim;         /* search.rs:62               0          */
+    int32_t  clause_lim;              /* simplify.rs:26             20         */
+    int32_t  subsumption_lim;         /* simplify.rs:27             1000       */
+    int32_t  ccmin_mode;              /* conflict.rs:5-15  0 none 1 basic 2 deep */
+    int32_t  phase_saving;            /* decision_heuristic.rs:6-10 0/1/2      */
+    uint8_t  luby_restart;            /* search.rs:30               1          */
+    uint8_t  rnd_pol;                 /* decision_heuristic.rs:29   0          */
+    uint8_t  rnd_init_act;            /* decision_heuristic.rs:30   0          */
+    uint8_t  use_rcheck;              /* search.rs:177              0 (unsupported: must be 0) */
+    uint8_t  use_asymm;               /* simplify.rs:29             0 (unsupported: must be 0) */
+    uint8_t  use_elim;                /* simplify.rs:30             1          */
+    uint8_t  extend_model;            /* minisat.rs:117             1          */
+    uint8_t  remove_satisfied;        /* clause_db.rs:13            1          */
+} b200sat_settings;
+
+/* src/sat/minisat/budget.rs:5-34.  The reference never sets a budget (no
+ * public setter exists); the struct shape is kept.  conflict/propagation
+ * budgets < 0 mean "off".  `interrupt` may point at a host int the caller sets
+ * non-zero to cancel (checked between launches). */
+typedef struct b200sat_budget {
+    int64_t       conflict_budget;
+    int64_t       propagation_budget;
+    volatile int *interrupt;
+} b200sat_budget;
+
+/* src/sat.rs:8-18, same field order. */
+typedef struct b200sat_stats {
+    uint64_t solves, restarts, decisions, rnd_decisions, conflicts, propagations,
+             tot_literals, del_literals;
+} b200sat_stats;
+
+enum { B200SAT_UNSAT = 0, B200SAT_SAT = 1, B200SAT_INTERRUPTED = 2 };   /* SolveRes src/sat.rs:21-25 */
+enum { B200SAT_CORE = 0, B200SAT_SIMP = 1 };                            /* CoreSolver / SimpSolver   */
+
+enum {
+    B200SAT_OK            = 0,
+    B200SAT_E_NO_DEVICE   = -1,   /* no CUDA device / driver: the product has no CPU path */
+    B200SAT_E_CUDA        = -2,   /* a CUDA runtime call failed (b200sat_last_error())    */
+    B200SAT_E_ARG         = -3,   /* bad argument / unsupported setting                   */
+    B200SAT_E_SPENT       = -4,   /* handle already consumed by solve_limited             */
+    B200SAT_E_MEM         = -5    /* an instance outgrew the largest slab the device can give it */
+};
+
+/* flags of the batch calls (driver behaviour of src/lib.rs:47-126) */
+enum {
+    B200SAT_F_PREPROCESS = 1,     /* Solver::preprocess before solve_limited (lib.rs:66)      */
+    B200SAT_F_NO_SOLVE   = 2,     /* stop after preprocess (--no-solve, lib.rs:83-86)         */
+    B200SAT_F_ZERO_STATS_ON_PRE_UNSAT = 4, /* lib.rs:75-78: "Solved by simplification" reports Stats::default() */
+    B200SAT_F_TRACE_HASH = 8,     /* fold (bt level, learnt lits) of every conflict into result.trace_hash */
+    B200SAT_F_COUNT_TRAFFIC = 16  /* fill result.traffic (SURVEY.md 8d counters)              */
+};
+
+void        b200sat_default_settings(b200sat_settings *s);   /* the Default impls, SURVEY App. B */
+const char *b200sat_last_error(void);                        /* thread-local message             */
+int         b200sat_device_count(void);                      /* <0: B200SAT_E_NO_DEVICE          */
+
+/* ------------------------------------------------------------------ single solver
+ * Mirrors `trait Solver` (src/sat.rs:28-36) one call per method. */
+typedef struct b200sat_solver b200sat_solver;
+
+/* CoreSolver::new (minisat.rs:90-102) / SimpSolver::new (minisat.rs:263-271) */
+b200sat_solver *b200sat_new(const b200sat_settings *s, int kind);
+void            b200sat_free(b200sat_solver *h);
+/* Solver::n_vars / n_clauses (sat.rs:29-30).  n_clauses is exact after
+ * preprocess/solve; before that it is the count of clauses handed in that are
+ * not trivially consumed (tautology / duplicate-literal folding is applied). */
+size_t   b200sat_n_vars(const b200sat_solver *h);
+size_t   b200sat_n_clauses(const b200sat_solver *h);
+/* Solver::new_var (sat.rs:31): upol -1 none / 0 false / 1 true; dvar bool. */
+uint32_t b200sat_new_var(b200sat_solver *h, int upol, int dvar);
+/* Solver::add_clause (sat.rs:32).  Returns 0 only when the clause is empty
+ * (after duplicate removal) or the handle is already known UNSAT; UNSAT found
+ * by unit propagation is reported by preprocess / solve_limited, because
+ * propagation runs on the device at solve time. */
+int      b200sat_add_clause(b200sat_solver *h, const uint32_t *lits, size_t n);
+/* Solver::preprocess (sat.rs:33; minisat.rs:50-55,161-191): 1 ok, 0 UNSAT, <0 error */
+int      b200sat_preprocess(b200sat_solver *h, const b200sat_budget *b);
+/* Solver::solve_limited (sat.rs:34).  Returns B200SAT_UNSAT/SAT/INTERRUPTED or
+ * <0.  model (may be NULL) receives n_vars bytes: 1 true, 0 false, 2 absent
+ * (model in var-index order, minisat.rs:68,235-239).  Only empty assumption
+ * lists are supported (the reference's callers always pass &[]). */
+int      b200sat_solve_limited(b200sat_solver *h, const b200sat_budget *b,
+                               const uint32_t *assumps, size_t n_assumps,
+                               uint8_t *model, size_t model_cap);
+/* Solver::stats (sat.rs:35; search.rs:590-601) */
+void     b200sat_get_stats(const b200sat_solver *h, b200sat_stats *out);
+
+/* ------------------------------------------------------------------ batch (new: no reference analogue)
+ * Many independent solvers advanced by one persistent kernel, one warp per
+ * instance.  Instances are given as CSR and are ingested on the device exactly
+ * as the equivalent DIMACS stream would be (dimacs.rs:146-167: lazy var
+ * creation in id order, then Solver::add_clause per clause in file order). */
+typedef struct b200sat_batch {
+    uint32_t        n_inst;
+    const uint32_t *inst_clause_off;  /* n_inst+1: clause index range of each instance */
+    const uint32_t *clause_off;       /* total_clauses+1: absolute literal offsets      */
+    const uint32_t *lits;             /* Lit-encoded literals                           */
+} b200sat_batch;
+
+typedef struct b200sat_result {
+    int32_t  verdict;          /* B200SAT_UNSAT / SAT / INTERRUPTED                     */
+    int32_t  status;           /* B200SAT_OK or B200SAT_E_MEM                           */
+    uint32_t n_vars;           /* Solver::n_vars after ingest                           */
+    uint32_t n_clauses_ingest; /* Solver::n_clauses after ingest (lib.rs:56)            */
+    uint32_t n_clauses_pre;    /* Solver::n_clauses after preprocess                    */
+    uint32_t eliminated_vars;  /* simplify.rs:388                                       */
+    uint32_t pre_ok;           /* result of preprocess()                                */
+    uint32_t attempts;         /* 1 + number of larger-slab retries                     */
+    uint64_t stats[8];         /* b200sat_stats order                                   */
+    uint64_t traffic[8];       /* visited, kept, deref, tail, moves, implied, analysis words, learnt words */
+    uint64_t trace_hash;       /* FNV-1a over conflicts when B200SAT_F_TRACE_HASH       */
+} b200sat_result;
+
+typedef struct b200sat_engine b200sat_engine;
+
+/* One engine per GPU (device index as in cudaSetDevice). */
+b200sat_engine *b200sat_engine_create(int device);
+void            b200sat_engine_destroy(b200sat_engine *e);
+/* Copy a host CSR batch to the device (pinned staging + async copies on
+ * `stream`, a cudaStream_t passed as void*; NULL = the legacy default stream)
+ * and size the per-warp working slabs for it. */
+int b200sat_engine_upload(b200sat_engine *e, const b200sat_batch *batch, void *stream);
+/* Generate the SURVEY.md 8d synthetic uniform k-SAT batch directly on the
+ * device (kernel gen_random_ksat; bit-identical to the host generator). */
+int b200sat_engine_generate_ksat(b200sat_engine *e, uint64_t seed_base, uint32_t n_inst,
+                                 uint32_t n_vars, uint32_t n_clauses, uint32_t k, void *stream);
+/* Solve the resident batch (kernel cdcl_warp).  Asynchronous on `stream`
+ * unless a slab overflow forces a retry pass (which synchronises). */
+int b200sat_engine_solve(b200sat_engine *e, const b200sat_settings *s, int kind, int flags,
+                         void *stream);
+/* Copy results (and models: n_inst*model_stride bytes, may be NULL) to the host; synchronises. */
+int b200sat_engine_download(b200sat_engine *e, b200sat_result *results, uint8_t *models,
+                            uint32_t model_stride, void *stream);
+/* Copy the resident CSR back to the host (sizes via b200sat_engine_batch_dims). */
+int b200sat_engine_batch_dims(b200sat_engine *e, uint32_t *n_inst, uint64_t *n_clauses, uint64_t *n_lits);
+int b200sat_engine_download_batch(b200sat_engine *e, uint32_t *inst_clause_off, uint32_t *clause_off,
+                                  uint32_t *lits);
+/* Tunables: warps per block / blocks per SM (0 = auto).  Launch facts of the last solve. */
+int b200sat_engine_configure(b200sat_engine *e, int warps_per_block, int blocks_per_sm,
+                             uint64_t arena_words, uint64_t wpool_entries);
+typedef struct b200sat_launch_info {
+    uint32_t grid, block, smem_bytes, warps_total, tier /*0 smem var state, 1 global*/, launches;
+    uint64_t slab_bytes;
+    float    last_kernel_ms;   /* CUDA-event time of the cdcl_warp launch(es) of the last solve */
+} b200sat_launch_info;
+int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out);
+
+/* upload + solve + download with HOST buffers (the end-to-end call). */
+int b200sat_solve_batch(b200sat_engine *e, const b200sat_batch *batch, const b200sat_settings *s,
+                        int kind, int flags, b200sat_result *results, uint8_t *models,
+                        uint32_t model_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

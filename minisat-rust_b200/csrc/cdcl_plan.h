@@ -1,0 +1,60 @@
+/*
+ * cdcl_plan.h -- host-side sizing of the per-warp working slab and choice of
+ * the var-state tier.  Shared by the C-ABI host (b200sat_api.cu) and the
+ * test-only emulator harness so both size memory identically.
+ */
+#ifndef B200SAT_CDCL_PLAN_H
+#define B200SAT_CDCL_PLAN_H
+#include <string.h>
+#include "cdcl_types.h"
+
+namespace b200sat {
+
+struct BatchShape {
+    u32 max_vars;        /* largest (max var id + 1) over the instances  */
+    u32 max_clauses;     /* largest clause count of one instance         */
+    u64 max_lits;        /* largest literal count of one instance        */
+    u32 max_clause_len;  /* longest clause                               */
+};
+
+/* shared-memory tiers compiled into the library (template instantiations) */
+static const int kSmemTiers[] = {128, 256, 512, 1024};
+static const int kNumSmemTiers = 4;
+
+/* smallest shared-memory tier that holds `nvars`, or 0 for the global tier */
+static inline int pick_tier_nv(u32 nvars, u32 max_clauses) {
+    if (max_clauses > 60000) return 0; /* u16 watch-list lengths */
+    for (int i = 0; i < kNumSmemTiers; i++) if (nvars <= (u32)kSmemTiers[i]) return kSmemTiers[i];
+    return 0;
+}
+
+static inline u32 sat_u32(u64 x) { return x > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)x; }
+
+/* attempt 0 is the first try; every retry multiplies the growable regions by 4 */
+static inline Layout plan_layout(const BatchShape &sh, int tier_nv, int kind, u32 attempt,
+                                 u64 arena_words_override, u64 wpool_override) {
+    Layout L;
+    memset(&L, 0, sizeof L);
+    const u64 nv = sh.max_vars ? sh.max_vars : 1;
+    const u64 grow = 1ull << (2 * attempt);
+    const u64 orig_words = sh.max_lits + 4ull * sh.max_clauses;
+    L.tier = tier_nv ? 0 : 1;
+    L.nv_cap = tier_nv ? (u32)tier_nv : (u32)nv;
+    u64 arena = (orig_words * 4 + 64 * nv + 32768) * grow;
+    if (kind == B200SAT_SIMP) arena += orig_words * 4;
+    if (arena_words_override) arena = arena_words_override * grow;
+    L.arena_cap = sat_u32((arena + 3) & ~3ull);
+    u64 wpool = (4 * sh.max_lits + 32 * nv + 16384) * grow;
+    if (wpool_override) wpool = wpool_override * grow;
+    if (wpool > (1ull << 25)) wpool = (wpool < (1ull << 26)) ? wpool : (1ull << 26) - 64; /* start<<W_SHIFT must fit u32 */
+    L.wpool_cap = sat_u32(wpool);
+    L.learnts_cap = sat_u32((8192 + (u64)sh.max_clauses) * grow);
+    L.clauses_cap = sat_u32((u64)sh.max_clauses * (kind == B200SAT_SIMP ? 3 : 1) + 64);
+    L.tmp_cap = sh.max_clause_len < 64 ? 64 : sh.max_clause_len;
+    L.simp_cap = 0;
+    layout_finalize(L);
+    return L;
+}
+
+} // namespace b200sat
+#endif

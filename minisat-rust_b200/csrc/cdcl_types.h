@@ -1,0 +1,97 @@
+/*
+ * cdcl_types.h -- plain-data definitions shared by the host launcher and the
+ * device solver (kernel parameters, per-warp slab layout, clause/watch word
+ * encodings).  No reference code is copied here; encodings are this
+ * engine's own (DESIGN.md "Data layout in HBM").
+ */
+#ifndef B200SAT_CDCL_TYPES_H
+#define B200SAT_CDCL_TYPES_H
+#include <stdint.h>
+#include "../../include/b200sat.h"
+
+namespace b200sat {
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int32_t i32;
+
+static const u32 FULL_MASK = 0xFFFFFFFFu;
+static const u32 CREF_UNDEF = 0xFFFFFFFFu;
+static const u32 LIT_NONE = 0xFFFFFFFFu;
+static const u32 GROUND = 1; /* assignment.rs:10 GROUND_LEVEL */
+
+/* clause header word: len << H_SHIFT | flags.  A clause block is
+ *   [hdr][lit0][lit1]...[lit len-1][extra?]   rounded up to 4 words, 16-byte aligned,
+ * extra = f32 activity (learnt, clause_header.rs:7) or u32 signature (clause_header.rs:6). */
+enum : u32 { H_DELETED = 1, H_RELOCED = 2, H_LEARNT = 4, H_EXTRA = 8, H_TOUCHED = 16, H_SHIFT = 5 };
+/* per-literal watch list descriptor: start << W_SHIFT | dirty | log2(capacity) */
+enum : u32 { W_CAP_MASK = 31, W_DIRTY = 32, W_SHIFT = 6 };
+/* per-var flag byte */
+enum : u32 { VF_SEEN = 3, VF_POL = 4, VF_DEC = 8, VF_UPOL_SET = 16, VF_UPOL_VAL = 32, VF_FROZEN = 64, VF_ELIM = 128 };
+enum : u32 { SEEN_UNDEF = 0, SEEN_SOURCE = 1, SEEN_REMOVABLE = 2, SEEN_FAILED = 3 }; /* conflict.rs:18-24 */
+enum : u8 { LB_FALSE = 0, LB_TRUE = 1, LB_UNDEF = 2 };                                /* formula.rs:14-18 */
+
+/* internal per-instance status */
+enum : u32 { ST_OK = 0, ST_MEM_ARENA = 1, ST_MEM_WPOOL = 2, ST_MEM_LIST = 3, ST_MEM_VARS = 4, ST_MEM_SIMP = 5, ST_INTERNAL = 9 };
+
+/* Per-warp working slab in HBM (all sizes in elements; offsets in bytes). */
+struct Layout {
+    u32 nv_cap;       /* variable capacity                                  */
+    u32 arena_cap;    /* words per arena half (multiple of 4)               */
+    u32 wpool_cap;    /* watchers per pool half                             */
+    u32 learnts_cap;  /* entries of the learnts list                        */
+    u32 clauses_cap;  /* entries of the clauses list                        */
+    u32 tmp_cap;      /* words of ingest scratch (>= longest input clause)  */
+    u32 simp_cap;     /* words of simplifier heap (0 when CORE only)        */
+    u32 tier;         /* 0: var state in shared memory, 1: in the slab      */
+    u64 off_arena[2], off_wpool[2], off_learnts, off_clauses, off_ol, off_tc, off_stk, off_tmp, off_vars,
+        off_simp;
+    u64 slab_bytes;
+};
+
+static inline u64 layout_align(u64 x) { return (x + 255) & ~(u64)255; }
+
+/* bytes of the var-state block when it lives in the slab (tier 1) */
+static inline u64 layout_vars_bytes(u32 nv) {
+    u64 n = nv;
+    return layout_align(8 * n) + layout_align(4 * n) + layout_align(4 * 2 * n) + layout_align(4 * 2 * n) +
+           5 * layout_align(4 * (n + 2)) + 2 * layout_align(n);
+}
+
+static inline void layout_finalize(Layout &L) {
+    u64 o = 0;
+    for (int h = 0; h < 2; h++) { L.off_arena[h] = o; o += layout_align(4ull * L.arena_cap); }
+    for (int h = 0; h < 2; h++) { L.off_wpool[h] = o; o += layout_align(8ull * L.wpool_cap); }
+    L.off_learnts = o; o += layout_align(4ull * L.learnts_cap);
+    L.off_clauses = o; o += layout_align(4ull * L.clauses_cap);
+    L.off_ol = o; o += layout_align(4ull * (L.nv_cap + 2));
+    L.off_tc = o; o += layout_align(4ull * (L.nv_cap + 2));
+    L.off_stk = o; o += layout_align(16ull * (L.nv_cap + 2));
+    L.off_tmp = o; o += layout_align(4ull * L.tmp_cap);
+    L.off_vars = o; if (L.tier == 1) o += layout_vars_bytes(L.nv_cap);
+    L.off_simp = o; o += layout_align(4ull * L.simp_cap);
+    L.slab_bytes = layout_align(o);
+}
+
+struct KParams {
+    const u32 *inst_clause_off;
+    const u32 *clause_off;
+    const u32 *lits;
+    const u32 *work;     /* optional list of instance ids to solve (retry pass); NULL = identity */
+    u32 n_work;
+    u32 *queue;          /* atomic work counter */
+    b200sat_result *results;
+    u8 *models;
+    u32 model_stride;
+    u8 *slabs;
+    Layout L;
+    b200sat_settings st;
+    i32 kind;
+    i32 flags;
+    u32 attempt;
+};
+
+} // namespace b200sat
+#endif

@@ -1,0 +1,1454 @@
+/*
+ * cdcl_warp.cuh -- warp-per-instance CDCL search for sm_100a.
+ *
+ * One warp owns one SAT instance.  Control flow is warp-uniform; the 32 lanes
+ * cooperate inside the data-parallel steps (watch-list scanning with ordered
+ * commit, clause loads for conflict analysis and minimisation, trail undo,
+ * reduceDB sort, garbage collection) and lane 0 runs the strictly sequential
+ * data-structure updates (VSIDS heap, activity bumps, list heads).
+ *
+ * The ALGORITHM follows mishun/minisat-rust so that decisions / conflicts /
+ * propagations are bit-exact against it.  Reference
+ * anchors (paths relative to /root/reference/src/sat/minisat):
+ *   propagate()        search/watches.rs:64-152
+ *   analyze()          search/conflict.rs:70-176
+ *   lit_redundant()    search/conflict.rs:195-249
+ *   cancel_until()     search.rs:253-261 + formula/assignment.rs:116-130
+ *   decide()           search.rs:216-237, search/decision_heuristic.rs:158-192
+ *   heap_*()           formula/index_map.rs:183-309
+ *   reduce_db()        search/clause_db.rs:156-215
+ *   remove_satisfied() search/clause_db.rs:238-254,283-303
+ *   garbage_collect()  formula/clause.rs:192-223, watches.rs:154-169, clause_db.rs:256-280
+ *   try_simplify()     search.rs:522-568
+ *   search_loop()      search.rs:452-517
+ *   add_clause()       search.rs:342-386
+ * The IMPLEMENTATION (data layout, warp cooperation, memory management) is new.
+ *
+ * Memory discipline: scalar state in memory is written by lane 0 only; a
+ * __syncwarp() separates such writes from reads by other lanes.
+ */
+#ifndef B200SAT_CDCL_WARP_CUH
+#define B200SAT_CDCL_WARP_CUH
+
+#include "cdcl_types.h"
+
+#ifdef B200SAT_EMU
+#include "simt_emu.h"
+#else
+#include <cuda_runtime.h>
+#define DEV __device__ __forceinline__
+#define DEVNI __device__ __noinline__
+#endif
+
+namespace b200sat {
+
+/* ------------------------------------------------------------------ per-warp scalar state (shared memory) */
+struct Scal {
+    u64 solves, starts, decisions, rnd_decisions, conflicts, propagations, max_literals, tot_literals;
+    u64 traffic[8];
+    u64 clauses_literals, learnts_literals, lc_size, lc_wasted, simp_db_props, trace_hash;
+    double var_inc, cla_inc, max_learnts, size_adjust_confl, seed, inv_var_decay, inv_cla_decay;
+    u32 arena_top, wpool_top, n_learnts, n_clauses, num_clauses, num_learnts;
+    i32 size_adjust_cnt;
+    u32 simp_db_assigns, simp_db_assigns_set, status, dec_vars, heap_n, cur_arena, cur_wpool, eliminated_vars;
+    u32 remove_satisfied, extra_clause_field;
+};
+
+/* ------------------------------------------------------------------ var-state tiers */
+template <int NV> struct SmemVars {
+    double act[NV];
+    u32 reason[NV];
+    u32 wstart[2 * NV];
+    u16 wlen[2 * NV];
+    u16 level[NV];
+    u16 trail[NV];
+    u16 lim[NV + 2];
+    u16 heap[NV];
+    u16 hidx[NV];
+    u8 assign[NV];
+    u8 vflags[NV];
+    Scal sc;
+    u32 bl[32];
+};
+
+template <int NV> struct VarsS {
+    typedef u16 idx_t;
+    static const u32 ABSENT = 0xFFFFu;
+    static const u32 MAXLEN = 0xFFF0u;
+    SmemVars<NV> *s;
+    DEV double *act() const { return s->act; }
+    DEV u32 *reason() const { return s->reason; }
+    DEV u32 *wstart() const { return s->wstart; }
+    DEV u16 *wlen() const { return s->wlen; }
+    DEV u16 *level() const { return s->level; }
+    DEV u16 *trail() const { return s->trail; }
+    DEV u16 *lim() const { return s->lim; }
+    DEV u16 *heap() const { return s->heap; }
+    DEV u16 *hidx() const { return s->hidx; }
+    DEV u8 *assign() const { return s->assign; }
+    DEV u8 *vflags() const { return s->vflags; }
+    DEV Scal &sc() const { return s->sc; }
+    DEV u32 *bl() const { return s->bl; }
+    DEV u32 cap() const { return NV; }
+};
+
+struct SmemSmall {
+    Scal sc;
+    u32 bl[32];
+};
+
+struct VarsG {
+    typedef u32 idx_t;
+    static const u32 ABSENT = 0xFFFFFFFFu;
+    static const u32 MAXLEN = 0x3FFFFFF0u;
+    SmemSmall *s;
+    double *act_;
+    u32 *reason_, *wstart_, *wlen_, *level_, *trail_, *lim_, *heap_, *hidx_;
+    u8 *assign_, *vflags_;
+    u32 cap_;
+    DEV double *act() const { return act_; }
+    DEV u32 *reason() const { return reason_; }
+    DEV u32 *wstart() const { return wstart_; }
+    DEV u32 *wlen() const { return wlen_; }
+    DEV u32 *level() const { return level_; }
+    DEV u32 *trail() const { return trail_; }
+    DEV u32 *lim() const { return lim_; }
+    DEV u32 *heap() const { return heap_; }
+    DEV u32 *hidx() const { return hidx_; }
+    DEV u8 *assign() const { return assign_; }
+    DEV u8 *vflags() const { return vflags_; }
+    DEV Scal &sc() const { return s->sc; }
+    DEV u32 *bl() const { return s->bl; }
+    DEV u32 cap() const { return cap_; }
+    DEV void bind(u8 *base, u32 nv) {
+        u64 n = nv, o = 0;
+        act_ = (double *)(base + o); o += layout_align(8 * n);
+        reason_ = (u32 *)(base + o); o += layout_align(4 * n);
+        wstart_ = (u32 *)(base + o); o += layout_align(4 * 2 * n);
+        wlen_ = (u32 *)(base + o); o += layout_align(4 * 2 * n);
+        level_ = (u32 *)(base + o); o += layout_align(4 * (n + 2));
+        trail_ = (u32 *)(base + o); o += layout_align(4 * (n + 2));
+        lim_ = (u32 *)(base + o); o += layout_align(4 * (n + 2));
+        heap_ = (u32 *)(base + o); o += layout_align(4 * (n + 2));
+        hidx_ = (u32 *)(base + o); o += layout_align(4 * (n + 2));
+        assign_ = base + o; o += layout_align(n);
+        vflags_ = base + o;
+        cap_ = nv;
+    }
+};
+
+/* ------------------------------------------------------------------ small helpers */
+DEV u32 ceil_log2(u32 x) { return x <= 1 ? 0 : 32 - __clz(x - 1); }
+DEV u32 round4(u32 x) { return (x + 3) & ~3u; }
+DEV u32 lanemask_lt(u32 lane) { return (1u << lane) - 1; }
+DEV u32 bcast(u32 x) { return __shfl_sync(FULL_MASK, x, 0); }
+DEV u32 warp_sum(u32 x) {
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL_MASK, x, o);
+    return x;
+}
+DEV u32 warp_max(u32 x) {
+    for (int o = 16; o > 0; o >>= 1) { u32 y = __shfl_xor_sync(FULL_MASK, x, o); x = y > x ? y : x; }
+    return x;
+}
+DEV u32 warp_excl_scan(u32 x, u32 lane, u32 &total) {
+    u32 v = x;
+    for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= (u32)o) v += y; }
+    total = __shfl_sync(FULL_MASK, v, 31);
+    return v - x;
+}
+DEV uint4 ld4(const u32 *p) { return *reinterpret_cast<const uint4 *>(p); }
+DEV float u2f(u32 x) { return __uint_as_float(x); }
+DEV u32 f2u(float x) { return __float_as_uint(x); }
+
+enum : u32 { OUT_NONE = 0, OUT_KEEPW = 1, OUT_KEEPCW = 2, OUT_MOVE = 3, OUT_UNIT = 4, OUT_CONFL = 5 };
+enum : u32 { LR_RESTART = 0, LR_UNSAT = 1, LR_SAT = 2, LR_ABORT = 3 };
+
+/* ================================================================== the solver */
+template <class VT, bool COUNT> struct WarpSolver {
+    typedef typename VT::idx_t idx_t;
+    VT V;
+    const KParams &P;
+    u32 lane;
+    u8 *slab;
+    u32 *arena;   /* active arena half */
+    uint2 *wpool; /* active watcher pool half */
+    u32 nvars, trail_n, qhead, nlevels;
+
+    DEV WarpSolver(const KParams &p, u32 ln) : P(p), lane(ln) {}
+
+    DEV Scal &sc() const { return V.sc(); }
+    DEV u32 *learnts() const { return (u32 *)(slab + P.L.off_learnts); }
+    DEV u32 *clauses() const { return (u32 *)(slab + P.L.off_clauses); }
+    DEV u32 *ol() const { return (u32 *)(slab + P.L.off_ol); }
+    DEV u32 *tc() const { return (u32 *)(slab + P.L.off_tc); }
+    DEV u32 *stk() const { return (u32 *)(slab + P.L.off_stk); }
+    DEV u32 *tmp() const { return (u32 *)(slab + P.L.off_tmp); }
+    DEV u32 *arena_half(u32 h) const { return (u32 *)(slab + P.L.off_arena[h]); }
+    DEV uint2 *wpool_half(u32 h) const { return (uint2 *)(slab + P.L.off_wpool[h]); }
+
+    DEV u32 lval(u32 lit) const { return (u32)V.assign()[lit >> 1] ^ (lit & 1); }
+    DEV bool is_true(u32 lit) const { return lval(lit) == 1; }
+    DEV bool is_false(u32 lit) const { return lval(lit) == 0; }
+    DEV bool failed() const { return sc().status != ST_OK; }
+    DEV void fail(u32 code) {
+        if (lane == 0 && sc().status == ST_OK) sc().status = code;
+        __syncwarp();
+    }
+    /* reference byte accounting, clause.rs:226-251 (LegacyCounter) */
+    DEV static u32 ref_size(u32 hdr) {
+        u32 len = hdr >> H_SHIFT;
+        return (hdr & (H_LEARNT | H_EXTRA)) ? 4 * (2 + len) : 4 * (1 + len);
+    }
+    DEV static u32 block_words(u32 hdr) { return round4(1 + (hdr >> H_SHIFT) + ((hdr & H_EXTRA) ? 1 : 0)); }
+
+    /* -------------------------------------------------------------- VSIDS heap (lane 0 only), index_map.rs:183-309 */
+    DEV void heap_sift_up(u32 i) {
+        idx_t *heap = V.heap(); idx_t *hidx = V.hidx(); const double *act = V.act();
+        u32 x = heap[i];
+        double ax = act[x];
+        while (i > 0) {
+            u32 p = (i - 1) >> 1;
+            u32 y = heap[p];
+            if (ax > act[y]) { heap[i] = (idx_t)y; hidx[y] = (idx_t)i; i = p; } else break;
+        }
+        heap[i] = (idx_t)x; hidx[x] = (idx_t)i;
+    }
+    DEV void heap_sift_down(u32 i) {
+        idx_t *heap = V.heap(); idx_t *hidx = V.hidx(); const double *act = V.act();
+        u32 n = sc().heap_n;
+        u32 x = heap[i];
+        double ax = act[x];
+        for (;;) {
+            u32 l = 2 * i + 1;
+            if (l >= n) break;
+            u32 r = l + 1;
+            u32 yl = heap[l];
+            double al = act[yl];
+            u32 c = l, yc = yl;
+            double ac = al;
+            if (r < n) {
+                u32 yr = heap[r];
+                double ar = act[yr];
+                if (ar > al) { c = r; yc = yr; ac = ar; }
+            }
+            if (ac > ax) { heap[i] = (idx_t)yc; hidx[yc] = (idx_t)i; i = c; } else break;
+        }
+        heap[i] = (idx_t)x; hidx[x] = (idx_t)i;
+    }
+    DEV void heap_insert(u32 v) {
+        if (V.hidx()[v] != (idx_t)VT::ABSENT) return;
+        u32 place = sc().heap_n;
+        sc().heap_n = place + 1;
+        V.heap()[place] = (idx_t)v;
+        heap_sift_up(place);
+    }
+    DEV u32 heap_pop() {
+        idx_t *heap = V.heap();
+        u32 x = heap[0];
+        u32 n = sc().heap_n - 1;
+        sc().heap_n = n;
+        u32 last = heap[n];
+        V.hidx()[x] = (idx_t)VT::ABSENT;
+        if (n > 0) { heap[0] = (idx_t)last; heap_sift_down(0); }
+        return x;
+    }
+    /* decision_heuristic.rs:126-140 (lane 0).  sift_down of IdxHeap::update is a
+     * no-op after an activity increase (children <= old key <= new key), so only
+     * the sift_up half is executed. */
+    DEV void bump_var(u32 v) {
+        double *act = V.act();
+        double nw = act[v] + sc().var_inc;
+        if (nw > 1e100) {
+            sc().var_inc *= 1e-100;
+            for (u32 i = 0; i < nvars; i++) act[i] *= 1e-100;
+            act[v] = nw * 1e-100;
+        } else act[v] = nw;
+        u32 place = V.hidx()[v];
+        if (place != VT::ABSENT) heap_sift_up(place);
+    }
+    /* random.rs:12-26 (lane 0) */
+    DEV double drand() {
+        double seed = sc().seed;
+        seed *= 1389796.0;
+        i32 q = (i32)(seed / 2147483647.0);
+        seed -= (double)q * 2147483647.0;
+        sc().seed = seed;
+        return seed / 2147483647.0;
+    }
+
+    /* -------------------------------------------------------------- trail (assignment.rs:99-130) */
+    DEV void assign_lit(u32 l, u32 reason) {
+        if (lane == 0) {
+            u32 v = l >> 1;
+            V.assign()[v] = (u8)((l & 1) ^ 1);
+            V.level()[v] = (idx_t)nlevels;
+            V.reason()[v] = reason;
+            V.trail()[trail_n] = (idx_t)l;
+        }
+        trail_n++;
+        __syncwarp();
+    }
+    DEV void new_decision_level() {
+        if (lane == 0) V.lim()[nlevels] = (idx_t)trail_n;
+        nlevels++;
+        __syncwarp();
+    }
+
+    /* -------------------------------------------------------------- watch lists */
+    /* relocate list `l` to the pool end with doubled capacity; false on failure */
+    DEV bool grow_list(u32 l) {
+        u32 word = V.wstart()[l];
+        u32 len = V.wlen()[l];
+        u32 capc = word & W_CAP_MASK;
+        u32 ncap = 2u << capc;
+        if (ncap > VT::MAXLEN) { fail(ST_MEM_LIST); return false; }
+        if (sc().wpool_top + ncap > P.L.wpool_cap) {
+            if (!compact_wpool(ncap + 64)) return false;
+            word = V.wstart()[l];
+        }
+        u32 top = sc().wpool_top;
+        uint2 *src = wpool + (word >> W_SHIFT);
+        uint2 *dst = wpool + top;
+        for (u32 i = lane; i < len; i += 32) dst[i] = src[i];
+        __syncwarp();
+        if (lane == 0) {
+            V.wstart()[l] = (top << W_SHIFT) | (word & W_DIRTY) | (capc + 1);
+            sc().wpool_top = top + ncap;
+        }
+        __syncwarp();
+        return true;
+    }
+    /* copy every list into the other pool half with fresh capacities */
+    DEV bool compact_wpool(u32 reserve) {
+        u32 nl = 2 * nvars;
+        u32 h = sc().cur_wpool ^ 1;
+        uint2 *dst = wpool_half(h);
+        u32 top = 0;
+        for (u32 l0 = 0; l0 < nl; l0 += 32) {
+            u32 l = l0 + lane;
+            u32 word = 0, len = 0, ncapc = 0, ncap = 0;
+            if (l < nl) {
+                word = V.wstart()[l]; len = V.wlen()[l];
+                u32 want = len + (len >> 1) + 2;
+                ncapc = ceil_log2(want < 4 ? 4 : want);
+                ncap = 1u << ncapc;
+            }
+            u32 tot;
+            u32 off = top + warp_excl_scan(ncap, lane, tot);
+            if (top + tot + reserve > P.L.wpool_cap) { fail(ST_MEM_WPOOL); return false; }
+            if (l < nl) {
+                const uint2 *src = wpool + (word >> W_SHIFT);
+                for (u32 i = 0; i < len; i++) dst[off + i] = src[i];
+                V.wstart()[l] = (off << W_SHIFT) | (word & W_DIRTY) | ncapc;
+            }
+            top += tot;
+        }
+        __syncwarp();
+        if (lane == 0) { sc().wpool_top = top; sc().cur_wpool = h; }
+        wpool = dst;
+        __syncwarp();
+        return true;
+    }
+    DEV bool push_watch(u32 l, u32 cref, u32 blocker) {
+        u32 word = V.wstart()[l];
+        u32 len = V.wlen()[l];
+        if (len == (1u << (word & W_CAP_MASK))) {
+            __syncwarp();
+            if (!grow_list(l)) return false;
+            word = V.wstart()[l];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            wpool[(word >> W_SHIFT) + len] = make_uint2(cref, blocker);
+            V.wlen()[l] = (idx_t)(len + 1);
+        }
+        __syncwarp();
+        return true;
+    }
+    /* watches.rs:39-44 */
+    DEV bool attach(u32 cref) {
+        u32 c0 = arena[cref + 1], c1 = arena[cref + 2];
+        if (!push_watch(c0 ^ 1, cref, c1)) return false;
+        return push_watch(c1 ^ 1, cref, c0);
+    }
+
+    /* -------------------------------------------------------------- BCP, watches.rs:64-152
+     * Lanes evaluate up to 32 watchers of watches[p] at once against the current
+     * assignment.  Outcomes before (and including) the first lane that implies a
+     * literal or conflicts are exactly what the sequential scan would produce and
+     * are committed in list order; lanes behind it are re-evaluated after the
+     * assignment (their watcher and clause words are already in registers). */
+    DEV u32 propagate() {
+        u32 confl = CREF_UNDEF;
+        u32 nprops = 0;
+        u32 t_vis = 0, t_kept = 0, t_deref = 0, t_tail = 0, t_moves = 0, t_impl = 0;
+        const u32 lt = lanemask_lt(lane);
+        while (qhead < trail_n && confl == CREF_UNDEF) {
+            u32 p = V.trail()[qhead];
+            qhead++;
+            nprops++;
+            const u32 not_p = p ^ 1;
+            u32 word = V.wstart()[p];
+            const u32 n = V.wlen()[p];
+            const bool dirty = (word & W_DIRTY) != 0;
+            uint2 *ws = wpool + (word >> W_SHIFT);
+            u32 j = 0;
+            for (u32 i = 0; i < n; i += 32) {
+                u32 idx = i + lane;
+                bool valid = idx < n;
+                uint2 w = make_uint2(0, 0);
+                if (valid) w = ws[idx];
+                uint4 hd = make_uint4(0, 0, 0, 0);
+                bool loaded = false, dead = false;
+                if (valid && dirty) { hd = ld4(arena + w.x); loaded = true; dead = (hd.x & H_DELETED) != 0; }
+                const bool live = valid && !dead;
+                if (confl != CREF_UNDEF) {
+                    /* conflict already found: copy the remainder unchanged (watches.rs:123-137) */
+                    u32 m = __ballot_sync(FULL_MASK, live);
+                    if (live) ws[j + __popc(m & lt)] = w;
+                    j += __popc(m);
+                    continue;
+                }
+                u32 kf = 2, lbase = 0;
+                for (;;) {
+                    const bool pend = live && lane >= lbase;
+                    u32 out = OUT_NONE, first = 0, lk = 0, len = 0;
+                    if (pend) {
+                        if (is_true(w.y)) out = OUT_KEEPW;
+                        else {
+                            if (!loaded) { hd = ld4(arena + w.x); loaded = true; }
+                            first = (hd.y == not_p) ? hd.z : hd.y;
+                            if (is_true(first)) out = OUT_KEEPCW;
+                            else {
+                                len = hd.x >> H_SHIFT;
+                                out = is_false(first) ? OUT_CONFL : OUT_UNIT;
+                                for (; kf < len; kf++) {
+                                    u32 l = (kf == 2) ? hd.w : arena[w.x + 1 + kf];
+                                    if (!is_false(l)) { lk = l; out = OUT_MOVE; break; }
+                                }
+                            }
+                        }
+                    }
+                    const u32 pendmask = __ballot_sync(FULL_MASK, pend);
+                    if (!pendmask) break;
+                    const u32 umask = __ballot_sync(FULL_MASK, out >= OUT_UNIT);
+                    const u32 u = umask ? (u32)__ffs(umask) - 1 : 32;
+                    const bool commit = pend && lane <= u;
+                    const bool keep = commit && out != OUT_MOVE;
+                    const u32 keepmask = __ballot_sync(FULL_MASK, keep);
+                    if (keep) ws[j + __popc(keepmask & lt)] = (out == OUT_KEEPW) ? w : make_uint2(w.x, first);
+                    j += __popc(keepmask);
+                    if (commit && out != OUT_KEEPW) {
+                        if (hd.y == not_p || out == OUT_MOVE) {
+                            arena[w.x + 1] = first;
+                            arena[w.x + 2] = (out == OUT_MOVE) ? lk : not_p;
+                        }
+                        if (out == OUT_MOVE) arena[w.x + 1 + kf] = not_p;
+                    }
+                    u32 movemask = __ballot_sync(FULL_MASK, commit && out == OUT_MOVE);
+                    if (COUNT) {
+                        t_vis += __popc(__ballot_sync(FULL_MASK, commit));
+                        t_kept += __popc(keepmask);
+                        t_deref += __popc(__ballot_sync(FULL_MASK, commit && out != OUT_KEEPW));
+                        u32 tl = 0;
+                        if (commit && out >= OUT_MOVE) tl = (out == OUT_MOVE) ? kf - 1 : len - 2;
+                        t_tail += warp_sum(tl);
+                        t_moves += __popc(movemask);
+                    }
+                    if (movemask) {
+                        while (movemask) {
+                            u32 ml = (u32)__ffs(movemask) - 1;
+                            movemask &= movemask - 1;
+                            u32 tgt = __shfl_sync(FULL_MASK, lk, ml) ^ 1;
+                            u32 mcr = __shfl_sync(FULL_MASK, w.x, ml);
+                            u32 mbl = __shfl_sync(FULL_MASK, first, ml);
+                            if (!push_watch(tgt, mcr, mbl)) return CREF_UNDEF;
+                        }
+                        ws = wpool + (V.wstart()[p] >> W_SHIFT); /* the pool may have been compacted */
+                    }
+                    if (u == 32) break;
+                    const u32 uout = __shfl_sync(FULL_MASK, out, u);
+                    const u32 ucr = __shfl_sync(FULL_MASK, w.x, u);
+                    const u32 ufirst = __shfl_sync(FULL_MASK, first, u);
+                    lbase = u + 1;
+                    if (uout == OUT_CONFL) {
+                        confl = ucr;
+                        const bool rem = live && lane >= lbase;
+                        u32 m = __ballot_sync(FULL_MASK, rem);
+                        if (rem) ws[j + __popc(m & lt)] = w;
+                        j += __popc(m);
+                        break;
+                    }
+                    assign_lit(ufirst, ucr);
+                    if (COUNT) t_impl++;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                V.wlen()[p] = (idx_t)j;
+                if (dirty) V.wstart()[p] = V.wstart()[p] & ~W_DIRTY;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            sc().propagations += nprops;
+            if (COUNT) {
+                u64 *t = sc().traffic;
+                t[0] += t_vis; t[1] += t_kept; t[2] += t_deref; t[3] += t_tail; t[4] += t_moves; t[5] += t_impl;
+            }
+        }
+        __syncwarp();
+        return confl;
+    }
+
+    /* -------------------------------------------------------------- clause arena */
+    /* returns cref or CREF_UNDEF; lits are written by the caller */
+    DEV u32 alloc_clause(u32 len, u32 flags) {
+        u32 hdr = (len << H_SHIFT) | flags;
+        u32 blk = block_words(hdr);
+        u32 top = sc().arena_top;
+        if (top + blk > P.L.arena_cap) { fail(ST_MEM_ARENA); return CREF_UNDEF; }
+        __syncwarp();
+        if (lane == 0) {
+            arena[top] = hdr;
+            sc().arena_top = top + blk;
+            sc().lc_size += ref_size(hdr);
+        }
+        __syncwarp();
+        return top;
+    }
+    /* clause_db.rs:119-143 */
+    DEV void bump_cla(u32 cr, u32 len) {
+        u32 resc = 0;
+        if (lane == 0) {
+            double nw = (double)u2f(arena[cr + 1 + len]) + sc().cla_inc;
+            arena[cr + 1 + len] = f2u((float)nw);
+            if (nw > 1e20) { sc().cla_inc *= 1e-20; resc = 1; }
+        }
+        resc = bcast(resc);
+        if (resc) {
+            __syncwarp();
+            u32 nl = sc().n_learnts;
+            const u32 *ls = learnts();
+            for (u32 i = lane; i < nl; i += 32) {
+                u32 c = ls[i];
+                u32 l = arena[c] >> H_SHIFT;
+                arena[c + 1 + l] = f2u((float)((double)u2f(arena[c + 1 + l]) * 1e-20));
+            }
+        }
+        __syncwarp();
+    }
+
+    /* -------------------------------------------------------------- conflict analysis, conflict.rs:70-249 */
+    /* iterative redundancy check; frames are (lit, cref, pos, len); the scan of one
+     * reason clause is lane-parallel, the first non-trivial literal in clause order
+     * decides what happens next, exactly as the sequential walk would. */
+    DEV bool lit_redundant(u32 literal, u32 &tcn, u64 &an_words) {
+        u32 fcr = V.reason()[literal >> 1];
+        if (fcr == CREF_UNDEF) return false;
+        u32 *st = stk();
+        u32 *tcl = tc();
+        u32 sp = 0;
+        u32 fp = literal, fpos = 1, flen = arena[fcr] >> H_SHIFT;
+        if (COUNT) an_words += 1 + flen;
+        for (;;) {
+            bool pushed = false;
+            while (fpos < flen) {
+                u32 k = fpos + lane;
+                u32 code = 0, l = 0;
+                if (k < flen) {
+                    l = arena[fcr + 1 + k];
+                    u32 v = l >> 1;
+                    u32 s = V.vflags()[v] & VF_SEEN;
+                    if (!(V.level()[v] == GROUND || s == SEEN_SOURCE || s == SEEN_REMOVABLE))
+                        code = (V.reason()[v] != CREF_UNDEF && s == SEEN_UNDEF) ? 1 : 2;
+                }
+                u32 nm = __ballot_sync(FULL_MASK, code != 0);
+                if (!nm) { fpos += 32; continue; }
+                u32 f = (u32)__ffs(nm) - 1;
+                u32 fc = __shfl_sync(FULL_MASK, code, f);
+                u32 fl = __shfl_sync(FULL_MASK, l, f);
+                if (fc == 2) {
+                    /* failure: every literal on the stack is not redundant either (conflict.rs:232-240) */
+                    __syncwarp();
+                    if (lane == 0) {
+                        u8 *vf = V.vflags();
+                        for (u32 t = 0; t <= sp; t++) {
+                            u32 q = (t == sp) ? fp : st[4 * t];
+                            if ((vf[q >> 1] & VF_SEEN) == SEEN_UNDEF) { vf[q >> 1] |= SEEN_FAILED; tcl[tcn++] = q; }
+                        }
+                    }
+                    tcn = bcast(tcn);
+                    __syncwarp();
+                    return false;
+                }
+                if (lane == 0) { st[4 * sp] = fp; st[4 * sp + 1] = fcr; st[4 * sp + 2] = fpos + f + 1; st[4 * sp + 3] = flen; }
+                sp++;
+                fp = fl;
+                fcr = V.reason()[fl >> 1];
+                fpos = 1;
+                flen = arena[fcr] >> H_SHIFT;
+                if (COUNT) an_words += 1 + flen;
+                pushed = true;
+                break;
+            }
+            if (pushed) continue;
+            /* frame exhausted: fp is implied by redundant literals (conflict.rs:241-246) */
+            __syncwarp();
+            if (lane == 0) {
+                u8 *vf = V.vflags();
+                if ((vf[fp >> 1] & VF_SEEN) == SEEN_UNDEF) { vf[fp >> 1] |= SEEN_REMOVABLE; tcl[tcn++] = fp; }
+            }
+            tcn = bcast(tcn);
+            __syncwarp();
+            if (sp == 0) return true;
+            sp--;
+            fp = st[4 * sp]; fcr = st[4 * sp + 1]; fpos = st[4 * sp + 2]; flen = st[4 * sp + 3];
+        }
+    }
+    DEV bool lit_redundant_basic(u32 literal, u64 &an_words) { /* conflict.rs:178-192 */
+        u32 cr = V.reason()[literal >> 1];
+        if (cr == CREF_UNDEF) return false;
+        u32 len = arena[cr] >> H_SHIFT;
+        if (COUNT) an_words += 1 + len;
+        bool bad = false;
+        for (u32 k = 1 + lane; k < len; k += 32) {
+            u32 v = arena[cr + 1 + k] >> 1;
+            if ((V.vflags()[v] & VF_SEEN) == SEEN_UNDEF && V.level()[v] > GROUND) bad = true;
+        }
+        return __ballot_sync(FULL_MASK, bad) == 0;
+    }
+
+    /* returns number of literals of the learnt clause (in ol()), sets bt */
+    DEV u32 analyze(u32 confl0, u32 &bt) {
+        u32 *out = ol();
+        u32 *tcl = tc();
+        u8 *vf = V.vflags();
+        const u32 lt = lanemask_lt(lane);
+        const u32 cur = nlevels;
+        i32 path_c = 0;
+        u32 index = trail_n;
+        u32 n_out = 1;
+        u32 confl = confl0;
+        u64 an_words = 0;
+        for (;;) {
+            u32 h = arena[confl];
+            u32 len = h >> H_SHIFT;
+            if (h & H_LEARNT) bump_cla(confl, len);
+            if (COUNT) an_words += 1 + len;
+            for (u32 k0 = (confl == confl0) ? 0 : 1; k0 < len; k0 += 32) {
+                u32 k = k0 + lane;
+                bool fresh = false, iscur = false;
+                u32 q = 0, v = 0;
+                if (k < len) {
+                    q = arena[confl + 1 + k];
+                    v = q >> 1;
+                    u32 f = vf[v];
+                    if ((f & VF_SEEN) == SEEN_UNDEF) {
+                        u32 lv = V.level()[v];
+                        if (lv > GROUND) { fresh = true; iscur = lv >= cur; vf[v] = (u8)(f | SEEN_SOURCE); }
+                    }
+                }
+                u32 fm = __ballot_sync(FULL_MASK, fresh);
+                u32 cm = __ballot_sync(FULL_MASK, fresh && iscur);
+                path_c += __popc(cm);
+                u32 lowm = fm & ~cm;
+                if (fresh && !iscur) out[n_out + __popc(lowm & lt)] = q;
+                n_out += __popc(lowm);
+                if (fm) {
+                    u32 *bl = V.bl();
+                    if (fresh) bl[__popc(fm & lt)] = v;
+                    __syncwarp();
+                    if (lane == 0) {
+                        u32 cnt = __popc(fm);
+                        for (u32 t = 0; t < cnt; t++) bump_var(bl[t]);
+                    }
+                    __syncwarp();
+                }
+            }
+            /* next literal to expand: last seen literal on the trail (conflict.rs:112-121) */
+            __syncwarp();
+            for (;;) {
+                i32 idx = (i32)index - 1 - (i32)lane;
+                bool s = idx >= 0 && (vf[V.trail()[idx] >> 1] & VF_SEEN) != 0;
+                u32 m = __ballot_sync(FULL_MASK, s);
+                if (m) { index = index - (u32)__ffs(m); break; }
+                if (index <= 32) { fail(ST_INTERNAL); return 0; }
+                index -= 32;
+            }
+            u32 pl = V.trail()[index];
+            __syncwarp();
+            if (lane == 0) vf[pl >> 1] &= (u8)~VF_SEEN;
+            __syncwarp();
+            path_c -= 1;
+            if (path_c <= 0) {
+                if (lane == 0) out[0] = pl ^ 1;
+                break;
+            }
+            confl = V.reason()[pl >> 1];
+        }
+        __syncwarp();
+        /* minimisation (conflict.rs:139-152); retain() visits position 0 too */
+        u32 tcn = 0;
+        u32 n_min = n_out;
+        const i32 ccmin = P.st.ccmin_mode;
+        if (ccmin != 0) {
+            u32 j = 0;
+            for (u32 i = 0; i < n_out; i++) {
+                u32 l = out[i];
+                bool red = (ccmin == 2) ? lit_redundant(l, tcn, an_words) : lit_redundant_basic(l, an_words);
+                if (lane == 0) {
+                    if (red) tcl[tcn] = l; else out[j] = l;
+                }
+                if (red) tcn++; else j++;
+                __syncwarp();
+            }
+            n_min = j;
+        }
+        /* clear seen[] (conflict.rs:154-156) */
+        for (u32 i = lane; i < n_min; i += 32) vf[out[i] >> 1] &= (u8)~VF_SEEN;
+        for (u32 i = lane; i < tcn; i += 32) vf[tcl[i] >> 1] &= (u8)~VF_SEEN;
+        /* backtrack level: first literal of the highest level among positions >= 1 (conflict.rs:158-175) */
+        if (n_min == 1) bt = GROUND;
+        else {
+            u32 best_lv = 0, best_i = 0xFFFFFFFFu;
+            for (u32 i = 1 + lane; i < n_min; i += 32) {
+                u32 lv = V.level()[out[i] >> 1];
+                if (lv > best_lv) { best_lv = lv; best_i = i; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                u32 olv = __shfl_xor_sync(FULL_MASK, best_lv, o);
+                u32 oi = __shfl_xor_sync(FULL_MASK, best_i, o);
+                if (olv > best_lv || (olv == best_lv && oi < best_i)) { best_lv = olv; best_i = oi; }
+            }
+            if (lane == 0 && best_i != 1) { u32 t = out[1]; out[1] = out[best_i]; out[best_i] = t; }
+            bt = best_lv;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            sc().max_literals += n_out;
+            sc().tot_literals += n_min;
+            if (COUNT) sc().traffic[6] += an_words;
+            if (P.flags & B200SAT_F_TRACE_HASH) {
+                u64 hsh = sc().trace_hash;
+                for (u32 i = 0; i < n_min + 2; i++) {
+                    u32 x = (i == 0) ? bt : (i == 1) ? n_min : out[i - 2];
+                    for (int b = 0; b < 4; b++) { hsh ^= (x >> (8 * b)) & 0xff; hsh *= 1099511628211ull; }
+                }
+                sc().trace_hash = hsh;
+            }
+        }
+        __syncwarp();
+        return n_min;
+    }
+
+    /* -------------------------------------------------------------- backtracking: search.rs:253-261 + assignment.rs:116-130 */
+    DEV void cancel_until(u32 target_level) {
+        if (nlevels > target_level) {
+            const u32 lt = lanemask_lt(lane);
+            const u32 target = V.lim()[target_level];
+            const u32 top = nlevels;
+            const i32 ps = P.st.phase_saving;
+            u8 *vf = V.vflags();
+            for (i32 hi = (i32)trail_n; hi > (i32)target; hi -= 32) {
+                i32 k = hi - 1 - (i32)lane;
+                bool ins = false;
+                u32 v = 0;
+                if (k >= (i32)target) {
+                    u32 l = V.trail()[k];
+                    v = l >> 1;
+                    u32 f = vf[v];
+                    if (ps == 2 || (ps == 1 && V.level()[v] == top)) f = (f & ~VF_POL) | ((l & 1) ? VF_POL : 0);
+                    vf[v] = (u8)f;
+                    V.assign()[v] = LB_UNDEF;
+                    ins = (f & VF_DEC) && V.hidx()[v] == (idx_t)VT::ABSENT;
+                }
+                u32 im = __ballot_sync(FULL_MASK, ins);
+                if (im) {
+                    u32 *bl = V.bl();
+                    if (ins) bl[__popc(im & lt)] = v;
+                    __syncwarp();
+                    if (lane == 0) {
+                        u32 cnt = __popc(im);
+                        for (u32 t = 0; t < cnt; t++) heap_insert(bl[t]);
+                    }
+                    __syncwarp();
+                }
+            }
+            trail_n = target;
+            nlevels = target_level;
+        }
+        if (qhead > trail_n) qhead = trail_n;
+        __syncwarp();
+    }
+
+    /* -------------------------------------------------------------- decision: search.rs:216-237, decision_heuristic.rs:158-192 */
+    DEV u32 pick_branch_lit() {
+        u32 next = LIT_NONE;
+        if (lane == 0) {
+            bool got = false;
+            u32 v = 0;
+            const bool use_rand = (P.st.random_var_freq != 0.0) || P.st.rnd_pol;
+            if (use_rand) {
+                if (drand() < P.st.random_var_freq && sc().heap_n > 0) {
+                    v = V.heap()[(u32)(drand() * (double)sc().heap_n)];
+                    if (V.assign()[v] == LB_UNDEF && (V.vflags()[v] & VF_DEC)) { sc().rnd_decisions++; got = true; }
+                }
+            }
+            if (!got) {
+                while (sc().heap_n > 0) {
+                    v = heap_pop();
+                    if (V.assign()[v] == LB_UNDEF && (V.vflags()[v] & VF_DEC)) { got = true; break; }
+                }
+            }
+            if (got) {
+                u32 f = V.vflags()[v];
+                u32 sign;
+                if (f & VF_UPOL_SET) sign = (f & VF_UPOL_VAL) ? 1 : 0;
+                else if (P.st.rnd_pol) sign = drand() < 0.5 ? 1 : 0;
+                else sign = (f & VF_POL) ? 1 : 0;
+                next = (v << 1) | sign;
+            }
+        }
+        return bcast(next);
+    }
+
+    /* -------------------------------------------------------------- learnt DB */
+    /* clause_db.rs:156-215.  The stable sort is done as a bitonic sort of the
+     * unique keys (class/activity bits << 32 | list position). */
+    DEV void reduce_db() {
+        const u32 L = sc().n_learnts;
+        if (L == 0) return;
+        u32 *ls = learnts();
+        u32 *scratch = arena_half(sc().cur_arena ^ 1);
+        u32 P2 = 1u << ceil_log2(L < 2 ? 2 : L);
+        if ((u64)P2 * 2 + L > P.L.arena_cap) { fail(ST_MEM_ARENA); return; }
+        u64 *keys = (u64 *)scratch;
+        u32 *oldl = scratch + 2 * (size_t)P2;
+        for (u32 i = lane; i < P2; i += 32) {
+            u64 k = ~0ull;
+            if (i < L) {
+                u32 cr = ls[i];
+                u32 len = arena[cr] >> H_SHIFT;
+                u32 kb = (len == 2) ? 0x7F800000u : arena[cr + 1 + len];
+                k = ((u64)kb << 32) | i;
+                oldl[i] = cr;
+            }
+            keys[i] = k;
+        }
+        __syncwarp();
+        for (u32 k = 2; k <= P2; k <<= 1) {
+            for (u32 jj = k >> 1; jj > 0; jj >>= 1) {
+                for (u32 t = lane; t < (P2 >> 1); t += 32) {
+                    u32 i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+                    u32 ix = i | jj;
+                    u64 a = keys[i], b = keys[ix];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ix] = a; }
+                }
+                __syncwarp();
+            }
+        }
+        for (u32 i = lane; i < L; i += 32) ls[i] = oldl[(u32)(keys[i] & 0xFFFFFFFFu)];
+        __syncwarp();
+        const u32 index_lim = L / 2;
+        const double extra_lim = sc().cla_inc / (double)L;
+        const u32 lt = lanemask_lt(lane);
+        u32 j = 0, removed = 0, rem_lits = 0, rem_bytes = 0;
+        for (u32 i0 = 0; i0 < L; i0 += 32) {
+            u32 i = i0 + lane;
+            bool keep = false;
+            u32 cr = 0, rl = 0, rb = 0;
+            if (i < L) {
+                cr = ls[i];
+                u32 h = arena[cr];
+                if (!(h & H_DELETED)) {
+                    u32 len = h >> H_SHIFT;
+                    u32 c0 = arena[cr + 1];
+                    bool locked = is_true(c0) && V.reason()[c0 >> 1] == cr;
+                    bool rm = len > 2 && !locked && (i < index_lim || (double)u2f(arena[cr + 1 + len]) < extra_lim);
+                    if (rm) {
+                        u32 c1 = arena[cr + 2];
+                        atomicOr(&V.wstart()[c0 ^ 1], (u32)W_DIRTY);
+                        atomicOr(&V.wstart()[c1 ^ 1], (u32)W_DIRTY);
+                        arena[cr] = h | H_DELETED;
+                        rl = len; rb = ref_size(h);
+                    } else keep = true;
+                }
+            }
+            u32 km = __ballot_sync(FULL_MASK, keep);
+            if (keep) ls[j + __popc(km & lt)] = cr;
+            j += __popc(km);
+            removed += __popc(__ballot_sync(FULL_MASK, rl != 0));
+            rem_lits += warp_sum(rl);
+            rem_bytes += warp_sum(rb);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            sc().n_learnts = j;
+            sc().num_learnts -= removed;
+            sc().learnts_literals -= rem_lits;
+            sc().lc_wasted += rem_bytes;
+        }
+        __syncwarp();
+    }
+
+    /* clause_db.rs:217-254,283-303 over one list */
+    DEV u32 remove_satisfied_list(u32 *list, u32 n, bool is_learnt) {
+        const u32 lt = lanemask_lt(lane);
+        u32 j = 0, removed = 0, rem_lits = 0, rem_bytes = 0;
+        for (u32 i0 = 0; i0 < n; i0 += 32) {
+            u32 i = i0 + lane;
+            bool keep = false;
+            u32 cr = 0, rl = 0, rb = 0, rmv = 0;
+            if (i < n) {
+                cr = list[i];
+                u32 h = arena[cr];
+                if (!(h & H_DELETED)) {
+                    u32 len = h >> H_SHIFT;
+                    bool sat = false;
+                    for (u32 k = 0; k < len; k++) if (is_true(arena[cr + 1 + k])) { sat = true; break; }
+                    if (sat) {
+                        atomicOr(&V.wstart()[arena[cr + 1] ^ 1], (u32)W_DIRTY);
+                        atomicOr(&V.wstart()[arena[cr + 2] ^ 1], (u32)W_DIRTY);
+                        arena[cr] = h | H_DELETED;
+                        rl = len; rb = ref_size(h); rmv = 1;
+                    } else {
+                        u32 l = 2, r = len;
+                        while (l < r) {
+                            if (!is_false(arena[cr + 1 + l])) l++;
+                            else { r--; arena[cr + 1 + l] = arena[cr + 1 + r]; }
+                        }
+                        if (r != len) {
+                            if (h & H_EXTRA) arena[cr + 1 + r] = arena[cr + 1 + len];
+                            arena[cr] = (r << H_SHIFT) | (h & ((1u << H_SHIFT) - 1));
+                        }
+                        keep = true;
+                    }
+                }
+            }
+            u32 km = __ballot_sync(FULL_MASK, keep);
+            if (keep) list[j + __popc(km & lt)] = cr;
+            j += __popc(km);
+            removed += __popc(__ballot_sync(FULL_MASK, rmv != 0));
+            rem_lits += warp_sum(rl);
+            rem_bytes += warp_sum(rb);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (is_learnt) { sc().num_learnts -= removed; sc().learnts_literals -= rem_lits; }
+            else { sc().num_clauses -= removed; sc().clauses_literals -= rem_lits; }
+            sc().lc_wasted += rem_bytes;
+        }
+        __syncwarp();
+        return j;
+    }
+    DEV void remove_satisfied() {
+        u32 j = remove_satisfied_list(learnts(), sc().n_learnts, true);
+        if (lane == 0) sc().n_learnts = j;
+        __syncwarp();
+        if (sc().remove_satisfied) {
+            j = remove_satisfied_list(clauses(), sc().n_clauses, false);
+            if (lane == 0) sc().n_clauses = j;
+            __syncwarp();
+        }
+    }
+
+    /* -------------------------------------------------------------- copying GC into the other arena half
+     * (clause.rs:136-155,192-223).  One call relocates up to 32 distinct clauses. */
+    struct GcState { u32 *dst; u32 top; u64 size; };
+    DEV bool gc_relocate(GcState &g, bool valid, u32 cr, u32 &ncr) {
+        bool alive = false, need = false;
+        u32 h = 0, blk = 0;
+        if (valid) {
+            h = arena[cr];
+            if (!(h & H_DELETED)) {
+                alive = true;
+                if (h & H_RELOCED) ncr = arena[cr + 1];
+                else {
+                    need = true;
+                    /* ClauseAllocator::reloc drops the signature when extra_clause_field is off (clause.rs:143-149) */
+                    if ((h & H_EXTRA) && !(h & H_LEARNT) && !sc().extra_clause_field) h &= ~(u32)H_EXTRA;
+                    blk = block_words(h);
+                }
+            }
+        }
+        u32 tot;
+        u32 off = warp_excl_scan(blk, lane, tot);
+        if (need) {
+            ncr = g.top + off;
+            u32 words = 1 + (h >> H_SHIFT) + ((h & H_EXTRA) ? 1 : 0);
+            g.dst[ncr] = h;
+            for (u32 k = 1; k < words; k++) g.dst[ncr + k] = arena[cr + k];
+            arena[cr + 1] = ncr;
+            arena[cr] = arena[cr] | H_RELOCED;
+        }
+        g.top += tot;
+        g.size += warp_sum(need ? ref_size(h) : 0);
+        return alive;
+    }
+    DEV void garbage_collect() {
+        const u32 lt = lanemask_lt(lane);
+        GcState g;
+        u32 hnew = sc().cur_arena ^ 1;
+        g.dst = arena_half(hnew);
+        g.top = 0;
+        g.size = 0;
+        /* watches.rs:154-169 */
+        for (u32 l = 0; l < 2 * nvars; l++) {
+            u32 n = V.wlen()[l];
+            uint2 *ws = wpool + (V.wstart()[l] >> W_SHIFT);
+            u32 j = 0;
+            for (u32 i0 = 0; i0 < n; i0 += 32) {
+                u32 i = i0 + lane;
+                uint2 w = make_uint2(0, 0);
+                if (i < n) w = ws[i];
+                u32 ncr = 0;
+                bool alive = gc_relocate(g, i < n, w.x, ncr);
+                u32 m = __ballot_sync(FULL_MASK, alive);
+                if (alive) ws[j + __popc(m & lt)] = make_uint2(ncr, w.y);
+                j += __popc(m);
+            }
+            __syncwarp();
+            if (lane == 0) { V.wlen()[l] = (idx_t)j; V.wstart()[l] = V.wstart()[l] & ~W_DIRTY; }
+        }
+        __syncwarp();
+        /* assignment.rs:236-243 */
+        for (u32 i0 = 0; i0 < trail_n; i0 += 32) {
+            u32 i = i0 + lane;
+            u32 v = 0, r = CREF_UNDEF;
+            if (i < trail_n) { v = V.trail()[i] >> 1; r = V.reason()[v]; }
+            u32 ncr = 0;
+            bool has = r != CREF_UNDEF;
+            bool alive = gc_relocate(g, has, r, ncr);
+            if (has) V.reason()[v] = alive ? ncr : CREF_UNDEF;
+        }
+        /* clause_db.rs:256-280 */
+        for (int pass = 0; pass < 2; pass++) {
+            u32 *list = pass == 0 ? learnts() : clauses();
+            u32 n = pass == 0 ? sc().n_learnts : sc().n_clauses;
+            u32 j = 0;
+            for (u32 i0 = 0; i0 < n; i0 += 32) {
+                u32 i = i0 + lane;
+                u32 cr = (i < n) ? list[i] : 0;
+                u32 ncr = 0;
+                bool alive = gc_relocate(g, i < n, cr, ncr);
+                u32 m = __ballot_sync(FULL_MASK, alive);
+                if (alive) list[j + __popc(m & lt)] = ncr;
+                j += __popc(m);
+            }
+            __syncwarp();
+            if (lane == 0) { if (pass == 0) sc().n_learnts = j; else sc().n_clauses = j; }
+            __syncwarp();
+        }
+        gc_finish(g, hnew);
+    }
+    DEV void gc_finish(GcState &g, u32 hnew) {
+        __syncwarp();
+        if (lane == 0) {
+            sc().cur_arena = hnew;
+            sc().arena_top = g.top;
+            sc().lc_size = g.size;
+            sc().lc_wasted = 0;
+        }
+        arena = g.dst;
+        __syncwarp();
+    }
+    /* search.rs:577-581 (+ a capacity-driven trigger of our own; GC is trace-neutral during search) */
+    DEV void try_garbage_collect() {
+        bool ref_trigger = (double)sc().lc_wasted > (double)sc().lc_size * P.st.garbage_frac;
+        bool cap_trigger = sc().lc_wasted > 0 && sc().arena_top > (P.L.arena_cap / 4) * 3;
+        if (ref_trigger || cap_trigger) garbage_collect();
+    }
+
+    /* decision_heuristic.rs:146-156 + index_map.rs:257-264 */
+    DEV void rebuild_order_heap() {
+        const u32 lt = lanemask_lt(lane);
+        u32 cnt = 0;
+        for (u32 v0 = 0; v0 < nvars; v0 += 32) {
+            u32 v = v0 + lane;
+            bool in = v < nvars && (V.vflags()[v] & VF_DEC) && V.assign()[v] == LB_UNDEF;
+            u32 m = __ballot_sync(FULL_MASK, in);
+            u32 pos = cnt + __popc(m & lt);
+            if (v < nvars) V.hidx()[v] = (idx_t)(in ? pos : VT::ABSENT);
+            if (in) V.heap()[pos] = (idx_t)v;
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            sc().heap_n = cnt;
+            for (i32 i = (i32)(cnt / 2) - 1; i >= 0; i--) heap_sift_down((u32)i);
+        }
+        __syncwarp();
+    }
+
+    /* search.rs:522-568 */
+    DEV void try_simplify() {
+        if (nlevels != 1) return;
+        if ((sc().simp_db_assigns_set && sc().simp_db_assigns == trail_n) || sc().propagations < sc().simp_db_props) return;
+        remove_satisfied();
+        try_garbage_collect();
+        rebuild_order_heap();
+        if (lane == 0) {
+            sc().simp_db_assigns_set = 1;
+            sc().simp_db_assigns = trail_n;
+            sc().simp_db_props = sc().propagations + sc().clauses_literals + sc().learnts_literals;
+        }
+        __syncwarp();
+    }
+
+    /* -------------------------------------------------------------- conflict handling: search.rs:263-304,503-517 */
+    /* returns false on a ground-level conflict (UNSAT) or on abort (check failed()) */
+    DEV bool propagate_learn_backtrack() {
+        for (;;) {
+            u32 confl = propagate();
+            if (failed()) return false;
+            if (confl == CREF_UNDEF) return true;
+            if (lane == 0) sc().conflicts++;
+            if (nlevels == 1) { __syncwarp(); return false; }
+            u32 bt;
+            u32 n = analyze(confl, bt);
+            if (failed()) return false;
+            cancel_until(bt);
+            u32 reason = CREF_UNDEF;
+            const u32 *out = ol();
+            u32 asserting = out[0];
+            if (n > 1) {
+                if (sc().n_learnts >= P.L.learnts_cap) { fail(ST_MEM_ARENA); return false; }
+                reason = alloc_clause(n, H_LEARNT | H_EXTRA);
+                if (reason == CREF_UNDEF) return false;
+                for (u32 i = lane; i < n; i += 32) arena[reason + 1 + i] = out[i];
+                if (lane == 0) {
+                    arena[reason + 1 + n] = f2u(0.0f);
+                    learnts()[sc().n_learnts] = reason;
+                    sc().n_learnts++;
+                    sc().num_learnts++;
+                    sc().learnts_literals += n;
+                    if (COUNT) sc().traffic[7] += 1 + n + 4;
+                }
+                __syncwarp();
+                bump_cla(reason, n);
+            }
+            if (lane == 0) {
+                sc().var_inc *= sc().inv_var_decay;   /* decision_heuristic.rs:142-144 */
+                sc().cla_inc *= sc().inv_cla_decay;   /* clause_db.rs:145-147 */
+                /* LearningGuard::bump search.rs:96-110 */
+                sc().size_adjust_cnt -= 1;
+                if (sc().size_adjust_cnt == 0) {
+                    sc().size_adjust_confl *= P.st.size_adjust_inc;
+                    sc().size_adjust_cnt = (i32)sc().size_adjust_confl;
+                    sc().max_learnts *= P.st.size_inc;
+                }
+            }
+            __syncwarp();
+            assign_lit(asserting, reason);
+            if (reason != CREF_UNDEF && !attach(reason)) return false;
+        }
+    }
+
+    DEV static double powi(double b, i32 e) {
+        double r = 1.0;
+        while (e > 0) { if (e & 1) r *= b; b *= b; e >>= 1; }
+        return r;
+    }
+    DEV static double luby(double y, u32 x) { /* luby.rs:2-20 */
+        u32 size = 1;
+        i32 seq = 0;
+        while (size < x + 1) { seq += 1; size = 2 * size + 1; }
+        while (size - 1 != x) { size = (size - 1) >> 1; seq -= 1; x = x % size; }
+        return powi(y, seq);
+    }
+
+    /* search.rs:452-501 */
+    DEV u32 search_loop(u64 nof_conflicts) {
+        if (lane == 0) sc().starts++;
+        __syncwarp();
+        const u64 confl_limit = sc().conflicts + nof_conflicts;
+        for (;;) {
+            if (!propagate_learn_backtrack()) return failed() ? LR_ABORT : LR_UNSAT;
+            if (sc().conflicts >= confl_limit) { cancel_until(GROUND); return LR_RESTART; }
+            try_simplify();
+            if ((double)sc().n_learnts >= sc().max_learnts + (double)trail_n) {
+                reduce_db();
+                if (failed()) return LR_ABORT;
+                try_garbage_collect();
+            }
+            if (lane == 0) sc().decisions++;
+            u32 next = pick_branch_lit();
+            if (next == LIT_NONE) return LR_SAT;
+            new_decision_level();
+            assign_lit(next, CREF_UNDEF);
+        }
+    }
+    /* search.rs:409-442; returns LR_SAT / LR_UNSAT / LR_ABORT */
+    DEV u32 search() {
+        if (lane == 0) {
+            sc().solves++;
+            double ml = (double)sc().num_clauses * P.st.size_factor;       /* LearningGuard::reset search.rs:89-94 */
+            double lo = (double)P.st.min_learnts_lim;
+            sc().max_learnts = ml > lo ? ml : lo;
+            sc().size_adjust_confl = (double)P.st.size_adjust_start_confl;
+            sc().size_adjust_cnt = P.st.size_adjust_start_confl;
+        }
+        __syncwarp();
+        u32 curr_restarts = 0;
+        for (;;) {
+            double base = P.st.luby_restart ? luby(P.st.restart_inc, curr_restarts) : powi(P.st.restart_inc, (i32)curr_restarts);
+            u64 ctg = (u64)(base * P.st.restart_first);
+            u32 r = search_loop(ctg);
+            if (r == LR_RESTART) { curr_restarts++; continue; }
+            return r;
+        }
+    }
+
+    /* -------------------------------------------------------------- per-instance setup + ingest */
+    DEV bool setup(u32 inst, u32 &cb, u32 &ce) {
+        cb = P.inst_clause_off[inst];
+        ce = P.inst_clause_off[inst + 1];
+        const u32 lb = P.clause_off[cb], le = P.clause_off[ce];
+        u32 mx = 0;
+        for (u32 k = lb + lane; k < le; k += 32) { u32 v = P.lits[k] >> 1; mx = v > mx ? v : mx; }
+        mx = warp_max(mx);
+        nvars = (le > lb) ? mx + 1 : 0;
+        trail_n = 0; qhead = 0; nlevels = 1;
+        if (lane == 0) {
+            Scal &s = sc();
+            s.solves = s.starts = s.decisions = s.rnd_decisions = s.conflicts = s.propagations = 0;
+            s.max_literals = s.tot_literals = 0;
+            for (int i = 0; i < 8; i++) s.traffic[i] = 0;
+            s.clauses_literals = s.learnts_literals = s.lc_size = s.lc_wasted = s.simp_db_props = 0;
+            s.trace_hash = 1469598103934665603ull;
+            s.var_inc = 1.0; s.cla_inc = 1.0; s.max_learnts = 0.0; s.size_adjust_confl = 0.0;
+            s.seed = P.st.random_seed;
+            s.inv_var_decay = 1.0 / P.st.var_decay;
+            s.inv_cla_decay = 1.0 / P.st.clause_decay;
+            s.arena_top = 0; s.wpool_top = 0; s.n_learnts = 0; s.n_clauses = 0; s.num_clauses = 0; s.num_learnts = 0;
+            s.size_adjust_cnt = 0; s.simp_db_assigns = 0; s.simp_db_assigns_set = 0; s.status = ST_OK;
+            s.dec_vars = nvars; s.heap_n = nvars; s.cur_arena = 0; s.cur_wpool = 0; s.eliminated_vars = 0;
+            s.remove_satisfied = P.st.remove_satisfied; s.extra_clause_field = 0;
+        }
+        arena = arena_half(0);
+        wpool = wpool_half(0);
+        __syncwarp();
+        if (nvars > V.cap() || nvars > P.L.nv_cap) { fail(ST_MEM_VARS); return false; }
+        for (u32 v = lane; v < nvars; v += 32) {
+            V.act()[v] = 0.0;
+            V.reason()[v] = CREF_UNDEF;
+            V.level()[v] = (idx_t)GROUND;
+            V.heap()[v] = (idx_t)v;
+            V.hidx()[v] = (idx_t)v;
+            V.assign()[v] = LB_UNDEF;
+            V.vflags()[v] = (u8)(VF_POL | VF_DEC);
+            V.wstart()[2 * v] = 0; V.wstart()[2 * v + 1] = 0;
+            V.wlen()[2 * v] = 0; V.wlen()[2 * v + 1] = 0;
+        }
+        if (lane == 0) V.lim()[0] = 0;
+        __syncwarp();
+        if (P.st.rnd_init_act) { /* decision_heuristic.rs:70-88: activity drawn at var creation, heap insert in creation order */
+            if (lane == 0) {
+                sc().heap_n = 0;
+                for (u32 v = 0; v < nvars; v++) {
+                    V.act()[v] = drand() * 0.00001;
+                    V.hidx()[v] = (idx_t)VT::ABSENT;
+                    heap_insert(v);
+                }
+            }
+            __syncwarp();
+        }
+        /* size the watch lists: list l can never hold more original watchers than
+         * the number of clauses containing the complement of l */
+        for (u32 k = lb + lane; k < le; k += 32) atomicAdd(&V.wstart()[P.lits[k] ^ 1], 1u);
+        __syncwarp();
+        u32 top = 0;
+        for (u32 l0 = 0; l0 < 2 * nvars; l0 += 32) {
+            u32 l = l0 + lane;
+            u32 capc = 0, cap = 0;
+            if (l < 2 * nvars) {
+                u32 cnt = V.wstart()[l];
+                capc = ceil_log2(cnt + 4);
+                cap = 1u << capc;
+            }
+            u32 tot;
+            u32 off = top + warp_excl_scan(cap, lane, tot);
+            if (l < 2 * nvars) V.wstart()[l] = (off << W_SHIFT) | capc;
+            top += tot;
+        }
+        __syncwarp();
+        if (top > P.L.wpool_cap) { fail(ST_MEM_WPOOL); return false; }
+        if (lane == 0) sc().wpool_top = top;
+        __syncwarp();
+        return true;
+    }
+
+    /* Searcher::add_clause search.rs:342-386.  0 = UNSAT, 1 = consumed, 2 = added (cref in out_cr) */
+    DEV u32 add_clause(const u32 *src, u32 len, u32 &out_cr) {
+        u32 nk = 0;
+        bool consumed = false;
+        u32 cr = CREF_UNDEF;
+        if (len <= 32) {
+            u32 lit = lane < len ? src[lane] : LIT_NONE;
+            bool dup = false, taut = false;
+            for (u32 j = 0; j < len; j++) {
+                u32 o = __shfl_sync(FULL_MASK, lit, j);
+                if (o == lit && j < lane) dup = true;
+                if (o == (lit ^ 1)) taut = true;
+            }
+            bool valid = lane < len;
+            bool kept = valid && !dup && !is_false(lit);
+            consumed = __ballot_sync(FULL_MASK, valid && (taut || is_true(lit))) != 0;
+            if (consumed) return 1;
+            u32 km = __ballot_sync(FULL_MASK, kept);
+            nk = __popc(km);
+            if (nk == 0) return 0;
+            if (nk == 1) {
+                u32 unit = __shfl_sync(FULL_MASK, lit, __ffs(km) - 1);
+                assign_lit(unit, CREF_UNDEF);
+                u32 confl = propagate();
+                if (failed()) return 0;
+                return confl == CREF_UNDEF ? 1 : 0;
+            }
+            u32 key = kept ? lit : LIT_NONE;
+            u32 rank = 0;
+            for (u32 j = 0; j < len; j++) {
+                u32 o = __shfl_sync(FULL_MASK, key, j);
+                if (o < key) rank++;
+            }
+            cr = alloc_clause(nk, sc().extra_clause_field ? (u32)H_EXTRA : 0u);
+            if (cr == CREF_UNDEF) return 0;
+            if (kept) arena[cr + 1 + rank] = lit;
+        } else {
+            /* long clause: strided over lanes, O(len^2/32) ranking through scratch memory */
+            u32 *t = tmp();
+            if (len > P.L.tmp_cap) { fail(ST_MEM_ARENA); return 0; }
+            bool cons = false;
+            u32 cnt = 0;
+            for (u32 i = lane; i < len; i += 32) {
+                u32 lit = src[i];
+                bool dup = false;
+                for (u32 j = 0; j < len; j++) {
+                    u32 o = src[j];
+                    if (o == lit && j < i) dup = true;
+                    if (o == (lit ^ 1)) cons = true;
+                }
+                if (is_true(lit)) cons = true;
+                bool kept = !dup && !is_false(lit);
+                t[i] = kept ? lit : LIT_NONE;
+                if (kept) cnt++;
+            }
+            if (__ballot_sync(FULL_MASK, cons)) return 1;
+            nk = warp_sum(cnt);
+            __syncwarp();
+            if (nk == 0) return 0;
+            if (nk == 1) {
+                u32 unit = LIT_NONE;
+                for (u32 i = lane; i < len; i += 32) if (t[i] != LIT_NONE) unit = t[i];
+                u32 m = __ballot_sync(FULL_MASK, unit != LIT_NONE);
+                unit = __shfl_sync(FULL_MASK, unit, __ffs(m) - 1);
+                assign_lit(unit, CREF_UNDEF);
+                u32 confl = propagate();
+                if (failed()) return 0;
+                return confl == CREF_UNDEF ? 1 : 0;
+            }
+            cr = alloc_clause(nk, sc().extra_clause_field ? (u32)H_EXTRA : 0u);
+            if (cr == CREF_UNDEF) return 0;
+            for (u32 i = lane; i < len; i += 32) {
+                u32 key = t[i];
+                if (key == LIT_NONE) continue;
+                u32 rank = 0;
+                for (u32 j = 0; j < len; j++) if (t[j] < key) rank++;
+                arena[cr + 1 + rank] = key;
+            }
+        }
+        __syncwarp();
+        if (sc().extra_clause_field) { /* clause_db.rs:78-91 + formula/util.rs:5-11 */
+            u32 a = 0;
+            for (u32 i = lane; i < nk; i += 32) a |= 1u << ((arena[cr + 1 + i] >> 1) & 31);
+            for (int o = 16; o > 0; o >>= 1) a |= __shfl_xor_sync(FULL_MASK, a, o);
+            if (lane == 0) arena[cr + 1 + nk] = a;
+        }
+        if (sc().n_clauses >= P.L.clauses_cap) { fail(ST_MEM_ARENA); return 0; }
+        if (lane == 0) {
+            clauses()[sc().n_clauses] = cr;
+            sc().n_clauses++;
+            sc().num_clauses++;
+            sc().clauses_literals += nk;
+        }
+        __syncwarp();
+        if (!attach(cr)) return 0;
+        out_cr = cr;
+        return 2;
+    }
+
+    /* -------------------------------------------------------------- one instance: ingest + CoreSolver driver
+     * (sat/minisat.rs:37-88, lib.rs:47-126) */
+    DEV void solve_core(u32 inst) {
+        u32 cb, ce;
+        bool ok = setup(inst, cb, ce);
+        u32 n_ingest = 0, n_pre = 0, pre_ok = 1;
+        i32 verdict = B200SAT_INTERRUPTED;
+        if (ok) {
+            for (u32 c = cb; c < ce && ok; c++) { /* CoreSolver::add_clause minisat.rs:41-48 */
+                u32 b = P.clause_off[c], e = P.clause_off[c + 1];
+                u32 cr;
+                if (add_clause(P.lits + b, e - b, cr) == 0) ok = false;
+                if (failed()) break;
+            }
+            n_ingest = sc().num_clauses;
+            n_pre = n_ingest;
+            if (!failed()) {
+                if (P.flags & B200SAT_F_PREPROCESS) { /* CoreSolver::preprocess minisat.rs:50-55, search.rs:388-395 */
+                    if (ok) {
+                        u32 confl = propagate();
+                        if (confl == CREF_UNDEF) try_simplify(); else ok = false;
+                    }
+                    pre_ok = ok ? 1 : 0;
+                    n_pre = sc().num_clauses;
+                }
+                if (!failed()) {
+                    if (!ok) verdict = B200SAT_UNSAT;
+                    else if (P.flags & B200SAT_F_NO_SOLVE) verdict = B200SAT_INTERRUPTED;
+                    else {
+                        u32 r = search();
+                        verdict = (r == LR_SAT) ? B200SAT_SAT : (r == LR_UNSAT) ? B200SAT_UNSAT : B200SAT_INTERRUPTED;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        write_result(inst, verdict, n_ingest, n_pre, pre_ok);
+    }
+
+    DEV void write_result(u32 inst, i32 verdict, u32 n_ingest, u32 n_pre, u32 pre_ok) {
+        b200sat_result *r = P.results + inst;
+        const Scal &s = sc();
+        bool zero = !pre_ok && (P.flags & B200SAT_F_ZERO_STATS_ON_PRE_UNSAT);
+        if (lane == 0) {
+            r->verdict = s.status == ST_OK ? verdict : B200SAT_INTERRUPTED;
+            r->status = s.status == ST_OK ? B200SAT_OK : -(i32)(100 + s.status);
+            r->n_vars = nvars;
+            r->n_clauses_ingest = n_ingest;
+            r->n_clauses_pre = n_pre;
+            r->eliminated_vars = s.eliminated_vars;
+            r->pre_ok = pre_ok;
+            r->attempts = P.attempt;
+            r->stats[0] = zero ? 0 : s.solves;       /* search.rs:590-601 */
+            r->stats[1] = zero ? 0 : s.starts;
+            r->stats[2] = zero ? 0 : s.decisions;
+            r->stats[3] = zero ? 0 : s.rnd_decisions;
+            r->stats[4] = zero ? 0 : s.conflicts;
+            r->stats[5] = zero ? 0 : s.propagations;
+            r->stats[6] = zero ? 0 : s.tot_literals;
+            r->stats[7] = zero ? 0 : s.max_literals - s.tot_literals;
+            for (int i = 0; i < 8; i++) r->traffic[i] = s.traffic[i];
+            r->trace_hash = s.trace_hash;
+        }
+        if (P.models && s.status == ST_OK && verdict == B200SAT_SAT) { /* formula/util.rs:35-41 */
+            u8 *m = P.models + (size_t)inst * P.model_stride;
+            for (u32 v = lane; v < P.model_stride; v += 32) m[v] = v < nvars ? V.assign()[v] : (u8)LB_UNDEF;
+        }
+        __syncwarp();
+    }
+};
+
+} // namespace b200sat
+#endif

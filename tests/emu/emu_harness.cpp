@@ -1,0 +1,198 @@
+/*
+ * emu_harness.cpp -- TEST-ONLY: runs the device solver source under the
+ * single-warp SIMT emulator (simt_emu.h) on the CPU.  Built by
+ * tests/emu/Makefile into tests/emu/libemu.so and loaded only by tests.
+ */
+#define B200SAT_EMU 1
+#include <string.h>
+#include <vector>
+#include "simt_emu.h"
+#include "../../minisat-rust_b200/csrc/cdcl_plan.h"
+#include "../../minisat-rust_b200/csrc/cdcl_warp.cuh"
+#ifdef B200SAT_HAVE_SIMP
+#include "../../minisat-rust_b200/csrc/simp_warp.cuh"
+#endif
+
+namespace simt {
+thread_local Warp *g_warp_tls = nullptr;
+Warp *g_warp = nullptr;
+
+static void trampoline(int lane) {
+    Warp *w = g_warp;
+    w->entry(w->user, lane);
+    w->done[lane] = true;
+    w->kind[lane] = K_EXIT;
+    swapcontext(&w->lanes[lane], &w->sched);
+}
+
+static inline uint64_t next_rng(uint64_t &s) {
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+void run_warp(void (*entry)(void *, int), void *user, uint64_t seed) {
+    static const size_t STACK = 512 * 1024;
+    Warp *w = new Warp();
+    memset(w->kind, 0, sizeof w->kind);
+    w->entry = entry;
+    w->user = user;
+    w->rng = seed;
+    w->n_collectives = 0;
+    g_warp = w;
+    for (int l = 0; l < 32; l++) {
+        w->stacks[l] = (char *)malloc(STACK);
+        w->done[l] = false;
+        getcontext(&w->lanes[l]);
+        w->lanes[l].uc_stack.ss_sp = w->stacks[l];
+        w->lanes[l].uc_stack.ss_size = STACK;
+        w->lanes[l].uc_link = &w->sched;
+        makecontext(&w->lanes[l], (void (*)())trampoline, 1, l);
+    }
+    int order[32];
+    for (;;) {
+        for (int i = 0; i < 32; i++) order[i] = i;
+        if (seed != 0) {
+            uint64_t mode = next_rng(w->rng) % 3;
+            if (mode == 0) for (int i = 31; i > 0; i--) { int j = (int)(next_rng(w->rng) % (uint64_t)(i + 1)); int t = order[i]; order[i] = order[j]; order[j] = t; }
+            else if (mode == 1) for (int i = 0; i < 32; i++) order[i] = 31 - i;
+        }
+        for (int i = 0; i < 32; i++) {
+            int l = order[i];
+            if (w->done[l]) continue;
+            w->cur = l;
+            swapcontext(&w->sched, &w->lanes[l]);
+        }
+        int k0 = w->kind[0];
+        for (int l = 1; l < 32; l++)
+            if (w->kind[l] != k0) {
+                fprintf(stderr, "simt_emu: DIVERGENCE at collective %llu: lane0 kind %d, lane %d kind %d\n",
+                        (unsigned long long)w->n_collectives, k0, l, w->kind[l]);
+                abort();
+            }
+        if (k0 == K_EXIT) break;
+        w->n_collectives++;
+        switch (k0) {
+        case K_BALLOT: {
+            uint32_t m = 0;
+            for (int l = 0; l < 32; l++) if (w->arg[l]) m |= 1u << l;
+            for (int l = 0; l < 32; l++) w->res[l] = m;
+            break;
+        }
+        case K_SHFL:
+            for (int l = 0; l < 32; l++) w->res[l] = w->arg[w->arg2[l]];
+            break;
+        case K_SHFL_XOR:
+            for (int l = 0; l < 32; l++) w->res[l] = w->arg[(l ^ w->arg2[l]) & 31];
+            break;
+        case K_SHFL_UP:
+            for (int l = 0; l < 32; l++) { int s = l - w->arg2[l]; w->res[l] = w->arg[s < 0 ? l : s]; }
+            break;
+        case K_SYNC: break;
+        default: fprintf(stderr, "simt_emu: bad collective %d\n", k0); abort();
+        }
+    }
+    for (int l = 0; l < 32; l++) free(w->stacks[l]);
+    g_warp = nullptr;
+    delete w;
+}
+} // namespace simt
+
+using namespace b200sat;
+
+namespace {
+struct Job {
+    KParams P;
+    void *smem;
+    int tier_nv;
+    u32 inst;
+    bool count;
+};
+
+template <class VT, bool COUNT> void run_one(WarpSolver<VT, COUNT> &S, const Job *j) {
+#ifdef B200SAT_HAVE_SIMP
+    if (j->P.kind == B200SAT_SIMP) { solve_simp(S, j->inst); return; }
+#endif
+    S.solve_core(j->inst);
+}
+
+template <int NV, bool COUNT> void entry_s(void *user, int lane) {
+    Job *j = (Job *)user;
+    WarpSolver<VarsS<NV>, COUNT> S(j->P, (u32)lane);
+    S.V.s = (SmemVars<NV> *)j->smem;
+    S.slab = j->P.slabs;
+    run_one(S, j);
+}
+template <bool COUNT> void entry_g(void *user, int lane) {
+    Job *j = (Job *)user;
+    WarpSolver<VarsG, COUNT> S(j->P, (u32)lane);
+    S.V.s = (SmemSmall *)j->smem;
+    S.slab = j->P.slabs;
+    S.V.bind(S.slab + j->P.L.off_vars, j->P.L.nv_cap);
+    run_one(S, j);
+}
+} // namespace
+
+extern "C" {
+
+/* tier_nv: 128/256/512/1024 = shared-memory tier, 0 = global tier, -1 = auto.
+ * sched_seed: 0 = lanes run in ascending order, else adversarial ordering.
+ * Returns 0, or -1 when `kind` is not compiled in. */
+int emu_solve_batch(const uint32_t *inst_clause_off, const uint32_t *clause_off, const uint32_t *lits,
+                    uint32_t n_inst, const b200sat_settings *st, int kind, int flags, int tier_nv,
+                    uint64_t arena_words, uint64_t wpool_entries, uint64_t sched_seed,
+                    b200sat_result *results, uint8_t *models, uint32_t model_stride) {
+#ifndef B200SAT_HAVE_SIMP
+    if (kind == B200SAT_SIMP) return -1;
+#endif
+    BatchShape sh = {0, 0, 0, 0};
+    for (u32 i = 0; i < n_inst; i++) {
+        u32 cb = inst_clause_off[i], ce = inst_clause_off[i + 1];
+        u32 nc = ce - cb;
+        u64 nl = clause_off[ce] - clause_off[cb];
+        if (nc > sh.max_clauses) sh.max_clauses = nc;
+        if (nl > sh.max_lits) sh.max_lits = nl;
+        for (u32 c = cb; c < ce; c++) {
+            u32 len = clause_off[c + 1] - clause_off[c];
+            if (len > sh.max_clause_len) sh.max_clause_len = len;
+        }
+        for (u32 k = clause_off[cb]; k < clause_off[ce]; k++) if ((lits[k] >> 1) + 1 > sh.max_vars) sh.max_vars = (lits[k] >> 1) + 1;
+    }
+    if (tier_nv < 0) tier_nv = pick_tier_nv(sh.max_vars, sh.max_clauses);
+    std::vector<u32> todo(n_inst);
+    for (u32 i = 0; i < n_inst; i++) todo[i] = i;
+    for (u32 attempt = 0; attempt < 4 && !todo.empty(); attempt++) {
+        Layout L = plan_layout(sh, tier_nv, kind, attempt, arena_words, wpool_entries);
+        std::vector<u64> slab((L.slab_bytes + 7) / 8 + 2);
+        std::vector<u64> smem(32 * 1024);
+        u32 queue = 0;
+        Job j;
+        memset(&j.P, 0, sizeof j.P);
+        j.P.inst_clause_off = inst_clause_off; j.P.clause_off = clause_off; j.P.lits = lits;
+        j.P.work = nullptr; j.P.n_work = n_inst; j.P.queue = &queue;
+        j.P.results = results; j.P.models = models; j.P.model_stride = model_stride;
+        j.P.slabs = (u8 *)slab.data(); j.P.L = L; j.P.st = *st; j.P.kind = kind; j.P.flags = flags;
+        j.P.attempt = attempt + 1;
+        j.smem = smem.data(); j.tier_nv = tier_nv;
+        const bool count = (flags & B200SAT_F_COUNT_TRAFFIC) != 0;
+        std::vector<u32> again;
+        for (u32 inst : todo) {
+            j.inst = inst;
+            void (*fn)(void *, int) = nullptr;
+            switch (tier_nv) {
+            case 128: fn = count ? entry_s<128, true> : entry_s<128, false>; break;
+            case 256: fn = count ? entry_s<256, true> : entry_s<256, false>; break;
+            case 512: fn = count ? entry_s<512, true> : entry_s<512, false>; break;
+            case 1024: fn = count ? entry_s<1024, true> : entry_s<1024, false>; break;
+            default: fn = count ? entry_g<true> : entry_g<false>; break;
+            }
+            simt::run_warp(fn, &j, sched_seed ? sched_seed + inst : 0);
+            if (results[inst].status != B200SAT_OK) again.push_back(inst);
+        }
+        todo.swap(again);
+    }
+    return 0;
+}
+}

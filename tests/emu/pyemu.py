@@ -1,0 +1,84 @@
+"""ctypes binding of the TEST-ONLY SIMT emulator harness (tests/emu/libemu.so).
+
+Runs the device solver source on the CPU, one emulated warp per instance.
+Used by the `not gpu` tests to check trace parity of the device algorithm
+against the oracle without a GPU.  Never imported by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libemu.so")
+
+
+class Settings(C.Structure):
+    _fields_ = [
+        ("var_decay", C.c_double), ("clause_decay", C.c_double), ("random_seed", C.c_double),
+        ("random_var_freq", C.c_double), ("restart_first", C.c_double), ("restart_inc", C.c_double),
+        ("size_factor", C.c_double), ("size_inc", C.c_double), ("size_adjust_inc", C.c_double),
+        ("garbage_frac", C.c_double), ("simp_garbage_frac", C.c_double), ("grow", C.c_uint64),
+        ("size_adjust_start_confl", C.c_int32), ("min_learnts_lim", C.c_int32),
+        ("clause_lim", C.c_int32), ("subsumption_lim", C.c_int32), ("ccmin_mode", C.c_int32),
+        ("phase_saving", C.c_int32), ("luby_restart", C.c_uint8), ("rnd_pol", C.c_uint8),
+        ("rnd_init_act", C.c_uint8), ("use_rcheck", C.c_uint8), ("use_asymm", C.c_uint8),
+        ("use_elim", C.c_uint8), ("extend_model", C.c_uint8), ("remove_satisfied", C.c_uint8),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("verdict", C.c_int32), ("status", C.c_int32), ("n_vars", C.c_uint32),
+        ("n_clauses_ingest", C.c_uint32), ("n_clauses_pre", C.c_uint32), ("eliminated_vars", C.c_uint32),
+        ("pre_ok", C.c_uint32), ("attempts", C.c_uint32),
+        ("stats", C.c_uint64 * 8), ("traffic", C.c_uint64 * 8), ("trace_hash", C.c_uint64),
+    ]
+
+
+def build(force=False):
+    subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        u32p = C.POINTER(C.c_uint32)
+        L.emu_solve_batch.argtypes = [u32p, u32p, u32p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Result),
+                                      C.POINTER(C.c_uint8), C.c_uint32]
+        L.emu_solve_batch.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _u32(a):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+def solve_batch(inst_clause_off, clause_off, lits, settings, kind=0, flags=1 | 4 | 8 | 16, tier_nv=-1,
+                arena_words=0, wpool_entries=0, sched_seed=0, model_stride=0):
+    """settings: any ctypes struct with the b200sat_settings layout (e.g. oracle Settings)."""
+    ioff, ioffp = _u32(inst_clause_off)
+    off, offp = _u32(clause_off)
+    li, lip = _u32(lits if len(lits) else np.zeros(1, np.uint32))
+    n = len(ioff) - 1
+    res = (Result * n)()
+    models = None
+    mp = None
+    if model_stride:
+        models = np.full((n, model_stride), 2, dtype=np.uint8)
+        mp = models.ctypes.data_as(C.POINTER(C.c_uint8))
+    rc = lib().emu_solve_batch(ioffp, offp, lip, n, C.addressof(settings), kind, flags, tier_nv,
+                               arena_words, wpool_entries, sched_seed, res, mp, model_stride)
+    if rc != 0:
+        raise RuntimeError("emulator: solver kind not compiled in")
+    return res, models
