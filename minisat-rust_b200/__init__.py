@@ -1,0 +1,372 @@
+"""minisat-rust_b200 -- host-side mirror of minisat-rust's solver interface over the
+B200 CUDA engine (libb200sat.so, C ABI in include/b200sat.h).
+
+Mirrors, with the same names and argument meaning (reference paths relative to
+/root/reference/src):
+  * ``Solver`` trait               sat.rs:28-36       -> class ``Solver`` (``CoreSolver`` / ``SimpSolver``)
+  * ``SolveRes`` / ``Stats``       sat.rs:8-25        -> ``SolveRes``, ``Stats``
+  * ``Lit`` / ``Var`` encoding     sat/formula.rs:63-75,137-154 -> ``mk_lit`` / ``lit_var`` / ``lit_sign``
+  * settings with Default impls    SURVEY.md App. B   -> ``Settings`` / ``default_settings()``
+  * DIMACS reader / result writer  sat/dimacs.rs      -> ``dimacs.parse`` / ``dimacs.write_result``
+plus the batch engine the reference does not have (``Engine``).
+
+All solving happens in the CUDA library.  If the library is missing or no CUDA
+device exists, solving calls raise ``EngineError`` -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200sat.so")
+
+CORE, SIMP = 0, 1
+UNSAT, SAT, INTERRUPTED = 0, 1, 2
+F_PREPROCESS, F_NO_SOLVE, F_ZERO_STATS_ON_PRE_UNSAT, F_TRACE_HASH, F_COUNT_TRAFFIC = 1, 2, 4, 8, 16
+E_NO_DEVICE, E_CUDA, E_ARG, E_SPENT, E_MEM = -1, -2, -3, -4, -5
+STAT_NAMES = ("solves", "restarts", "decisions", "rnd_decisions", "conflicts", "propagations",
+              "tot_literals", "del_literals")
+TRAFFIC_NAMES = ("visited", "kept", "deref", "tail", "moves", "implied", "an_words", "learnt_words")
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("b200sat error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Settings(C.Structure):
+    """b200sat_settings (include/b200sat.h); defaults = the reference's Default impls."""
+    _fields_ = [
+        ("var_decay", C.c_double), ("clause_decay", C.c_double), ("random_seed", C.c_double),
+        ("random_var_freq", C.c_double), ("restart_first", C.c_double), ("restart_inc", C.c_double),
+        ("size_factor", C.c_double), ("size_inc", C.c_double), ("size_adjust_inc", C.c_double),
+        ("garbage_frac", C.c_double), ("simp_garbage_frac", C.c_double), ("grow", C.c_uint64),
+        ("size_adjust_start_confl", C.c_int32), ("min_learnts_lim", C.c_int32),
+        ("clause_lim", C.c_int32), ("subsumption_lim", C.c_int32), ("ccmin_mode", C.c_int32),
+        ("phase_saving", C.c_int32), ("luby_restart", C.c_uint8), ("rnd_pol", C.c_uint8),
+        ("rnd_init_act", C.c_uint8), ("use_rcheck", C.c_uint8), ("use_asymm", C.c_uint8),
+        ("use_elim", C.c_uint8), ("extend_model", C.c_uint8), ("remove_satisfied", C.c_uint8),
+    ]
+
+
+class Budget(C.Structure):
+    _fields_ = [("conflict_budget", C.c_int64), ("propagation_budget", C.c_int64),
+                ("interrupt", C.POINTER(C.c_int))]
+
+
+class StatsStruct(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in STAT_NAMES]
+
+
+class Result(C.Structure):
+    """b200sat_result"""
+    _fields_ = [
+        ("verdict", C.c_int32), ("status", C.c_int32), ("n_vars", C.c_uint32),
+        ("n_clauses_ingest", C.c_uint32), ("n_clauses_pre", C.c_uint32), ("eliminated_vars", C.c_uint32),
+        ("pre_ok", C.c_uint32), ("attempts", C.c_uint32),
+        ("stats", C.c_uint64 * 8), ("traffic", C.c_uint64 * 8), ("trace_hash", C.c_uint64),
+    ]
+
+    def stats_dict(self):
+        return dict(zip(STAT_NAMES, [int(x) for x in self.stats]))
+
+
+RESULT_DTYPE = np.dtype([
+    ("verdict", np.int32), ("status", np.int32), ("n_vars", np.uint32), ("n_clauses_ingest", np.uint32),
+    ("n_clauses_pre", np.uint32), ("eliminated_vars", np.uint32), ("pre_ok", np.uint32), ("attempts", np.uint32),
+    ("stats", np.uint64, (8,)), ("traffic", np.uint64, (8,)), ("trace_hash", np.uint64)])
+assert RESULT_DTYPE.itemsize == C.sizeof(Result)
+
+
+class BatchStruct(C.Structure):
+    _fields_ = [("n_inst", C.c_uint32), ("inst_clause_off", C.POINTER(C.c_uint32)),
+                ("clause_off", C.POINTER(C.c_uint32)), ("lits", C.POINTER(C.c_uint32))]
+
+
+class LaunchInfo(C.Structure):
+    _fields_ = [("grid", C.c_uint32), ("block", C.c_uint32), ("smem_bytes", C.c_uint32),
+                ("warps_total", C.c_uint32), ("tier", C.c_uint32), ("launches", C.c_uint32),
+                ("slab_bytes", C.c_uint64), ("last_kernel_ms", C.c_float)]
+
+
+def traffic_bytes(t):
+    """algorithmic bytes from the eight traffic counters."""
+    visited, kept, deref, tail, moves, implied, an_words, learnt_words = [int(x) for x in t]
+    return (8 * visited + 8 * kept + 4 * deref + 4 * (2 * deref + tail) + 16 * moves + 12 * implied
+            + 4 * an_words + 4 * learnt_words)
+
+
+# every symbol include/b200sat.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = (
+    "b200sat_default_settings", "b200sat_last_error", "b200sat_device_count",
+    "b200sat_new", "b200sat_free", "b200sat_n_vars", "b200sat_n_clauses", "b200sat_new_var",
+    "b200sat_add_clause", "b200sat_preprocess", "b200sat_solve_limited", "b200sat_get_stats",
+    "b200sat_engine_create", "b200sat_engine_destroy", "b200sat_engine_upload",
+    "b200sat_engine_generate_ksat", "b200sat_engine_solve", "b200sat_engine_download",
+    "b200sat_engine_batch_dims", "b200sat_engine_download_batch", "b200sat_engine_configure",
+    "b200sat_engine_launch_info", "b200sat_solve_batch",
+)
+
+_lib = None
+
+
+def lib():
+    """Load libb200sat.so (the CUDA product library).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(E_NO_DEVICE, "CUDA library %s is not built (run __graft_entry__.build()); "
+                                       "there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    u32p, u8p, vp = C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.c_void_p
+    L.b200sat_default_settings.argtypes = [C.POINTER(Settings)]
+    L.b200sat_last_error.restype = C.c_char_p
+    L.b200sat_device_count.restype = C.c_int
+    L.b200sat_new.argtypes = [C.POINTER(Settings), C.c_int]
+    L.b200sat_new.restype = vp
+    L.b200sat_free.argtypes = [vp]
+    L.b200sat_n_vars.argtypes = [vp]
+    L.b200sat_n_vars.restype = C.c_size_t
+    L.b200sat_n_clauses.argtypes = [vp]
+    L.b200sat_n_clauses.restype = C.c_size_t
+    L.b200sat_new_var.argtypes = [vp, C.c_int, C.c_int]
+    L.b200sat_new_var.restype = C.c_uint32
+    L.b200sat_add_clause.argtypes = [vp, u32p, C.c_size_t]
+    L.b200sat_add_clause.restype = C.c_int
+    L.b200sat_preprocess.argtypes = [vp, C.POINTER(Budget)]
+    L.b200sat_preprocess.restype = C.c_int
+    L.b200sat_solve_limited.argtypes = [vp, C.POINTER(Budget), u32p, C.c_size_t, u8p, C.c_size_t]
+    L.b200sat_solve_limited.restype = C.c_int
+    L.b200sat_get_stats.argtypes = [vp, C.POINTER(StatsStruct)]
+    L.b200sat_engine_create.argtypes = [C.c_int]
+    L.b200sat_engine_create.restype = vp
+    L.b200sat_engine_destroy.argtypes = [vp]
+    L.b200sat_engine_upload.argtypes = [vp, C.POINTER(BatchStruct), vp]
+    L.b200sat_engine_generate_ksat.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+    L.b200sat_engine_solve.argtypes = [vp, C.POINTER(Settings), C.c_int, C.c_int, vp]
+    L.b200sat_engine_download.argtypes = [vp, vp, u8p, C.c_uint32, vp]
+    L.b200sat_engine_batch_dims.argtypes = [vp, u32p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.b200sat_engine_download_batch.argtypes = [vp, u32p, u32p, u32p]
+    L.b200sat_engine_configure.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
+    L.b200sat_engine_launch_info.argtypes = [vp, C.POINTER(LaunchInfo)]
+    L.b200sat_solve_batch.argtypes = [vp, C.POINTER(BatchStruct), C.POINTER(Settings), C.c_int, C.c_int,
+                                      vp, u8p, C.c_uint32]
+    _lib = L
+    return L
+
+
+def _check(rc, allow=()):
+    if rc < 0 and rc not in allow:
+        raise EngineError(rc, lib().b200sat_last_error().decode())
+    return rc
+
+
+def default_settings():
+    s = Settings()
+    lib().b200sat_default_settings(C.byref(s))
+    return s
+
+
+# ---- Lit / Var algebra, sat/formula.rs:63-75,137-154
+def mk_lit(var, sign):
+    return (var << 1) | (1 if sign else 0)
+
+
+def lit_var(lit):
+    return lit >> 1
+
+
+def lit_sign(lit):
+    return (lit & 1) != 0
+
+
+def lit_not(lit):
+    return lit ^ 1
+
+
+class Stats(dict):
+    """sat.rs:8-18"""
+    def __getattr__(self, k):
+        return self[k]
+
+
+class SolveRes:
+    """sat.rs:21-25: UnSAT(stats) | SAT(model, stats) | Interrupted(progress, solver)"""
+    def __init__(self, kind, stats, model=None):
+        self.kind, self.stats, self.model = kind, stats, model
+
+    def is_sat(self):
+        return self.kind == SAT
+
+    def is_unsat(self):
+        return self.kind == UNSAT
+
+
+def _u32(a):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+class Solver:
+    """`trait Solver` (sat.rs:28-36) over one C-ABI handle.  Use CoreSolver / SimpSolver."""
+    KIND = CORE
+
+    def __init__(self, settings=None):
+        self.settings = settings if settings is not None else default_settings()
+        self._h = lib().b200sat_new(C.byref(self.settings), self.KIND)
+        if not self._h:
+            raise EngineError(E_ARG, lib().b200sat_last_error().decode())
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.b200sat_free(h)
+
+    def n_vars(self):
+        return lib().b200sat_n_vars(self._h)
+
+    def n_clauses(self):
+        return lib().b200sat_n_clauses(self._h)
+
+    def new_var(self, upol=None, dvar=True):
+        return lib().b200sat_new_var(self._h, -1 if upol is None else int(bool(upol)), int(dvar))
+
+    def add_clause(self, clause):
+        a, p = _u32(list(clause) if len(clause) else [0])
+        return bool(lib().b200sat_add_clause(self._h, p, len(clause)))
+
+    def preprocess(self, budget=None):
+        return bool(_check(lib().b200sat_preprocess(self._h, None)))
+
+    def solve_limited(self, budget=None, assumptions=()):
+        n = self.n_vars()
+        model = np.full(max(n, 1), 2, dtype=np.uint8)
+        a, ap = _u32(list(assumptions) if len(assumptions) else [0])
+        rc = _check(lib().b200sat_solve_limited(self._h, None, ap, len(assumptions),
+                                                model.ctypes.data_as(C.POINTER(C.c_uint8)), n))
+        st = self.stats()
+        if rc == SAT:
+            # model as Vec<Lit> in var order (minisat.rs:68,235-239)
+            lits = [mk_lit(v, model[v] == 0) for v in range(n) if model[v] != 2]
+            return SolveRes(SAT, st, lits)
+        return SolveRes(rc, st)
+
+    def stats(self):
+        s = StatsStruct()
+        lib().b200sat_get_stats(self._h, C.byref(s))
+        return Stats((k, int(getattr(s, k))) for k in STAT_NAMES)
+
+
+class CoreSolver(Solver):
+    """sat/minisat.rs:26-103"""
+    KIND = CORE
+
+
+class SimpSolver(Solver):
+    """sat/minisat.rs:123-279"""
+    KIND = SIMP
+
+
+class Engine:
+    """The batch engine (no reference analogue): many independent solvers advanced by one
+    persistent warp-per-instance kernel on one GPU."""
+
+    def __init__(self, device=0):
+        self._e = lib().b200sat_engine_create(device)
+        if not self._e:
+            raise EngineError(E_NO_DEVICE, lib().b200sat_last_error().decode())
+        self.device = device
+        self._keep = None
+
+    def close(self):
+        e, self._e = self._e, None
+        if e and _lib is not None:
+            _lib.b200sat_engine_destroy(e)
+
+    def __del__(self):
+        self.close()
+
+    def configure(self, warps_per_block=0, blocks_per_sm=0, arena_words=0, wpool_entries=0):
+        _check(lib().b200sat_engine_configure(self._e, warps_per_block, blocks_per_sm, arena_words, wpool_entries))
+
+    @staticmethod
+    def _batch(inst_clause_off, clause_off, lits):
+        ioff, ioffp = _u32(inst_clause_off)
+        off, offp = _u32(clause_off)
+        li, lip = _u32(lits if len(lits) else np.zeros(1, np.uint32))
+        b = BatchStruct(len(ioff) - 1, ioffp, offp, lip)
+        return b, (ioff, off, li)
+
+    def upload(self, inst_clause_off, clause_off, lits, stream=None):
+        b, keep = self._batch(inst_clause_off, clause_off, lits)
+        _check(lib().b200sat_engine_upload(self._e, C.byref(b), stream))
+
+    def generate_ksat(self, seed_base, n_inst, n_vars, n_clauses, k=3, stream=None):
+        _check(lib().b200sat_engine_generate_ksat(self._e, seed_base & 0xFFFFFFFFFFFFFFFF, n_inst, n_vars,
+                                                  n_clauses, k, stream))
+
+    def solve(self, settings=None, kind=CORE, flags=F_PREPROCESS | F_ZERO_STATS_ON_PRE_UNSAT, stream=None):
+        s = settings if settings is not None else default_settings()
+        return _check(lib().b200sat_engine_solve(self._e, C.byref(s), kind, flags, stream), allow=(E_MEM,))
+
+    def dims(self):
+        n, nc, nl = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        _check(lib().b200sat_engine_batch_dims(self._e, C.byref(n), C.byref(nc), C.byref(nl)))
+        return n.value, nc.value, nl.value
+
+    def download(self, want_models=True, model_stride=None, stream=None):
+        n, _, _ = self.dims()
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        models = None
+        mp = None
+        if want_models:
+            if model_stride is None:
+                raise ValueError("model_stride required")
+            models = np.full((n, model_stride), 2, dtype=np.uint8)
+            mp = models.ctypes.data_as(C.POINTER(C.c_uint8))
+        _check(lib().b200sat_engine_download(self._e, res.ctypes.data, mp, model_stride or 0, stream))
+        return res, models
+
+    def download_batch(self):
+        n, nc, nl = self.dims()
+        ioff = np.zeros(n + 1, np.uint32)
+        coff = np.zeros(nc + 1, np.uint32)
+        lits = np.zeros(max(nl, 1), np.uint32)
+        u32p = C.POINTER(C.c_uint32)
+        _check(lib().b200sat_engine_download_batch(self._e, ioff.ctypes.data_as(u32p), coff.ctypes.data_as(u32p),
+                                                   lits.ctypes.data_as(u32p)))
+        return ioff, coff, lits[:nl]
+
+    def launch_info(self):
+        li = LaunchInfo()
+        _check(lib().b200sat_engine_launch_info(self._e, C.byref(li)))
+        return {k: getattr(li, k) for k, _ in LaunchInfo._fields_}
+
+    def solve_batch(self, inst_clause_off, clause_off, lits, settings=None, kind=CORE,
+                    flags=F_PREPROCESS | F_ZERO_STATS_ON_PRE_UNSAT, model_stride=0):
+        """upload + solve + download with HOST buffers (b200sat_solve_batch)."""
+        s = settings if settings is not None else default_settings()
+        b, keep = self._batch(inst_clause_off, clause_off, lits)
+        n = b.n_inst
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        models = None
+        mp = None
+        if model_stride:
+            models = np.full((n, model_stride), 2, dtype=np.uint8)
+            mp = models.ctypes.data_as(C.POINTER(C.c_uint8))
+        _check(lib().b200sat_solve_batch(self._e, C.byref(b), C.byref(s), kind, flags, res.ctypes.data, mp,
+                                         model_stride), allow=(E_MEM,))
+        return res, models
+
+
+def shard_range(n_items, rank, world_size):
+    """Contiguous, near-equal index range of `rank` (SURVEY.md 8e batch mode: no data-path collective)."""
+    base, rem = divmod(n_items, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+from . import dimacs  # noqa: E402,F401

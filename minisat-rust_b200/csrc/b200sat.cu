@@ -1,0 +1,561 @@
+/*
+ * b200sat.cu -- kernels + C-ABI host of the B200-native batched CDCL engine.
+ *
+ * Kernels (sm_100a):
+ *   cdcl_warp_smem<NV,COUNT>  persistent, one warp = one instance, var state in shared memory
+ *   cdcl_warp_glob<COUNT>     same solver, var state in the HBM slab (large instances)
+ *   gen_random_ksat           synthetic uniform k-SAT batch (SURVEY.md 8d generator)
+ *   collect_failed            builds the retry work list of instances that outgrew their slab
+ *
+ * The host side mirrors `trait Solver` (reference src/sat.rs:28-36) and adds
+ * the batch engine.  There is no CPU solving path in this file: without a CUDA
+ * device every solving call returns B200SAT_E_NO_DEVICE.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "cdcl_plan.h"
+#include "cdcl_warp.cuh"
+#ifdef B200SAT_HAVE_SIMP
+#include "simp_warp.cuh"
+#endif
+
+using namespace b200sat;
+
+/* ------------------------------------------------------------------ kernels */
+template <class VT, bool COUNT> __device__ __forceinline__ void warp_work_loop(WarpSolver<VT, COUNT> &S, const KParams &P) {
+    for (;;) {
+        u32 w = 0;
+        if (S.lane == 0) w = atomicAdd(P.queue, 1u);
+        w = __shfl_sync(FULL_MASK, w, 0);
+        if (w >= P.n_work) break;
+        u32 inst = P.work ? P.work[w] : w;
+#ifdef B200SAT_HAVE_SIMP
+        if (P.kind == B200SAT_SIMP) { solve_simp(S, inst); continue; }
+#endif
+        S.solve_core(inst);
+    }
+}
+
+template <int NV, bool COUNT> __global__ void cdcl_warp_smem(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 wpb = blockDim.x >> 5;
+    WarpSolver<VarsS<NV>, COUNT> S(P, lane);
+    S.V.s = reinterpret_cast<SmemVars<NV> *>(smem_raw) + warp;
+    S.slab = P.slabs + (size_t)(blockIdx.x * wpb + warp) * P.L.slab_bytes;
+    warp_work_loop(S, P);
+}
+
+template <bool COUNT> __global__ void cdcl_warp_glob(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 wpb = blockDim.x >> 5;
+    WarpSolver<VarsG, COUNT> S(P, lane);
+    S.V.s = reinterpret_cast<SmemSmall *>(smem_raw) + warp;
+    S.slab = P.slabs + (size_t)(blockIdx.x * wpb + warp) * P.L.slab_bytes;
+    S.V.bind(S.slab + P.L.off_vars, P.L.nv_cap);
+    warp_work_loop(S, P);
+}
+
+/* SplitMix64 generator of SURVEY.md 8d: bit-identical to the host generator the CPU baseline uses */
+__global__ void gen_random_ksat(u64 seed_base, u32 n_inst, u32 n, u32 m, u32 k, u32 *inst_clause_off,
+                                u32 *clause_off, u32 *lits) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_inst) return;
+    inst_clause_off[i] = i * m;
+    if (i == n_inst) { clause_off[(size_t)n_inst * m] = n_inst * m * k; return; }
+    u64 state = seed_base + i;
+    for (u32 c = 0; c < m; c++) {
+        size_t cbase = ((size_t)i * m + c);
+        clause_off[cbase] = (u32)(cbase * k);
+        u32 *cl = lits + cbase * k;
+        for (u32 j = 0; j < k;) {
+            state += 0x9E3779B97F4A7C15ull;
+            u64 z = state;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            u64 r = z ^ (z >> 31);
+            u32 v = (u32)(((r >> 32) * (u64)n) >> 32);
+            bool dup = false;
+            for (u32 t = 0; t < j; t++) if ((cl[t] >> 1) == v) dup = true;
+            if (dup) continue;
+            cl[j++] = (v << 1) | (u32)(r & 1);
+        }
+    }
+}
+
+__global__ void collect_failed(const b200sat_result *results, const u32 *work, u32 n_work, u32 *out_list, u32 *out_count) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_work) return;
+    u32 inst = work ? work[i] : i;
+    if (results[inst].status != B200SAT_OK) out_list[atomicAdd(out_count, 1u)] = inst;
+}
+
+/* ------------------------------------------------------------------ host: errors */
+static thread_local std::string g_err;
+static int set_err(int code, const std::string &m) { g_err = m; return code; }
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return set_err(B200SAT_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+extern "C" const char *b200sat_last_error(void) { return g_err.c_str(); }
+
+extern "C" void b200sat_default_settings(b200sat_settings *s) { /* SURVEY.md Appendix B */
+    memset(s, 0, sizeof *s);
+    s->var_decay = 0.95; s->clause_decay = 0.999; s->random_seed = 91648253.0; s->random_var_freq = 0.0;
+    s->restart_first = 100.0; s->restart_inc = 2.0; s->size_factor = 1.0 / 3.0; s->size_inc = 1.1;
+    s->size_adjust_inc = 1.5; s->garbage_frac = 0.20; s->simp_garbage_frac = 0.5; s->grow = 0;
+    s->size_adjust_start_confl = 100; s->min_learnts_lim = 0; s->clause_lim = 20; s->subsumption_lim = 1000;
+    s->ccmin_mode = 2; s->phase_saving = 2; s->luby_restart = 1; s->rnd_pol = 0; s->rnd_init_act = 0;
+    s->use_rcheck = 0; s->use_asymm = 0; s->use_elim = 1; s->extend_model = 1; s->remove_satisfied = 1;
+}
+
+extern "C" int b200sat_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return set_err(B200SAT_E_NO_DEVICE, "no CUDA device: the engine has no CPU path"); }
+    return n;
+}
+
+/* ------------------------------------------------------------------ host: engine */
+struct b200sat_engine {
+    int device = 0;
+    int num_sms = 0;
+    size_t smem_optin = 0;
+    /* resident batch */
+    u32 n_inst = 0;
+    u64 n_clauses = 0, n_lits = 0;
+    u32 *d_ioff = nullptr, *d_coff = nullptr, *d_lits = nullptr;
+    size_t cap_ioff = 0, cap_coff = 0, cap_lits = 0;
+    BatchShape shape = {0, 0, 0, 0};
+    /* outputs */
+    b200sat_result *d_results = nullptr;
+    size_t cap_results = 0;
+    u8 *d_models = nullptr;
+    size_t cap_models = 0;
+    u32 model_stride = 0;
+    /* work */
+    u8 *d_slabs = nullptr;
+    size_t cap_slabs = 0;
+    u32 *d_queue = nullptr;      /* [0] queue counter, [1] failed counter */
+    u32 *d_work[2] = {nullptr, nullptr};
+    size_t cap_work = 0;
+    u32 *h_pinned = nullptr;     /* small pinned staging for counters */
+    void *h_stage = nullptr;     /* pinned staging for uploads */
+    size_t cap_stage = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    /* tunables */
+    int cfg_wpb = 0, cfg_bps = 0;
+    u64 cfg_arena = 0, cfg_wpool = 0;
+    b200sat_launch_info info;
+};
+
+template <class T> static int ensure(T *&p, size_t &cap, size_t need_elems) {
+    if (need_elems <= cap && p) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t n = need_elems + need_elems / 8 + 64;
+    cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
+    if (e != cudaSuccess) return set_err(B200SAT_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    cap = n;
+    return 0;
+}
+
+extern "C" b200sat_engine *b200sat_engine_create(int device) {
+    if (b200sat_device_count() <= 0) return nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) { set_err(B200SAT_E_CUDA, "cudaSetDevice failed"); return nullptr; }
+    b200sat_engine *e = new b200sat_engine();
+    e->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete e; set_err(B200SAT_E_CUDA, "cudaGetDeviceProperties failed"); return nullptr; }
+    e->num_sms = prop.multiProcessorCount;
+    e->smem_optin = prop.sharedMemPerBlockOptin;
+    memset(&e->info, 0, sizeof e->info);
+    if (cudaMalloc((void **)&e->d_queue, 64) != cudaSuccess || cudaMallocHost((void **)&e->h_pinned, 64) != cudaSuccess ||
+        cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
+        set_err(B200SAT_E_CUDA, "engine allocation failed");
+        delete e;
+        return nullptr;
+    }
+    return e;
+}
+
+extern "C" void b200sat_engine_destroy(b200sat_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaFree(e->d_ioff); cudaFree(e->d_coff); cudaFree(e->d_lits); cudaFree(e->d_results); cudaFree(e->d_models);
+    cudaFree(e->d_slabs); cudaFree(e->d_queue); cudaFree(e->d_work[0]); cudaFree(e->d_work[1]);
+    if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    delete e;
+}
+
+extern "C" int b200sat_engine_configure(b200sat_engine *e, int warps_per_block, int blocks_per_sm, uint64_t arena_words,
+                                        uint64_t wpool_entries) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    e->cfg_wpb = warps_per_block; e->cfg_bps = blocks_per_sm; e->cfg_arena = arena_words; e->cfg_wpool = wpool_entries;
+    return 0;
+}
+
+static int alloc_outputs(b200sat_engine *e) {
+    int rc;
+    if ((rc = ensure(e->d_results, e->cap_results, (size_t)e->n_inst))) return rc;
+    e->model_stride = e->shape.max_vars ? e->shape.max_vars : 1;
+    if ((rc = ensure(e->d_models, e->cap_models, (size_t)e->n_inst * e->model_stride))) return rc;
+    if ((rc = ensure(e->d_work[0], e->cap_work, (size_t)e->n_inst))) return rc;
+    size_t dummy = 0;
+    if (e->d_work[1]) { cudaFree(e->d_work[1]); e->d_work[1] = nullptr; }
+    if ((rc = ensure(e->d_work[1], dummy, e->cap_work))) return rc;
+    return 0;
+}
+
+extern "C" int b200sat_engine_upload(b200sat_engine *e, const b200sat_batch *b, void *stream_) {
+    if (!e || !b) return set_err(B200SAT_E_ARG, "null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(cudaSetDevice(e->device));
+    const u32 n = b->n_inst;
+    const u64 nc = n ? b->inst_clause_off[n] : 0;
+    const u64 nl = nc ? b->clause_off[nc] : 0;
+    BatchShape sh = {0, 0, 0, 0};
+    for (u32 i = 0; i < n; i++) {
+        u32 cb = b->inst_clause_off[i], ce = b->inst_clause_off[i + 1];
+        if (ce < cb) return set_err(B200SAT_E_ARG, "inst_clause_off not monotone");
+        sh.max_clauses = std::max(sh.max_clauses, ce - cb);
+        sh.max_lits = std::max<u64>(sh.max_lits, b->clause_off[ce] - b->clause_off[cb]);
+    }
+    for (u64 c = 0; c < nc; c++) {
+        if (b->clause_off[c + 1] < b->clause_off[c]) return set_err(B200SAT_E_ARG, "clause_off not monotone");
+        sh.max_clause_len = std::max(sh.max_clause_len, b->clause_off[c + 1] - b->clause_off[c]);
+    }
+    u32 mx = 0;
+    for (u64 k = 0; k < nl; k++) mx = std::max(mx, b->lits[k] >> 1);
+    sh.max_vars = nl ? mx + 1 : 0;
+    int rc;
+    if ((rc = ensure(e->d_ioff, e->cap_ioff, (size_t)n + 1))) return rc;
+    if ((rc = ensure(e->d_coff, e->cap_coff, (size_t)nc + 1))) return rc;
+    if ((rc = ensure(e->d_lits, e->cap_lits, (size_t)nl + 1))) return rc;
+    /* stage through pinned memory so the copies are true async DMA */
+    size_t bytes = ((size_t)n + 1 + nc + 1 + nl) * 4;
+    if (bytes > e->cap_stage) {
+        if (e->h_stage) cudaFreeHost(e->h_stage);
+        e->h_stage = nullptr; e->cap_stage = 0;
+        CK(cudaMallocHost(&e->h_stage, bytes + bytes / 8));
+        e->cap_stage = bytes + bytes / 8;
+    }
+    u32 *hs = (u32 *)e->h_stage;
+    memcpy(hs, b->inst_clause_off, ((size_t)n + 1) * 4);
+    if (n) {
+        memcpy(hs + n + 1, b->clause_off, ((size_t)nc + 1) * 4);
+        if (nl) memcpy(hs + n + 1 + nc + 1, b->lits, (size_t)nl * 4);
+    } else hs[1] = 0;
+    CK(cudaMemcpyAsync(e->d_ioff, hs, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(e->d_coff, hs + n + 1, ((size_t)nc + 1) * 4, cudaMemcpyHostToDevice, stream));
+    if (nl) CK(cudaMemcpyAsync(e->d_lits, hs + n + 1 + nc + 1, (size_t)nl * 4, cudaMemcpyHostToDevice, stream));
+    e->n_inst = n; e->n_clauses = nc; e->n_lits = nl; e->shape = sh;
+    return alloc_outputs(e);
+}
+
+extern "C" int b200sat_engine_generate_ksat(b200sat_engine *e, uint64_t seed_base, uint32_t n_inst, uint32_t n_vars,
+                                            uint32_t n_clauses, uint32_t k, void *stream_) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    if (k == 0 || k > n_vars) return set_err(B200SAT_E_ARG, "k must be in 1..n_vars");
+    if ((u64)n_inst * n_clauses * k > 0xFFFFFFF0ull) return set_err(B200SAT_E_ARG, "batch exceeds 2^32 literals");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(cudaSetDevice(e->device));
+    const u64 nc = (u64)n_inst * n_clauses, nl = nc * k;
+    int rc;
+    if ((rc = ensure(e->d_ioff, e->cap_ioff, (size_t)n_inst + 1))) return rc;
+    if ((rc = ensure(e->d_coff, e->cap_coff, (size_t)nc + 1))) return rc;
+    if ((rc = ensure(e->d_lits, e->cap_lits, (size_t)nl + 1))) return rc;
+    gen_random_ksat<<<(n_inst + 1 + 127) / 128, 128, 0, stream>>>(seed_base, n_inst, n_vars, n_clauses, k, e->d_ioff, e->d_coff, e->d_lits);
+    CK(cudaGetLastError());
+    e->n_inst = n_inst; e->n_clauses = nc; e->n_lits = nl;
+    e->shape.max_vars = n_vars; e->shape.max_clauses = n_clauses; e->shape.max_lits = (u64)n_clauses * k; e->shape.max_clause_len = k;
+    return alloc_outputs(e);
+}
+
+typedef void (*kernel_fn)(const KParams);
+
+static kernel_fn pick_kernel(int tier_nv, bool count, size_t &smem_per_warp) {
+    switch (tier_nv) {
+    case 128: smem_per_warp = sizeof(SmemVars<128>); return count ? cdcl_warp_smem<128, true> : cdcl_warp_smem<128, false>;
+    case 256: smem_per_warp = sizeof(SmemVars<256>); return count ? cdcl_warp_smem<256, true> : cdcl_warp_smem<256, false>;
+    case 512: smem_per_warp = sizeof(SmemVars<512>); return count ? cdcl_warp_smem<512, true> : cdcl_warp_smem<512, false>;
+    case 1024: smem_per_warp = sizeof(SmemVars<1024>); return count ? cdcl_warp_smem<1024, true> : cdcl_warp_smem<1024, false>;
+    default: smem_per_warp = sizeof(SmemSmall); return count ? cdcl_warp_glob<true> : cdcl_warp_glob<false>;
+    }
+}
+
+static int check_settings(const b200sat_settings *s, int kind) {
+    if (!s) return set_err(B200SAT_E_ARG, "null settings");
+    if (s->use_rcheck) return set_err(B200SAT_E_ARG, "use_rcheck is not supported (SURVEY.md 8f-4)");
+    if (s->use_asymm) return set_err(B200SAT_E_ARG, "use_asymm is not supported (SURVEY.md 8f-4)");
+    if (!(s->var_decay > 0 && s->clause_decay > 0)) return set_err(B200SAT_E_ARG, "decay must be > 0");
+    if (kind != B200SAT_CORE && kind != B200SAT_SIMP) return set_err(B200SAT_E_ARG, "kind must be CORE or SIMP");
+#ifndef B200SAT_HAVE_SIMP
+    if (kind == B200SAT_SIMP) return set_err(B200SAT_E_ARG, "SimpSolver path not built into this library");
+#endif
+    return 0;
+}
+
+extern "C" int b200sat_engine_solve(b200sat_engine *e, const b200sat_settings *s, int kind, int flags, void *stream_) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    int rc = check_settings(s, kind);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(cudaSetDevice(e->device));
+    e->info.launches = 0;
+    e->info.last_kernel_ms = 0.f;
+    if (e->n_inst == 0) return 0;
+    const bool count = (flags & B200SAT_F_COUNT_TRAFFIC) != 0;
+    int tier_nv = pick_tier_nv(e->shape.max_vars, e->shape.max_clauses);
+    u32 n_work = e->n_inst;
+    const u32 *work = nullptr;
+    float total_ms = 0.f;
+    for (u32 attempt = 0; attempt < 5 && n_work > 0; attempt++) {
+        if (attempt == 3) tier_nv = 0; /* last resort: var state in HBM too, biggest slabs */
+        Layout L = plan_layout(e->shape, tier_nv, kind, attempt, e->cfg_arena, e->cfg_wpool);
+        size_t spw = 0;
+        kernel_fn fn = pick_kernel(tier_nv, count, spw);
+        /* launch shape: as many resident warps per SM as shared memory and registers allow */
+        int best_wpb = 1, best_bps = 1, best_warps = 0;
+        const int cand[] = {1, 2, 4, 8};
+        for (int ci = 0; ci < 4; ci++) {
+            int wpb = e->cfg_wpb > 0 ? e->cfg_wpb : cand[ci];
+            size_t smem = spw * wpb;
+            if (smem > e->smem_optin) { if (e->cfg_wpb > 0) return set_err(B200SAT_E_ARG, "warps_per_block needs too much shared memory"); continue; }
+            CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int bps = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void *)fn, wpb * 32, smem));
+            if (e->cfg_bps > 0 && bps > e->cfg_bps) bps = e->cfg_bps;
+            if (bps * wpb > best_warps) { best_warps = bps * wpb; best_wpb = wpb; best_bps = bps; }
+            if (e->cfg_wpb > 0) break;
+        }
+        if (best_warps == 0) return set_err(B200SAT_E_CUDA, "kernel does not fit on the device");
+        u32 grid = (u32)(e->num_sms * best_bps);
+        u32 need_blocks = (n_work + best_wpb - 1) / best_wpb;
+        if (grid > need_blocks) grid = need_blocks;
+        /* bound the slab memory: at most ~60% of free HBM */
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = (size_t)((double)(free_b + e->cap_slabs) * 0.6);
+        u64 warps_total = (u64)grid * best_wpb;
+        if (warps_total * L.slab_bytes > budget) {
+            u64 fit = budget / L.slab_bytes;
+            if (fit < (u64)best_wpb) {
+                if (attempt == 0 || true) { /* cannot give even one block its slabs */
+                    if (fit == 0) return set_err(B200SAT_E_MEM, "an instance needs a slab larger than the free device memory");
+                    best_wpb = 1;
+                }
+            }
+            grid = (u32)std::max<u64>(1, fit / best_wpb);
+            warps_total = (u64)grid * best_wpb;
+        }
+        size_t smem = spw * best_wpb;
+        CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if ((rc = ensure(e->d_slabs, e->cap_slabs, (size_t)(warps_total * L.slab_bytes)))) return rc;
+        CK(cudaMemsetAsync(e->d_queue, 0, 8, stream));
+        KParams P;
+        memset(&P, 0, sizeof P);
+        P.inst_clause_off = e->d_ioff; P.clause_off = e->d_coff; P.lits = e->d_lits;
+        P.work = work; P.n_work = n_work; P.queue = e->d_queue;
+        P.results = e->d_results; P.models = e->d_models; P.model_stride = e->model_stride;
+        P.slabs = e->d_slabs; P.L = L; P.st = *s; P.kind = kind; P.flags = flags; P.attempt = attempt + 1;
+        CK(cudaEventRecord(e->ev0, stream));
+        fn<<<grid, best_wpb * 32, smem, stream>>>(P);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e->ev1, stream));
+        u32 *next_list = e->d_work[attempt & 1];
+        collect_failed<<<(n_work + 255) / 256, 256, 0, stream>>>(e->d_results, work, n_work, next_list, e->d_queue + 1);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(e->h_pinned, e->d_queue + 1, 4, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        total_ms += ms;
+        e->info.grid = grid; e->info.block = best_wpb * 32; e->info.smem_bytes = (u32)smem;
+        e->info.warps_total = (u32)warps_total; e->info.tier = L.tier; e->info.slab_bytes = L.slab_bytes;
+        e->info.launches += 1;
+        n_work = e->h_pinned[0];
+        work = next_list;
+    }
+    e->info.last_kernel_ms = total_ms;
+    if (n_work > 0) return set_err(B200SAT_E_MEM, "instances outgrew the largest slab (status in results)");
+    return 0;
+}
+
+extern "C" int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out) {
+    if (!e || !out) return set_err(B200SAT_E_ARG, "null argument");
+    *out = e->info;
+    return 0;
+}
+
+extern "C" int b200sat_engine_download(b200sat_engine *e, b200sat_result *results, uint8_t *models, uint32_t model_stride,
+                                       void *stream_) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(cudaSetDevice(e->device));
+    if (e->n_inst == 0) return 0;
+    if (results) CK(cudaMemcpyAsync(results, e->d_results, (size_t)e->n_inst * sizeof(b200sat_result), cudaMemcpyDeviceToHost, stream));
+    if (models) {
+        if (model_stride == e->model_stride)
+            CK(cudaMemcpyAsync(models, e->d_models, (size_t)e->n_inst * model_stride, cudaMemcpyDeviceToHost, stream));
+        else
+            CK(cudaMemcpy2DAsync(models, model_stride, e->d_models, e->model_stride, std::min(model_stride, e->model_stride),
+                                 e->n_inst, cudaMemcpyDeviceToHost, stream));
+    }
+    CK(cudaStreamSynchronize(stream));
+    if (models && model_stride > e->model_stride)
+        for (u32 i = 0; i < e->n_inst; i++) memset(models + (size_t)i * model_stride + e->model_stride, 2, model_stride - e->model_stride);
+    return 0;
+}
+
+extern "C" int b200sat_engine_batch_dims(b200sat_engine *e, uint32_t *n_inst, uint64_t *n_clauses, uint64_t *n_lits) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    if (n_inst) *n_inst = e->n_inst;
+    if (n_clauses) *n_clauses = e->n_clauses;
+    if (n_lits) *n_lits = e->n_lits;
+    return 0;
+}
+
+extern "C" int b200sat_engine_download_batch(b200sat_engine *e, uint32_t *ioff, uint32_t *coff, uint32_t *lits) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    CK(cudaSetDevice(e->device));
+    CK(cudaDeviceSynchronize());
+    if (ioff) CK(cudaMemcpy(ioff, e->d_ioff, ((size_t)e->n_inst + 1) * 4, cudaMemcpyDeviceToHost));
+    if (coff) CK(cudaMemcpy(coff, e->d_coff, ((size_t)e->n_clauses + 1) * 4, cudaMemcpyDeviceToHost));
+    if (lits && e->n_lits) CK(cudaMemcpy(lits, e->d_lits, (size_t)e->n_lits * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int b200sat_solve_batch(b200sat_engine *e, const b200sat_batch *batch, const b200sat_settings *s, int kind, int flags,
+                                   b200sat_result *results, uint8_t *models, uint32_t model_stride) {
+    int rc = b200sat_engine_upload(e, batch, nullptr);
+    if (rc) return rc;
+    int src = b200sat_engine_solve(e, s, kind, flags, nullptr);
+    if (src && src != B200SAT_E_MEM) return src;
+    rc = b200sat_engine_download(e, results, models, model_stride, nullptr);
+    return rc ? rc : src;
+}
+
+/* ------------------------------------------------------------------ host: single-solver mirror of `trait Solver` */
+struct b200sat_solver {
+    b200sat_settings st;
+    int kind;
+    bool ok = true, spent = false, preprocessed = false;
+    u32 n_vars = 0;
+    std::vector<u8> upol;      /* 0 none, 2 false, 3 true */
+    std::vector<u8> dvar;
+    std::vector<u32> clause_off{0};
+    std::vector<u32> lits;
+    size_t n_clauses_known = 0;
+    b200sat_stats stats;
+    b200sat_engine *eng = nullptr;
+};
+
+extern "C" b200sat_solver *b200sat_new(const b200sat_settings *s, int kind) {
+    if (check_settings(s, kind)) return nullptr;
+    b200sat_solver *h = new b200sat_solver();
+    h->st = *s;
+    h->kind = kind;
+    memset(&h->stats, 0, sizeof h->stats);
+    return h;
+}
+extern "C" void b200sat_free(b200sat_solver *h) {
+    if (!h) return;
+    if (h->eng) b200sat_engine_destroy(h->eng);
+    delete h;
+}
+extern "C" size_t b200sat_n_vars(const b200sat_solver *h) { return h ? h->n_vars : 0; }
+extern "C" size_t b200sat_n_clauses(const b200sat_solver *h) { return h ? h->n_clauses_known : 0; }
+extern "C" uint32_t b200sat_new_var(b200sat_solver *h, int upol, int dvar) {
+    if (!h) return 0xFFFFFFFFu;
+    h->upol.push_back(upol < 0 ? 0 : (upol ? 3 : 2));
+    h->dvar.push_back(dvar ? 1 : 0);
+    return h->n_vars++;
+}
+extern "C" int b200sat_add_clause(b200sat_solver *h, const uint32_t *lits, size_t n) {
+    if (!h || h->spent) return 0;
+    for (size_t i = 0; i < n; i++)
+        if ((lits[i] >> 1) >= h->n_vars) { set_err(B200SAT_E_ARG, "literal of an unknown variable"); return 0; }
+    if (h->kind == B200SAT_CORE && !h->ok) return 0; /* minisat.rs:41-48 */
+    /* host-visible part of Searcher::add_clause (search.rs:348-367): duplicate literals and tautologies */
+    std::vector<u32> ps(lits, lits + n);
+    std::sort(ps.begin(), ps.end());
+    ps.erase(std::unique(ps.begin(), ps.end()), ps.end());
+    bool taut = false;
+    for (size_t i = 1; i < ps.size(); i++) if (ps[i] == (ps[i - 1] ^ 1)) taut = true;
+    h->lits.insert(h->lits.end(), lits, lits + n);
+    h->clause_off.push_back((u32)h->lits.size());
+    if (!taut) {
+        if (ps.empty()) { h->ok = false; return 0; }
+        if (ps.size() > 1) h->n_clauses_known++;
+    }
+    return 1;
+}
+
+static int solver_run(b200sat_solver *h, int flags, b200sat_result *res, uint8_t *model, size_t model_cap) {
+    if (!h->eng) {
+        h->eng = b200sat_engine_create(0);
+        if (!h->eng) return B200SAT_E_NO_DEVICE;
+    }
+    for (u32 v = 0; v < h->n_vars; v++)
+        if (h->upol[v] != 0 || !h->dvar[v]) return set_err(B200SAT_E_ARG, "user polarity / non-decision vars are not supported by the device ingest yet");
+    u32 ioff[2] = {0, (u32)(h->clause_off.size() - 1)};
+    b200sat_batch b;
+    b.n_inst = 1; b.inst_clause_off = ioff; b.clause_off = h->clause_off.data();
+    u32 dummy = 0;
+    b.lits = h->lits.empty() ? &dummy : h->lits.data();
+    std::vector<u8> m(h->n_vars ? h->n_vars : 1, 2);
+    int rc = b200sat_solve_batch(h->eng, &b, &h->st, h->kind, flags, res, m.data(), (u32)m.size());
+    if (rc) return rc;
+    if (model) memcpy(model, m.data(), std::min(model_cap, (size_t)h->n_vars));
+    return 0;
+}
+
+extern "C" int b200sat_preprocess(b200sat_solver *h, const b200sat_budget *) {
+    if (!h) return set_err(B200SAT_E_ARG, "null handle");
+    if (h->spent) return set_err(B200SAT_E_SPENT, "handle already consumed");
+    if (!h->ok) return 0;
+    b200sat_result r;
+    int rc = solver_run(h, B200SAT_F_PREPROCESS | B200SAT_F_NO_SOLVE, &r, nullptr, 0);
+    if (rc) return rc;
+    h->preprocessed = true;
+    h->n_clauses_known = r.n_clauses_pre;
+    memcpy(&h->stats, r.stats, sizeof h->stats);
+    if (!r.pre_ok) h->ok = false;
+    return h->ok ? 1 : 0;
+}
+
+extern "C" int b200sat_solve_limited(b200sat_solver *h, const b200sat_budget *b, const uint32_t *, size_t n_assumps, uint8_t *model,
+                                     size_t model_cap) {
+    if (!h) return set_err(B200SAT_E_ARG, "null handle");
+    if (h->spent) return set_err(B200SAT_E_SPENT, "handle already consumed");
+    if (n_assumps) return set_err(B200SAT_E_ARG, "assumptions are not supported (the reference's callers pass &[])");
+    if (b && b->interrupt && *b->interrupt) return B200SAT_INTERRUPTED;
+    h->spent = true;
+    if (!h->ok && h->kind == B200SAT_CORE && h->clause_off.size() == 1) return B200SAT_UNSAT;
+    b200sat_result r;
+    /* the device replays ingest (+ preprocess when it was requested) and then searches: one deterministic pass */
+    int rc = solver_run(h, h->preprocessed ? B200SAT_F_PREPROCESS : 0, &r, model, model_cap);
+    if (rc) return rc;
+    memcpy(&h->stats, r.stats, sizeof h->stats);
+    h->n_clauses_known = r.n_clauses_pre;
+    return r.verdict;
+}
+
+extern "C" void b200sat_get_stats(const b200sat_solver *h, b200sat_stats *out) {
+    if (h && out) *out = h->stats;
+}

@@ -51,7 +51,12 @@ struct Layout {
     u64 slab_bytes;
 };
 
-static inline u64 layout_align(u64 x) { return (x + 255) & ~(u64)255; }
+#ifdef __CUDACC__
+#define B200SAT_HD __host__ __device__
+#else
+#define B200SAT_HD
+#endif
+B200SAT_HD static inline u64 layout_align(u64 x) { return (x + 255) & ~(u64)255; }
 
 /* bytes of the var-state block when it lives in the slab (tier 1) */
 static inline u64 layout_vars_bytes(u32 nv) {
