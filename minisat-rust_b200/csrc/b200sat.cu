@@ -246,7 +246,22 @@ extern "C" int b200sat_engine_upload(b200sat_engine *e, const b200sat_batch *b, 
     if ((rc = ensure(e->d_ioff, e->cap_ioff, (size_t)n + 1))) return rc;
     if ((rc = ensure(e->d_coff, e->cap_coff, (size_t)nc + 1))) return rc;
     if ((rc = ensure(e->d_lits, e->cap_lits, (size_t)nl + 1))) return rc;
-    /* stage through pinned memory so the copies are true async DMA */
+    /* caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory)
+     * are copied from directly; pageable ones are staged through pinned memory so the copies are async DMA */
+    {
+        cudaPointerAttributes a0, a1, a2;
+        bool pinned = cudaPointerGetAttributes(&a0, b->inst_clause_off) == cudaSuccess && a0.type == cudaMemoryTypeHost &&
+                      cudaPointerGetAttributes(&a1, b->clause_off) == cudaSuccess && a1.type == cudaMemoryTypeHost &&
+                      (nl == 0 || (cudaPointerGetAttributes(&a2, b->lits) == cudaSuccess && a2.type == cudaMemoryTypeHost));
+        cudaGetLastError();
+        if (pinned) {
+            CK(cudaMemcpyAsync(e->d_ioff, b->inst_clause_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(e->d_coff, b->clause_off, ((size_t)nc + 1) * 4, cudaMemcpyHostToDevice, stream));
+            if (nl) CK(cudaMemcpyAsync(e->d_lits, b->lits, (size_t)nl * 4, cudaMemcpyHostToDevice, stream));
+            e->n_inst = n; e->n_clauses = nc; e->n_lits = nl; e->shape = sh;
+            return alloc_outputs(e);
+        }
+    }
     size_t bytes = ((size_t)n + 1 + nc + 1 + nl) * 4;
     if (bytes > e->cap_stage) {
         if (e->h_stage) cudaFreeHost(e->h_stage);

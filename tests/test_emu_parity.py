@@ -1,0 +1,93 @@
+"""CPU tests: the DEVICE solver source (cdcl_warp.cuh), run under the test-only SIMT
+emulator, is trace-exact against the oracle: verdict, the 8 stats, the per-conflict
+trace hash, the traffic counters and the model."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import EDGE_CASES, SEED2, batch_of, csr_of, golden_instance, load_golden, synth_batch
+
+FLAGS = 1 | 4 | 8 | 16
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import pyemu
+    pyemu.build()
+    return pyemu
+
+
+def compare(po, emu, ioff, coff, lits, kind, settings=None, nv=None, **kw):
+    st = settings if settings is not None else po.default_settings()
+    n_inst = len(ioff) - 1
+    nv = nv or (int(lits.max() >> 1) + 1 if len(lits) else 1)
+    ores, omodels, _ = po.solve_batch(ioff, coff, lits, kind=kind, settings=st, threads=2, model_stride=nv)
+    eres, emodels = emu.solve_batch(ioff, coff, lits, st, kind=kind, flags=FLAGS, model_stride=nv, **kw)
+    for i in range(n_inst):
+        o, e = ores[i], eres[i]
+        assert e.status == 0, i
+        assert e.verdict == o.verdict, i
+        assert list(e.stats) == list(o.stats), (i, list(e.stats), list(o.stats))
+        assert e.trace_hash == o.trace_hash, i
+        assert list(e.traffic) == list(o.traffic), (i, list(e.traffic), list(o.traffic))
+        assert e.n_vars == o.n_vars and e.n_clauses_ingest == o.n_clauses_ingest, i
+        if o.verdict == 1:
+            assert (emodels[i][:o.n_vars] == omodels[i][:o.n_vars]).all(), i
+
+
+def test_core_edge_cases(po, emu):
+    ioff, coff, lits = batch_of([csr_of(EDGE_CASES[k]) for k in sorted(EDGE_CASES)])
+    compare(po, emu, ioff, coff, lits, po.CORE, nv=64)
+
+
+@pytest.mark.parametrize("tier,seed", [(-1, 0), (-1, 11), (0, 5)])
+def test_core_golden_small(po, emu, tier, seed):
+    g = load_golden()
+    idx = [i for i, n in enumerate(g["names"]) if n.startswith(("uf20", "uf50-01", "uf50-02", "uuf50-01"))]
+    ioff, coff, lits = batch_of([golden_instance(g, i) for i in idx])
+    compare(po, emu, ioff, coff, lits, po.CORE, tier_nv=tier, sched_seed=seed)
+
+
+def test_core_synthetic_adversarial_schedule(po, emu):
+    ioff, coff, lits = synth_batch(po, SEED2, 24, 40, 170)
+    compare(po, emu, ioff, coff, lits, po.CORE, sched_seed=1234)
+
+
+@pytest.mark.parametrize("variant", ["rnd_freq", "rnd_init", "rnd_pol", "ccmin_basic", "ccmin_none", "phase_none",
+                                     "phase_limited", "no_luby", "small_restart"])
+def test_core_settings_variants(po, emu, variant):
+    st = po.default_settings()
+    if variant == "rnd_freq": st.random_var_freq = 0.1
+    if variant == "rnd_init": st.rnd_init_act = 1
+    if variant == "rnd_pol": st.rnd_pol = 1
+    if variant == "ccmin_basic": st.ccmin_mode = 1
+    if variant == "ccmin_none": st.ccmin_mode = 0
+    if variant == "phase_none": st.phase_saving = 0
+    if variant == "phase_limited": st.phase_saving = 1
+    if variant == "no_luby": st.luby_restart = 0; st.restart_first = 10.0; st.restart_inc = 2.0
+    if variant == "small_restart": st.restart_first = 5.0; st.size_adjust_start_confl = 10; st.size_factor = 0.05
+    ioff, coff, lits = synth_batch(po, SEED2 + 1000, 10, 50, 213)
+    compare(po, emu, ioff, coff, lits, po.CORE, settings=st, sched_seed=3)
+
+
+def test_core_reduce_and_gc_paths(po, emu):
+    # tiny learnt limit + tiny restart interval: reduceDB, garbage collection and ground
+    # simplification run many times inside a short search
+    st = po.default_settings()
+    st.size_factor = 0.02
+    st.size_adjust_start_confl = 8
+    st.restart_first = 7.0
+    ioff, coff, lits = synth_batch(po, SEED2 + 5000, 6, 60, 256)
+    compare(po, emu, ioff, coff, lits, po.CORE, settings=st, sched_seed=9)
+
+
+def test_core_slab_overflow_retry(po, emu):
+    # an arena far too small for the instance forces the larger-slab retry ladder
+    ioff, coff, lits = synth_batch(po, SEED2 + 7000, 3, 50, 213)
+    st = po.default_settings()
+    eres, _ = emu.solve_batch(ioff, coff, lits, st, kind=0, flags=FLAGS, arena_words=1200, wpool_entries=700)
+    ores, _, _ = po.solve_batch(ioff, coff, lits, kind=po.CORE)
+    for i in range(3):
+        assert eres[i].status == 0 and eres[i].attempts > 1
+        assert list(eres[i].stats) == list(ores[i].stats)

@@ -1,0 +1,179 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI,
+against the oracle on the same inputs -- bit-exact verdict, 8 stats, trace hash, model."""
+import numpy as np
+import pytest
+
+from common import (EDGE_CASES, SEED2, SEED3, batch_of, check_models, csr_of, golden_instance, load_golden,
+                    synth_batch)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(pkg):
+    e = pkg.Engine(0)
+    yield e
+    e.close()
+
+
+def flags(pkg):
+    return pkg.F_PREPROCESS | pkg.F_ZERO_STATS_ON_PRE_UNSAT | pkg.F_TRACE_HASH | pkg.F_COUNT_TRAFFIC
+
+
+def assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, kind, settings=None, idx=None, threads=8):
+    sel = range(len(ioff) - 1) if idx is None else idx
+    ores, omodels, _ = po.solve_batch(ioff, coff, lits, kind=kind, settings=settings, threads=threads,
+                                      model_stride=models.shape[1] if models is not None else 0)
+    for i in sel:
+        o = ores[i]
+        assert res[i]["status"] == 0, i
+        assert res[i]["verdict"] == o.verdict, i
+        assert list(res[i]["stats"]) == list(o.stats), (i, list(res[i]["stats"]), list(o.stats))
+        assert int(res[i]["trace_hash"]) == o.trace_hash, i
+        assert list(res[i]["traffic"]) == list(o.traffic), i
+        if models is not None and o.verdict == 1:
+            assert (models[i][:o.n_vars] == omodels[i][:o.n_vars]).all(), i
+
+
+def test_golden_corpus_core(pkg, po, eng):
+    g = load_golden()
+    n = len(g["names"])
+    insts = [golden_instance(g, i) for i in range(n)]
+    # one launch per size class: small random instances together, the larger ones separately
+    small = [i for i in range(n) if g["n_vars"][i] <= 128]
+    big = [i for i in range(n) if g["n_vars"][i] > 128]
+    for group in (small, big):
+        ioff, coff, lits = batch_of([insts[i] for i in group])
+        stride = int(max(g["n_vars"][i] for i in group))
+        res, models = eng.solve_batch(ioff, coff, lits, kind=pkg.CORE, flags=flags(pkg), model_stride=stride)
+        for k, i in enumerate(group):
+            assert res[k]["status"] == 0, g["names"][i]
+            assert res[k]["verdict"] == int(g["core_verdict"][i]), g["names"][i]
+            assert list(res[k]["stats"]) == [int(x) for x in g["core_stats"][i]], g["names"][i]
+            assert int(res[k]["trace_hash"]) == int(g["core_hash"][i]), g["names"][i]
+            assert list(res[k]["traffic"]) == [int(x) for x in g["core_traffic"][i]], g["names"][i]
+        assert check_models(ioff, coff, lits, res["verdict"], models) == 0
+
+
+def test_edge_cases_core(pkg, po, eng):
+    ioff, coff, lits = batch_of([csr_of(EDGE_CASES[k]) for k in sorted(EDGE_CASES)])
+    res, models = eng.solve_batch(ioff, coff, lits, kind=pkg.CORE, flags=flags(pkg), model_stride=64)
+    assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, po.CORE)
+
+
+def test_synthetic_n100_vs_oracle(pkg, po, eng):
+    ioff, coff, lits = synth_batch(po, SEED2, 1500, 100, 426)
+    res, models = eng.solve_batch(ioff, coff, lits, kind=pkg.CORE, flags=flags(pkg), model_stride=100)
+    assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, po.CORE)
+    assert check_models(ioff, coff, lits, res["verdict"], models) == 0
+
+
+def test_device_generator_matches_host_generator(pkg, po, eng):
+    eng.generate_ksat(SEED2, 300, 100, 426, 3)
+    ioff, coff, lits = eng.download_batch()
+    h_ioff, h_coff, h_lits = synth_batch(po, SEED2, 300, 100, 426)
+    assert (ioff == h_ioff).all() and (coff == h_coff).all() and (lits == h_lits).all()
+
+
+def test_config2_full_size_properties(pkg, po, eng):
+    """BASELINE.json configs[1] at full size: 10k instances, n=100.  Size-independent properties:
+    every instance finishes, every SAT model satisfies its CNF, two runs are identical, and the
+    first 400 instances are bit-exact against the oracle."""
+    eng.generate_ksat(SEED2, 10000, 100, 426, 3)
+    eng.solve(kind=pkg.CORE, flags=flags(pkg))
+    res, models = eng.download(model_stride=100)
+    assert (res["status"] == 0).all()
+    assert set(np.unique(res["verdict"])) <= {0, 1}
+    ioff, coff, lits = eng.download_batch()
+    assert check_models(ioff, coff, lits, res["verdict"], models) == 0
+    eng.solve(kind=pkg.CORE, flags=flags(pkg) & ~pkg.F_COUNT_TRAFFIC)
+    res2, models2 = eng.download(model_stride=100)
+    assert (res2["stats"] == res["stats"]).all() and (res2["trace_hash"] == res["trace_hash"]).all()
+    assert (models2 == models).all()
+    assert_matches_oracle(pkg, po, res, models, ioff[:401], coff, lits, po.CORE)
+
+
+def test_n250_sample_vs_oracle(pkg, po, eng):
+    """config 3 shape (n=250, m=1065): the easiest instances of a seeded sample, full trace equality
+    (thousands of conflicts, several reduceDB rounds and garbage collections)."""
+    ioff, coff, lits = synth_batch(po, SEED3, 48, 250, 1065)
+    ores, _, _ = po.solve_batch(ioff, coff, lits, kind=po.CORE, threads=8)  # a few seconds each at most
+    order = np.argsort([int(r.stats[4]) for r in ores])[:24]
+    sub = batch_of([((coff[ioff[i]:ioff[i + 1] + 1] - coff[ioff[i]]).astype(np.uint32),
+                     lits[coff[ioff[i]]:coff[ioff[i + 1]]]) for i in order])
+    res, models = eng.solve_batch(*sub, kind=pkg.CORE, flags=flags(pkg), model_stride=250)
+    for k, i in enumerate(order):
+        assert res[k]["status"] == 0
+        assert res[k]["verdict"] == ores[i].verdict
+        assert list(res[k]["stats"]) == list(ores[i].stats), (k, list(res[k]["stats"]), list(ores[i].stats))
+        assert int(res[k]["trace_hash"]) == ores[i].trace_hash
+    assert check_models(sub[0], sub[1], sub[2], res["verdict"], models) == 0
+
+
+@pytest.mark.parametrize("variant", ["rnd_freq", "rnd_init", "rnd_pol", "ccmin_basic", "ccmin_none", "phase_none",
+                                     "phase_limited", "no_luby", "tiny_db"])
+def test_settings_variants(pkg, po, eng, variant):
+    st = pkg.default_settings()
+    if variant == "rnd_freq": st.random_var_freq = 0.1
+    if variant == "rnd_init": st.rnd_init_act = 1
+    if variant == "rnd_pol": st.rnd_pol = 1
+    if variant == "ccmin_basic": st.ccmin_mode = 1
+    if variant == "ccmin_none": st.ccmin_mode = 0
+    if variant == "phase_none": st.phase_saving = 0
+    if variant == "phase_limited": st.phase_saving = 1
+    if variant == "no_luby": st.luby_restart = 0; st.restart_first = 10.0
+    if variant == "tiny_db": st.size_factor = 0.02; st.size_adjust_start_confl = 8; st.restart_first = 7.0
+    ost = po.default_settings()
+    import ctypes as C
+    C.memmove(C.addressof(ost), C.addressof(st), C.sizeof(st))
+    ioff, coff, lits = synth_batch(po, SEED2 + 1000, 200, 80, 341)
+    res, models = eng.solve_batch(ioff, coff, lits, settings=st, kind=pkg.CORE, flags=flags(pkg), model_stride=80)
+    assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, po.CORE, settings=ost)
+
+
+def test_global_tier_large_instance(pkg, po, eng):
+    """An instance with more variables than the largest shared-memory tier runs with its var state in HBM."""
+    ioff, coff, lits = synth_batch(po, SEED2 + 9000, 4, 1500, 6000)   # ratio 4.0: easy but > 1024 vars
+    res, models = eng.solve_batch(ioff, coff, lits, kind=pkg.CORE, flags=flags(pkg), model_stride=1500)
+    assert eng.launch_info()["tier"] == 1
+    assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, po.CORE)
+
+
+def test_slab_overflow_retry(pkg, po):
+    e = pkg.Engine(0)
+    e.configure(arena_words=1200, wpool_entries=700)
+    ioff, coff, lits = synth_batch(po, SEED2 + 7000, 40, 50, 213)
+    res, models = e.solve_batch(ioff, coff, lits, kind=pkg.CORE, flags=flags(pkg), model_stride=50)
+    assert (res["status"] == 0).all() and res["attempts"].max() > 1
+    assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, po.CORE)
+    e.close()
+
+
+def test_single_solver_api(pkg, po):
+    """`trait Solver` mirror: new_var / add_clause / preprocess / solve_limited / stats on one handle."""
+    g = load_golden()
+    i = list(g["names"]).index("uf50-01.cnf.gz")
+    off, lits = golden_instance(g, i)
+    s = pkg.CoreSolver()
+    for c in range(len(off) - 1):
+        cl = [int(x) for x in lits[off[c]:off[c + 1]]]
+        for l in cl:
+            while pkg.lit_var(l) >= s.n_vars():
+                s.new_var(None, True)
+        assert s.add_clause(cl)
+    assert s.n_vars() == int(g["n_vars"][i])
+    assert s.preprocess()
+    r = s.solve_limited()
+    assert r.kind == int(g["core_verdict"][i])
+    assert [r.stats[k] for k in pkg.STAT_NAMES] == [int(x) for x in g["core_stats"][i]]
+    model = np.full(s.n_vars(), 2, np.uint8)
+    for l in r.model:
+        model[pkg.lit_var(l)] = 0 if pkg.lit_sign(l) else 1
+    assert po.check_model(off, lits, model)
+    with pytest.raises(pkg.EngineError):
+        s.solve_limited()          # the handle is spent (solve_limited consumes self, sat.rs:34)
+    u = pkg.CoreSolver()
+    a = u.new_var()
+    assert u.add_clause([pkg.mk_lit(a, False)]) and u.add_clause([pkg.mk_lit(a, True)])
+    assert not u.preprocess()
+    assert u.solve_limited().kind == pkg.UNSAT

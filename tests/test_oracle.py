@@ -1,0 +1,97 @@
+"""CPU tests of the ORACLE (test infrastructure): golden pins, SATLIB verdicts, model
+validity, Lit/LBool tables of the reference (src/sat/formula.rs:183-261), edge cases."""
+import numpy as np
+import pytest
+
+from common import EDGE_CASES, csr_of, golden_instance, load_golden, synth_batch, SEED2
+
+
+def test_lit_encoding_tables(pkg):
+    # formula.rs:183-207 test_lits: var/sign round trip, !!l == l, !l flips only the sign
+    for v in (0, 1, 5, 1000):
+        for sign in (False, True):
+            l = pkg.mk_lit(v, sign)
+            assert pkg.lit_var(l) == v and pkg.lit_sign(l) == sign
+            assert pkg.lit_not(pkg.lit_not(l)) == l
+            assert pkg.lit_var(pkg.lit_not(l)) == v and pkg.lit_sign(pkg.lit_not(l)) != sign
+    assert pkg.mk_lit(3, False) == 6 and pkg.mk_lit(3, True) == 7
+
+
+def test_golden_pins(po):
+    g = load_golden()
+    for i, name in enumerate(g["names"]):
+        off, lits = golden_instance(g, i)
+        for kind, tag in ((po.CORE, "core"), (po.SIMP, "simp")):
+            r, m = po.solve_csr(off, lits, kind=kind)
+            assert r.verdict == int(g[tag + "_verdict"][i]), name
+            assert list(r.stats) == [int(x) for x in g[tag + "_stats"][i]], (name, tag)
+            assert r.trace_hash == int(g[tag + "_hash"][i]), (name, tag)
+            if g["name_verdict"][i] >= 0:
+                assert r.verdict == int(g["name_verdict"][i]), name    # SATLIB naming: uf SAT, uuf UNSAT
+            if r.verdict == po.SAT:
+                assert po.check_model(off, lits, m), name
+
+
+@pytest.mark.parametrize("case", sorted(EDGE_CASES))
+def test_edge_cases_consistent(po, case):
+    off, lits = csr_of(EDGE_CASES[case])
+    verdicts = set()
+    for kind in (po.CORE, po.SIMP):
+        r, m = po.solve_csr(off, lits, kind=kind)
+        verdicts.add(r.verdict)
+        if r.verdict == po.SAT:
+            assert po.check_model(off, lits, m)
+    assert len(verdicts) == 1
+    expect_unsat = {"unit_conflict", "empty_clause", "unit_chain_unsat", "php_3_2", "late_unit"}
+    assert (verdicts == {po.UNSAT}) == (case in expect_unsat)
+
+
+def test_synthetic_generator_shape(po):
+    lits = po.gen_ksat(SEED2, 100, 426)
+    assert lits.shape == (1278,)
+    v = (lits >> 1).reshape(426, 3)
+    assert v.max() < 100
+    assert (v[:, 0] != v[:, 1]).all() and (v[:, 0] != v[:, 2]).all() and (v[:, 1] != v[:, 2]).all()
+    assert (po.gen_ksat(SEED2, 100, 426) == lits).all()
+    assert (po.gen_ksat(SEED2 + 1, 100, 426) != lits).any()
+
+
+def test_core_simp_agree_on_synthetic(po):
+    ioff, coff, lits = synth_batch(po, SEED2, 60, 60, 256)
+    rc, mc, _ = po.solve_batch(ioff, coff, lits, kind=po.CORE, threads=2, model_stride=60)
+    rs, ms, _ = po.solve_batch(ioff, coff, lits, kind=po.SIMP, threads=2, model_stride=60)
+    for i in range(60):
+        assert rc[i].verdict == rs[i].verdict
+        cb, ce = ioff[i], ioff[i + 1]
+        if rc[i].verdict == po.SAT:
+            assert po.check_model(coff[cb:ce + 1], lits, mc[i]) and po.check_model(coff[cb:ce + 1], lits, ms[i])
+
+
+def test_dimacs_reader_matches_oracle_parser(pkg, po, tmp_path):
+    text = "c hello\np cnf 5 4\n1 -2 0\nc mid comment\n 3 +4\n -5 0 2 0\n-1 0\nc % \n"
+    p = tmp_path / "t.cnf"
+    p.write_text(text)
+    off, lits, hv, hc = pkg.dimacs.read_csr(str(p))
+    o_off, o_lits, o_hv, o_hc = po.parse_dimacs(str(p))
+    assert (off == o_off).all() and (lits == o_lits).all() and (hv, hc) == (o_hv, o_hc) == (5, 4)
+    with pytest.raises(IOError):
+        pkg.dimacs.read_csr_text("p cnf 1 1\n1 0\n%\n0\n")          # '%' -> "int expected" (dimacs.rs:319-336)
+    with pytest.raises(IOError):
+        pkg.dimacs.read_csr_text("1 2 0\n")                          # header is mandatory
+    with pytest.raises(IOError):
+        pkg.dimacs.read_csr_text("p cnf 2 3\n1 2 0\n", validate=True)  # --strict header check
+    import gzip
+    gz = tmp_path / "t.cnf.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(text.encode())
+    off2, lits2, _, _ = pkg.dimacs.read_csr(str(gz))
+    assert (off2 == off).all() and (lits2 == lits).all()
+
+
+def test_write_result_format(pkg):
+    res = pkg.SolveRes(pkg.SAT, pkg.Stats(), [pkg.mk_lit(0, False), pkg.mk_lit(1, True), pkg.mk_lit(2, False)])
+    assert pkg.dimacs.result_string(res) == "SAT\n1 -2 3 0\n"
+    assert pkg.dimacs.result_string(pkg.SolveRes(pkg.UNSAT, pkg.Stats())) == "UNSAT\n"
+    assert pkg.dimacs.result_string(pkg.SolveRes(pkg.INTERRUPTED, pkg.Stats())) == "INDET\n"
+    assert pkg.dimacs.validate_model_text("p cnf 3 2\n1 -2 0\n2 3 0\n", res.model)
+    assert not pkg.dimacs.validate_model_text("p cnf 3 1\n-1 2 -3 0\n", res.model)
