@@ -133,7 +133,7 @@ def test_settings_variants(pkg, po, eng, variant):
 
 def test_global_tier_large_instance(pkg, po, eng):
     """An instance with more variables than the largest shared-memory tier runs with its var state in HBM."""
-    ioff, coff, lits = synth_batch(po, SEED2 + 9000, 4, 1500, 6000)   # ratio 4.0: easy but > 1024 vars
+    ioff, coff, lits = synth_batch(po, SEED2 + 9000, 4, 1500, 4500)   # ratio 3.0: easy, but > 1024 vars
     res, models = eng.solve_batch(ioff, coff, lits, kind=pkg.CORE, flags=flags(pkg), model_stride=1500)
     assert eng.launch_info()["tier"] == 1
     assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, po.CORE)
