@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sat.so")
+LIB_PATH = os.environ.get("B200SAT_LIB") or os.path.join(_HERE, "libb200sat.so")
 
 CORE, SIMP = 0, 1
 UNSAT, SAT, INTERRUPTED = 0, 1, 2

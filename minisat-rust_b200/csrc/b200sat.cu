@@ -27,6 +27,10 @@
 
 using namespace b200sat;
 
+#ifndef B200SAT_MINBLOCKS
+#define B200SAT_MINBLOCKS 16
+#endif
+
 /* ------------------------------------------------------------------ kernels */
 template <class VT, bool COUNT> __device__ __forceinline__ void warp_work_loop(WarpSolver<VT, COUNT> &S, const KParams &P) {
     for (;;) {
@@ -42,7 +46,8 @@ template <class VT, bool COUNT> __device__ __forceinline__ void warp_work_loop(W
     }
 }
 
-template <int NV, bool COUNT> __global__ void cdcl_warp_smem(const __grid_constant__ KParams P) {
+/* <= 64 threads per block and >= 16 blocks per SM: 64 registers per thread, 32 resident warps per SM */
+template <int NV, bool COUNT> __global__ void __launch_bounds__(64, B200SAT_MINBLOCKS) cdcl_warp_smem(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 wpb = blockDim.x >> 5;
@@ -52,7 +57,7 @@ template <int NV, bool COUNT> __global__ void cdcl_warp_smem(const __grid_consta
     warp_work_loop(S, P);
 }
 
-template <bool COUNT> __global__ void cdcl_warp_glob(const __grid_constant__ KParams P) {
+template <bool COUNT> __global__ void __launch_bounds__(64, 8) cdcl_warp_glob(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 wpb = blockDim.x >> 5;
@@ -346,12 +351,14 @@ extern "C" int b200sat_engine_solve(b200sat_engine *e, const b200sat_settings *s
         kernel_fn fn = pick_kernel(tier_nv, count, spw);
         /* launch shape: as many resident warps per SM as shared memory and registers allow */
         int best_wpb = 1, best_bps = 1, best_warps = 0;
-        const int cand[] = {1, 2, 4, 8};
-        for (int ci = 0; ci < 4; ci++) {
+        const int cand[] = {1, 2};
+        for (int ci = 0; ci < 2; ci++) {
             int wpb = e->cfg_wpb > 0 ? e->cfg_wpb : cand[ci];
+            if (wpb > 2) return set_err(B200SAT_E_ARG, "warps_per_block must be 1 or 2 (launch bounds)");
             size_t smem = spw * wpb;
             if (smem > e->smem_optin) { if (e->cfg_wpb > 0) return set_err(B200SAT_E_ARG, "warps_per_block needs too much shared memory"); continue; }
             CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
             int bps = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void *)fn, wpb * 32, smem));
             if (e->cfg_bps > 0 && bps > e->cfg_bps) bps = e->cfg_bps;
@@ -380,6 +387,14 @@ extern "C" int b200sat_engine_solve(b200sat_engine *e, const b200sat_settings *s
         }
         size_t smem = spw * best_wpb;
         CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {   /* give shared memory only what the resident blocks need; the rest of the 256 KB stays L1 for the slab traffic */
+            int per_sm = (int)((grid + e->num_sms - 1) / e->num_sms);
+            if (per_sm > best_bps) per_sm = best_bps;
+            size_t need = (size_t)per_sm * (smem + 1024);
+            int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+            if (pct > 100) pct = 100;
+            cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
         if ((rc = ensure(e->d_slabs, e->cap_slabs, (size_t)(warps_total * L.slab_bytes)))) return rc;
         CK(cudaMemsetAsync(e->d_queue, 0, 8, stream));
         KParams P;

@@ -374,30 +374,89 @@ template <class VT, bool COUNT> struct WarpSolver {
 
     /* -------------------------------------------------------------- BCP, watches.rs:64-152
      * Lanes evaluate up to 32 watchers of watches[p] at once against the current
-     * assignment.  Outcomes before (and including) the first lane that implies a
-     * literal or conflicts are exactly what the sequential scan would produce and
-     * are committed in list order; lanes behind it are re-evaluated after the
-     * assignment (their watcher and clause words are already in registers). */
+     * assignment.  A watcher's verdict can only be changed by an implication made
+     * by an EARLIER watcher of the same list, and only when the implied variable
+     * occurs among the literals the verdict depends on (blocker, first literal,
+     * chosen replacement watch).  So the lanes are committed in list order up to
+     * the first lane that such an implication touches (or a conflict); that lane
+     * and the ones behind it are re-evaluated (their watcher and clause words are
+     * already in registers).  Several implications commit in one round. */
+
+    /* ordered parallel append: lane i (if `moving`) appends (cref, blocker) to list tgt; lanes
+     * with the same target keep their lane order.  One step per distinct target list. */
+    DEV bool push_watch_multi(u32 movemask, bool moving, u32 tgt, u32 cref, u32 blocker) {
+        const u32 lt = lanemask_lt(lane);
+        while (movemask) {
+            const u32 l = (u32)__ffs(movemask) - 1;
+            const u32 t = __shfl_sync(FULL_MASK, tgt, l);
+            const bool mine = moving && tgt == t;
+            const u32 same = __ballot_sync(FULL_MASK, mine);
+            const u32 cnt = __popc(same);
+            movemask &= ~same;
+            u32 word = V.wstart()[t];
+            const u32 len = V.wlen()[t];
+            if (len + cnt > (1u << (word & W_CAP_MASK))) { /* the list has to grow: one by one */
+                u32 mm = same;
+                while (mm) {
+                    u32 ml = (u32)__ffs(mm) - 1;
+                    mm &= mm - 1;
+                    u32 c = __shfl_sync(FULL_MASK, cref, ml);
+                    u32 bk = __shfl_sync(FULL_MASK, blocker, ml);
+                    if (!push_watch(t, c, bk)) return false;
+                }
+                continue;
+            }
+            __syncwarp();
+            if (mine) wpool[(word >> W_SHIFT) + len + __popc(same & lt)] = make_uint2(cref, blocker);
+            if (lane == l) V.wlen()[t] = (idx_t)(len + cnt);
+        }
+        __syncwarp();
+        return true;
+    }
+
     DEV u32 propagate() {
         u32 confl = CREF_UNDEF;
         u32 nprops = 0;
         u32 t_vis = 0, t_kept = 0, t_deref = 0, t_tail = 0, t_moves = 0, t_impl = 0;
         const u32 lt = lanemask_lt(lane);
+        bool have_pf = false;
+        u32 pf_word = 0, pf_n = 0;
+        uint2 pf_w = make_uint2(0, 0);
         while (qhead < trail_n && confl == CREF_UNDEF) {
             u32 p = V.trail()[qhead];
             qhead++;
             nprops++;
             const u32 not_p = p ^ 1;
-            u32 word = V.wstart()[p];
-            const u32 n = V.wlen()[p];
+            u32 word, n;
+            uint2 w0 = make_uint2(0, 0);
+            if (have_pf) { word = pf_word; n = pf_n; w0 = pf_w; }
+            else {
+                word = V.wstart()[p];
+                n = V.wlen()[p];
+                if (lane < n) w0 = wpool[(word >> W_SHIFT) + lane];
+            }
+            /* software pipelining: fetch the head of the NEXT literal's list now.  That list cannot
+             * change while this one is processed (a true literal is never a move target). */
+#ifdef B200SAT_PREFETCH /* measured slower on B200 (r01: 248 vs 208 ms at 2 warps/SM): off by default */
+            have_pf = qhead < trail_n;
+#else
+            have_pf = false;
+#endif
+            if (have_pf) {
+                const u32 p2 = V.trail()[qhead];
+                pf_word = V.wstart()[p2];
+                pf_n = V.wlen()[p2];
+                pf_w = make_uint2(0, 0);
+                if (lane < pf_n) pf_w = wpool[(pf_word >> W_SHIFT) + lane];
+            }
             const bool dirty = (word & W_DIRTY) != 0;
             uint2 *ws = wpool + (word >> W_SHIFT);
             u32 j = 0;
             for (u32 i = 0; i < n; i += 32) {
                 u32 idx = i + lane;
                 bool valid = idx < n;
-                uint2 w = make_uint2(0, 0);
-                if (valid) w = ws[idx];
+                uint2 w = w0;
+                if (i != 0) { w = make_uint2(0, 0); if (valid) w = ws[idx]; }
                 uint4 hd = make_uint4(0, 0, 0, 0);
                 bool loaded = false, dead = false;
                 if (valid && dirty) { hd = ld4(arena + w.x); loaded = true; dead = (hd.x & H_DELETED) != 0; }
@@ -418,10 +477,11 @@ template <class VT, bool COUNT> struct WarpSolver {
                         else {
                             if (!loaded) { hd = ld4(arena + w.x); loaded = true; }
                             first = (hd.y == not_p) ? hd.z : hd.y;
-                            if (is_true(first)) out = OUT_KEEPCW;
+                            const u32 fv = lval(first);
+                            if (fv == 1) out = OUT_KEEPCW;
                             else {
                                 len = hd.x >> H_SHIFT;
-                                out = is_false(first) ? OUT_CONFL : OUT_UNIT;
+                                out = (fv == 0) ? OUT_CONFL : OUT_UNIT;
                                 for (; kf < len; kf++) {
                                     u32 l = (kf == 2) ? hd.w : arena[w.x + 1 + kf];
                                     if (!is_false(l)) { lk = l; out = OUT_MOVE; break; }
@@ -431,56 +491,74 @@ template <class VT, bool COUNT> struct WarpSolver {
                     }
                     const u32 pendmask = __ballot_sync(FULL_MASK, pend);
                     if (!pendmask) break;
-                    const u32 umask = __ballot_sync(FULL_MASK, out >= OUT_UNIT);
-                    const u32 u = umask ? (u32)__ffs(umask) - 1 : 32;
-                    const bool commit = pend && lane <= u;
+                    u32 umask = __ballot_sync(FULL_MASK, out >= OUT_UNIT);
+                    u32 stop = 32;     /* first lane that is NOT committed this round */
+                    u32 cfl_lane = 32; /* lane whose clause is conflicting, if inside the committed prefix */
+                    while (umask) {
+                        const u32 u = (u32)__ffs(umask) - 1;
+                        if (u >= stop) break;
+                        umask &= umask - 1;
+                        const u32 uout = __shfl_sync(FULL_MASK, out, u);
+                        if (uout == OUT_CONFL) { cfl_lane = u; stop = u + 1; break; }
+                        const u32 xv = __shfl_sync(FULL_MASK, first, u) >> 1;
+                        const bool aff = pend && lane > u && out != OUT_KEEPW &&
+                                         ((w.y >> 1) == xv || (first >> 1) == xv || (out == OUT_MOVE && (lk >> 1) == xv));
+                        const u32 am = __ballot_sync(FULL_MASK, aff);
+                        if (am) { const u32 s2 = (u32)__ffs(am) - 1; if (s2 < stop) stop = s2; }
+                    }
+                    const bool commit = pend && lane < stop;
                     const bool keep = commit && out != OUT_MOVE;
                     const u32 keepmask = __ballot_sync(FULL_MASK, keep);
                     if (keep) ws[j + __popc(keepmask & lt)] = (out == OUT_KEEPW) ? w : make_uint2(w.x, first);
                     j += __popc(keepmask);
+                    const bool mv = commit && out == OUT_MOVE;
                     if (commit && out != OUT_KEEPW) {
-                        if (hd.y == not_p || out == OUT_MOVE) {
+                        if (hd.y == not_p || mv) {
                             arena[w.x + 1] = first;
-                            arena[w.x + 2] = (out == OUT_MOVE) ? lk : not_p;
+                            arena[w.x + 2] = mv ? lk : not_p;
                         }
-                        if (out == OUT_MOVE) arena[w.x + 1 + kf] = not_p;
+                        if (mv) arena[w.x + 1 + kf] = not_p;
                     }
-                    u32 movemask = __ballot_sync(FULL_MASK, commit && out == OUT_MOVE);
+                    /* implications of the committed prefix, in lane order (assignment.rs:104-113) */
+                    const bool imp = commit && out == OUT_UNIT;
+                    const u32 impmask = __ballot_sync(FULL_MASK, imp);
+                    if (imp) {
+                        const u32 v = first >> 1;
+                        V.assign()[v] = (u8)((first & 1) ^ 1);
+                        V.level()[v] = (idx_t)nlevels;
+                        V.reason()[v] = w.x;
+                        V.trail()[trail_n + __popc(impmask & lt)] = (idx_t)first;
+                    }
+                    trail_n += __popc(impmask);
+                    const u32 movemask = __ballot_sync(FULL_MASK, mv);
                     if (COUNT) {
                         t_vis += __popc(__ballot_sync(FULL_MASK, commit));
                         t_kept += __popc(keepmask);
                         t_deref += __popc(__ballot_sync(FULL_MASK, commit && out != OUT_KEEPW));
                         u32 tl = 0;
-                        if (commit && out >= OUT_MOVE) tl = (out == OUT_MOVE) ? kf - 1 : len - 2;
+                        if (commit && out >= OUT_MOVE) tl = mv ? kf - 1 : len - 2;
                         t_tail += warp_sum(tl);
                         t_moves += __popc(movemask);
+                        t_impl += __popc(impmask);
                     }
                     if (movemask) {
-                        while (movemask) {
-                            u32 ml = (u32)__ffs(movemask) - 1;
-                            movemask &= movemask - 1;
-                            u32 tgt = __shfl_sync(FULL_MASK, lk, ml) ^ 1;
-                            u32 mcr = __shfl_sync(FULL_MASK, w.x, ml);
-                            u32 mbl = __shfl_sync(FULL_MASK, first, ml);
-                            if (!push_watch(tgt, mcr, mbl)) return CREF_UNDEF;
+                        if (!push_watch_multi(movemask, mv, lk ^ 1, w.x, first)) return CREF_UNDEF;
+                        if (wpool + (V.wstart()[p] >> W_SHIFT) != ws) { /* the pool was compacted: descriptors moved */
+                            ws = wpool + (V.wstart()[p] >> W_SHIFT);
+                            have_pf = false;
                         }
-                        ws = wpool + (V.wstart()[p] >> W_SHIFT); /* the pool may have been compacted */
                     }
-                    if (u == 32) break;
-                    const u32 uout = __shfl_sync(FULL_MASK, out, u);
-                    const u32 ucr = __shfl_sync(FULL_MASK, w.x, u);
-                    const u32 ufirst = __shfl_sync(FULL_MASK, first, u);
-                    lbase = u + 1;
-                    if (uout == OUT_CONFL) {
-                        confl = ucr;
-                        const bool rem = live && lane >= lbase;
+                    __syncwarp();
+                    if (cfl_lane != 32) {
+                        confl = __shfl_sync(FULL_MASK, w.x, cfl_lane);
+                        const bool rem = live && lane >= stop;
                         u32 m = __ballot_sync(FULL_MASK, rem);
                         if (rem) ws[j + __popc(m & lt)] = w;
                         j += __popc(m);
                         break;
                     }
-                    assign_lit(ufirst, ucr);
-                    if (COUNT) t_impl++;
+                    if (stop == 32) break;
+                    lbase = stop;
                 }
             }
             __syncwarp();
@@ -548,26 +626,36 @@ template <class VT, bool COUNT> struct WarpSolver {
         if (fcr == CREF_UNDEF) return false;
         u32 *st = stk();
         u32 *tcl = tc();
+        const u32 amax = P.L.arena_cap - 1;
         u32 sp = 0;
-        u32 fp = literal, fpos = 1, flen = arena[fcr] >> H_SHIFT;
-        if (COUNT) an_words += 1 + flen;
+        u32 fp = literal, fpos = 1, flen = 0;
+        bool fresh_frame = true; /* header not read yet: fetch it together with the first literals */
         for (;;) {
             bool pushed = false;
-            while (fpos < flen) {
-                u32 k = fpos + lane;
-                u32 code = 0, l = 0;
-                if (k < flen) {
-                    l = arena[fcr + 1 + k];
-                    u32 v = l >> 1;
+            for (;;) {
+                /* words [wb, wb+32) of the clause block; word 0 is the header */
+                const u32 wb = fresh_frame ? 0 : fpos + 1;
+                const u32 wi = wb + lane;
+                u32 x = arena[(fcr + wi) < amax ? (fcr + wi) : amax];
+                if (fresh_frame) {
+                    flen = bcast(x) >> H_SHIFT;
+                    if (COUNT) an_words += 1 + flen;
+                    fresh_frame = false;
+                }
+                if (fpos >= flen) break;
+                const u32 k = wi - 1;
+                u32 code = 0;
+                if (wi >= 1 && k >= fpos && k < flen) {
+                    u32 v = x >> 1;
                     u32 s = V.vflags()[v] & VF_SEEN;
                     if (!(V.level()[v] == GROUND || s == SEEN_SOURCE || s == SEEN_REMOVABLE))
                         code = (V.reason()[v] != CREF_UNDEF && s == SEEN_UNDEF) ? 1 : 2;
                 }
                 u32 nm = __ballot_sync(FULL_MASK, code != 0);
-                if (!nm) { fpos += 32; continue; }
+                if (!nm) { fpos = wb + 31; if (fpos >= flen) break; continue; }
                 u32 f = (u32)__ffs(nm) - 1;
                 u32 fc = __shfl_sync(FULL_MASK, code, f);
-                u32 fl = __shfl_sync(FULL_MASK, l, f);
+                u32 fl = __shfl_sync(FULL_MASK, x, f);
                 if (fc == 2) {
                     /* failure: every literal on the stack is not redundant either (conflict.rs:232-240) */
                     __syncwarp();
@@ -582,13 +670,12 @@ template <class VT, bool COUNT> struct WarpSolver {
                     __syncwarp();
                     return false;
                 }
-                if (lane == 0) { st[4 * sp] = fp; st[4 * sp + 1] = fcr; st[4 * sp + 2] = fpos + f + 1; st[4 * sp + 3] = flen; }
+                if (lane == 0) { st[4 * sp] = fp; st[4 * sp + 1] = fcr; st[4 * sp + 2] = wb + f; st[4 * sp + 3] = flen; }
                 sp++;
                 fp = fl;
                 fcr = V.reason()[fl >> 1];
                 fpos = 1;
-                flen = arena[fcr] >> H_SHIFT;
-                if (COUNT) an_words += 1 + flen;
+                fresh_frame = true;
                 pushed = true;
                 break;
             }
@@ -631,17 +718,23 @@ template <class VT, bool COUNT> struct WarpSolver {
         u32 n_out = 1;
         u32 confl = confl0;
         u64 an_words = 0;
+        const u32 amax = P.L.arena_cap - 1;
         for (;;) {
-            u32 h = arena[confl];
-            u32 len = h >> H_SHIFT;
+            /* one round trip: lane 0 reads the header, lanes 1..31 the first 31 literals */
+            u32 x = arena[(confl + lane) < amax ? (confl + lane) : amax];
+            const u32 h = bcast(x);
+            const u32 len = h >> H_SHIFT;
             if (h & H_LEARNT) bump_cla(confl, len);
             if (COUNT) an_words += 1 + len;
-            for (u32 k0 = (confl == confl0) ? 0 : 1; k0 < len; k0 += 32) {
-                u32 k = k0 + lane;
+            const u32 kbase = (confl == confl0) ? 0 : 1;
+            for (u32 w0 = 0; w0 <= len; w0 += 32) {
+                const u32 wi = w0 + lane;          /* word index inside the clause block, 0 = header */
+                const u32 k = wi - 1;              /* literal index */
+                if (w0 != 0) x = (wi <= len) ? arena[confl + wi] : 0;
                 bool fresh = false, iscur = false;
                 u32 q = 0, v = 0;
-                if (k < len) {
-                    q = arena[confl + 1 + k];
+                if (wi >= 1 && k < len && k >= kbase) {
+                    q = x;
                     v = q >> 1;
                     u32 f = vf[v];
                     if ((f & VF_SEEN) == SEEN_UNDEF) {

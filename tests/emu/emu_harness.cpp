@@ -90,6 +90,9 @@ void run_warp(void (*entry)(void *, int), void *user, uint64_t seed) {
         case K_SHFL_UP:
             for (int l = 0; l < 32; l++) { int s = l - w->arg2[l]; w->res[l] = w->arg[s < 0 ? l : s]; }
             break;
+        case K_MATCH:
+            for (int l = 0; l < 32; l++) { uint32_t m = 0; for (int o = 0; o < 32; o++) if (w->arg[o] == w->arg[l]) m |= 1u << o; w->res[l] = m; }
+            break;
         case K_SYNC: break;
         default: fprintf(stderr, "simt_emu: bad collective %d\n", k0); abort();
         }

@@ -34,7 +34,7 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 
 namespace simt {
 
-enum Kind { K_NONE = 0, K_BALLOT, K_SHFL, K_SHFL_XOR, K_SHFL_UP, K_SYNC, K_EXIT };
+enum Kind { K_NONE = 0, K_BALLOT, K_SHFL, K_SHFL_XOR, K_SHFL_UP, K_SYNC, K_MATCH, K_EXIT };
 
 struct Warp {
     ucontext_t sched;
@@ -88,6 +88,10 @@ template <class T> static inline T __shfl_up_sync(uint32_t mask, T v, int d) {
     uint64_t a = 0; memcpy(&a, &v, sizeof(T));
     simt::arrive(simt::K_SHFL_UP, a, d);
     uint64_t r = simt::result(); T o; memcpy(&o, &r, sizeof(T)); return o;
+}
+static inline uint32_t __match_any_sync(uint32_t mask, uint32_t v) {
+    simt::arrive(simt::K_MATCH, v, 0);
+    return (uint32_t)simt::result();
 }
 static inline void __syncwarp(uint32_t mask = 0xFFFFFFFFu) { simt::arrive(simt::K_SYNC, 0, 0); }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }

@@ -1,0 +1,15 @@
+"""One solve of a config-2-style batch with a fixed launch shape (profiling aid)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import _b200pkg
+pkg = _b200pkg.load()
+n_inst, n, wpb, bps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+m = int(round(4.26 * n))
+eng = pkg.Engine(0)
+eng.generate_ksat(0x5EED000000000000 if n == 100 else 0x5EED000100000000, n_inst, n, m, 3)
+eng.configure(warps_per_block=wpb, blocks_per_sm=bps)
+for it in range(2):
+    eng.solve(kind=pkg.CORE, flags=pkg.F_PREPROCESS | pkg.F_ZERO_STATS_ON_PRE_UNSAT)
+info = eng.launch_info()
+res, _ = eng.download(want_models=False)
+print(info, "props/s %.3e" % (res["stats"][:, 5].sum() / info["last_kernel_ms"] * 1e3))
