@@ -20,53 +20,11 @@
 #include <vector>
 
 #include "cdcl_plan.h"
-#include "cdcl_warp.cuh"
-#ifdef B200SAT_HAVE_SIMP
-#include "simp_warp.cuh"
-#endif
 
 using namespace b200sat;
 
-#ifndef B200SAT_MINBLOCKS
-#define B200SAT_MINBLOCKS 16
-#endif
-
-/* ------------------------------------------------------------------ kernels */
-template <class VT, bool COUNT> __device__ __forceinline__ void warp_work_loop(WarpSolver<VT, COUNT> &S, const KParams &P) {
-    for (;;) {
-        u32 w = 0;
-        if (S.lane == 0) w = atomicAdd(P.queue, 1u);
-        w = __shfl_sync(FULL_MASK, w, 0);
-        if (w >= P.n_work) break;
-        u32 inst = P.work ? P.work[w] : w;
-#ifdef B200SAT_HAVE_SIMP
-        if (P.kind == B200SAT_SIMP) { solve_simp(S, inst); continue; }
-#endif
-        S.solve_core(inst);
-    }
-}
-
-/* <= 64 threads per block and >= 16 blocks per SM: 64 registers per thread, 32 resident warps per SM */
-template <int NV, bool COUNT> __global__ void __launch_bounds__(64, B200SAT_MINBLOCKS) cdcl_warp_smem(const __grid_constant__ KParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u32 wpb = blockDim.x >> 5;
-    WarpSolver<VarsS<NV>, COUNT> S(P, lane);
-    S.V.s = reinterpret_cast<SmemVars<NV> *>(smem_raw) + warp;
-    S.slab = P.slabs + (size_t)(blockIdx.x * wpb + warp) * P.L.slab_bytes;
-    warp_work_loop(S, P);
-}
-
-template <bool COUNT> __global__ void __launch_bounds__(64, 8) cdcl_warp_glob(const __grid_constant__ KParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u32 wpb = blockDim.x >> 5;
-    WarpSolver<VarsG, COUNT> S(P, lane);
-    S.V.s = reinterpret_cast<SmemSmall *>(smem_raw) + warp;
-    S.slab = P.slabs + (size_t)(blockIdx.x * wpb + warp) * P.L.slab_bytes;
-    S.V.bind(S.slab + P.L.off_vars, P.L.nv_cap);
-    warp_work_loop(S, P);
-}
+/* the cdcl_warp kernels are instantiated in kern_*.cu (one translation unit per COUNT x SIMP combination) */
+#include "cdcl_kernels.cuh"
 
 /* SplitMix64 generator of SURVEY.md 8d: bit-identical to the host generator the CPU baseline uses */
 __global__ void gen_random_ksat(u64 seed_base, u32 n_inst, u32 n, u32 m, u32 k, u32 *inst_clause_off,
@@ -306,16 +264,11 @@ extern "C" int b200sat_engine_generate_ksat(b200sat_engine *e, uint64_t seed_bas
     return alloc_outputs(e);
 }
 
-typedef void (*kernel_fn)(const KParams);
-
-static kernel_fn pick_kernel(int tier_nv, bool count, size_t &smem_per_warp) {
-    switch (tier_nv) {
-    case 128: smem_per_warp = sizeof(SmemVars<128>); return count ? cdcl_warp_smem<128, true> : cdcl_warp_smem<128, false>;
-    case 256: smem_per_warp = sizeof(SmemVars<256>); return count ? cdcl_warp_smem<256, true> : cdcl_warp_smem<256, false>;
-    case 512: smem_per_warp = sizeof(SmemVars<512>); return count ? cdcl_warp_smem<512, true> : cdcl_warp_smem<512, false>;
-    case 1024: smem_per_warp = sizeof(SmemVars<1024>); return count ? cdcl_warp_smem<1024, true> : cdcl_warp_smem<1024, false>;
-    default: smem_per_warp = sizeof(SmemSmall); return count ? cdcl_warp_glob<true> : cdcl_warp_glob<false>;
-    }
+static kernel_fn pick_kernel(int tier_nv, bool count, int kind, size_t &smem_per_warp) {
+#ifdef B200SAT_HAVE_SIMP
+    if (kind == B200SAT_SIMP) return count ? b200sat_pick_c1s1(tier_nv, &smem_per_warp) : b200sat_pick_c0s1(tier_nv, &smem_per_warp);
+#endif
+    return count ? b200sat_pick_c1s0(tier_nv, &smem_per_warp) : b200sat_pick_c0s0(tier_nv, &smem_per_warp);
 }
 
 static int check_settings(const b200sat_settings *s, int kind) {
@@ -348,7 +301,7 @@ extern "C" int b200sat_engine_solve(b200sat_engine *e, const b200sat_settings *s
         if (attempt == 3) tier_nv = 0; /* last resort: var state in HBM too, biggest slabs */
         Layout L = plan_layout(e->shape, tier_nv, kind, attempt, e->cfg_arena, e->cfg_wpool);
         size_t spw = 0;
-        kernel_fn fn = pick_kernel(tier_nv, count, spw);
+        kernel_fn fn = pick_kernel(tier_nv, count, kind, spw);
         /* launch shape: as many resident warps per SM as shared memory and registers allow */
         int best_wpb = 1, best_bps = 1, best_warps = 0;
         const int cand[] = {1, 2};

@@ -18,8 +18,8 @@ struct BatchShape {
 };
 
 /* shared-memory tiers compiled into the library (template instantiations) */
-static const int kSmemTiers[] = {128, 256, 512, 1024};
-static const int kNumSmemTiers = 4;
+static const int kSmemTiers[] = {128, 256, 1024};
+static const int kNumSmemTiers = 3;
 
 /* smallest shared-memory tier that holds `nvars`, or 0 for the global tier */
 static inline int pick_tier_nv(u32 nvars, u32 max_clauses) {
@@ -52,6 +52,11 @@ static inline Layout plan_layout(const BatchShape &sh, int tier_nv, int kind, u3
     L.clauses_cap = sat_u32((u64)sh.max_clauses * (kind == B200SAT_SIMP ? 3 : 1) + 64);
     L.tmp_cap = sh.max_clause_len < 64 ? 64 : sh.max_clause_len;
     L.simp_cap = 0;
+    L.simp_lits = 0;
+    if (kind == B200SAT_SIMP) {
+        L.simp_lits = sat_u32((sh.max_lits + 64) * grow);
+        L.simp_cap = simp_layout(L.nv_cap, L.clauses_cap, L.simp_lits, L.tmp_cap).total;
+    }
     layout_finalize(L);
     return L;
 }

@@ -45,6 +45,7 @@ struct Layout {
     u32 clauses_cap;  /* entries of the clauses list                        */
     u32 tmp_cap;      /* words of ingest scratch (>= longest input clause)  */
     u32 simp_cap;     /* words of simplifier heap (0 when CORE only)        */
+    u32 simp_lits;    /* literal budget the simplifier region was sized for */
     u32 tier;         /* 0: var state in shared memory, 1: in the slab      */
     u64 off_arena[2], off_wpool[2], off_learnts, off_clauses, off_ol, off_tc, off_stk, off_tmp, off_vars,
         off_simp;
@@ -78,6 +79,40 @@ static inline void layout_finalize(Layout &L) {
     L.off_vars = o; if (L.tier == 1) o += layout_vars_bytes(L.nv_cap);
     L.off_simp = o; o += layout_align(4ull * L.simp_cap);
     L.slab_bytes = layout_align(o);
+}
+
+/* sub-layout of the slab's simplifier region (word offsets), identical on host and device */
+struct SimpLayout {
+    u32 o_ostart, o_olen, o_ocap, o_eheap, o_eidx, o_nocc, o_flags, o_sq, o_elits, o_esizes, o_cand, o_cls, o_pn,
+        o_rbuf, o_roff, o_tmp, o_opool[2];
+    u32 sq_cap, elits_cap, esizes_cap, cand_cap, rbuf_cap, roff_cap, opool_cap, tmp_cap;
+    u32 total;
+};
+B200SAT_HD static inline SimpLayout simp_layout(u32 nv, u32 max_clauses, u64 max_lits, u32 max_clause_len) {
+    SimpLayout s;
+    u32 o = 0;
+    const u32 M = max_clauses, L = (u32)max_lits;
+    s.o_ostart = o; o += nv;
+    s.o_olen = o; o += nv;
+    s.o_ocap = o; o += nv;
+    s.o_eheap = o; o += nv;
+    s.o_eidx = o; o += nv;
+    s.o_nocc = o; o += 2 * nv;
+    s.o_flags = o; o += (3 * nv + 3) / 4 + 1;
+    s.sq_cap = 8 * M + 4096; s.o_sq = o; o += s.sq_cap;
+    s.elits_cap = 6 * L + 8 * nv + 1024; s.o_elits = o; o += s.elits_cap;
+    s.esizes_cap = 3 * M + 2 * nv + 64; s.o_esizes = o; o += s.esizes_cap;
+    s.cand_cap = 3 * M + 256; s.o_cand = o; o += s.cand_cap;
+    s.o_cls = o; o += s.cand_cap;
+    s.o_pn = o; o += s.cand_cap;
+    s.rbuf_cap = 4 * L + 64 * (max_clause_len + 32) + 4096; s.o_rbuf = o; o += s.rbuf_cap;
+    s.roff_cap = 3 * M + 256; s.o_roff = o; o += s.roff_cap;
+    s.tmp_cap = 4 * max_clause_len + 256; s.o_tmp = o; o += s.tmp_cap;
+    s.opool_cap = 6 * L + 16 * nv + 4096;
+    s.o_opool[0] = o; o += s.opool_cap;
+    s.o_opool[1] = o; o += s.opool_cap;
+    s.total = o;
+    return s;
 }
 
 struct KParams {

@@ -51,7 +51,7 @@ struct Scal {
     u32 arena_top, wpool_top, n_learnts, n_clauses, num_clauses, num_learnts;
     i32 size_adjust_cnt;
     u32 simp_db_assigns, simp_db_assigns_set, status, dec_vars, heap_n, cur_arena, cur_wpool, eliminated_vars;
-    u32 remove_satisfied, extra_clause_field;
+    u32 remove_satisfied, extra_clause_field, elim_n;
 };
 
 /* ------------------------------------------------------------------ var-state tiers */
@@ -166,6 +166,8 @@ enum : u32 { LR_RESTART = 0, LR_UNSAT = 1, LR_SAT = 2, LR_ABORT = 3 };
 /* ================================================================== the solver */
 template <class VT, bool COUNT> struct WarpSolver {
     typedef typename VT::idx_t idx_t;
+    static const u32 VT_ABSENT = VT::ABSENT;
+    static const u32 VT_MAXLEN = VT::MAXLEN;
     VT V;
     const KParams &P;
     u32 lane;

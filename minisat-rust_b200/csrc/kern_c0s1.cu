@@ -1,0 +1,5 @@
+/* cdcl_warp kernels: COUNT=0 SIMP=1 */
+#define B200SAT_KERNEL_TU_NAME b200sat_pick_c0s1
+#define B200SAT_KERNEL_TU_COUNT 0
+#define B200SAT_KERNEL_TU_SIMP 1
+#include "cdcl_kernels.cuh"

@@ -187,7 +187,6 @@ int emu_solve_batch(const uint32_t *inst_clause_off, const uint32_t *clause_off,
             switch (tier_nv) {
             case 128: fn = count ? entry_s<128, true> : entry_s<128, false>; break;
             case 256: fn = count ? entry_s<256, true> : entry_s<256, false>; break;
-            case 512: fn = count ? entry_s<512, true> : entry_s<512, false>; break;
             case 1024: fn = count ? entry_s<1024, true> : entry_s<1024, false>; break;
             default: fn = count ? entry_g<true> : entry_g<false>; break;
             }

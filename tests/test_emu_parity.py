@@ -32,6 +32,7 @@ def compare(po, emu, ioff, coff, lits, kind, settings=None, nv=None, **kw):
         assert e.trace_hash == o.trace_hash, i
         assert list(e.traffic) == list(o.traffic), (i, list(e.traffic), list(o.traffic))
         assert e.n_vars == o.n_vars and e.n_clauses_ingest == o.n_clauses_ingest, i
+        assert e.n_clauses_pre == o.n_clauses_pre and e.eliminated_vars == o.eliminated_vars and e.pre_ok == o.pre_ok, i
         if o.verdict == 1:
             assert (emodels[i][:o.n_vars] == omodels[i][:o.n_vars]).all(), i
 
@@ -91,3 +92,55 @@ def test_core_slab_overflow_retry(po, emu):
     for i in range(3):
         assert eres[i].status == 0 and eres[i].attempts > 1
         assert list(eres[i].stats) == list(ores[i].stats)
+
+
+# ---------------------------------------------------------------- SimpSolver path (simp_warp.cuh)
+def test_simp_edge_cases(po, emu):
+    ioff, coff, lits = batch_of([csr_of(EDGE_CASES[k]) for k in sorted(EDGE_CASES)])
+    compare(po, emu, ioff, coff, lits, po.SIMP, nv=64)
+
+
+@pytest.mark.parametrize("tier,seed", [(-1, 0), (0, 13)])
+def test_simp_golden_small(po, emu, tier, seed):
+    g = load_golden()
+    idx = [i for i, n in enumerate(g["names"]) if n.startswith(("uf20", "uf50-01", "uf50-02", "uuf50-01"))]
+    ioff, coff, lits = batch_of([golden_instance(g, i) for i in idx])
+    compare(po, emu, ioff, coff, lits, po.SIMP, tier_nv=tier, sched_seed=seed)
+
+
+@pytest.mark.parametrize("name", ["2bitcomp_5.cnf.gz", "2bitmax_6.cnf.gz", "2bitadd_11.cnf.gz", "3blocks.cnf.gz"])
+def test_simp_structured(po, emu, name):
+    # heavy variable elimination (50..307 eliminated vars), simplifier-time garbage collection, model extension
+    g = load_golden()
+    i = list(g["names"]).index(name)
+    ioff, coff, lits = batch_of([golden_instance(g, i)])
+    compare(po, emu, ioff, coff, lits, po.SIMP, nv=int(g["n_vars"][i]), sched_seed=7)
+    e, _ = emu.solve_batch(ioff, coff, lits, po.default_settings(), kind=po.SIMP, flags=FLAGS)
+    assert list(e[0].stats) == [int(x) for x in g["simp_stats"][i]]
+    assert e[0].eliminated_vars == int(g["simp_elim"][i]) and e[0].n_clauses_pre == int(g["simp_nclauses_pre"][i])
+
+
+def test_simp_without_preprocess_call(po, emu):
+    # solve_limited on a SimpSolver whose preprocess() was never called (simplify.rs:165-211)
+    ioff, coff, lits = synth_batch(po, SEED2 + 50, 5, 50, 213)
+    st = po.default_settings()
+    ores, om, _ = po.solve_batch(ioff, coff, lits, kind=po.SIMP, flags=0, threads=2, model_stride=50)
+    eres, em = emu.solve_batch(ioff, coff, lits, st, kind=po.SIMP, flags=8 | 16, model_stride=50)
+    for o, e, a, b in zip(ores, eres, om, em):
+        assert e.status == 0 and e.verdict == o.verdict and list(e.stats) == list(o.stats) and e.trace_hash == o.trace_hash
+        if o.verdict == 1:
+            assert (a[:o.n_vars] == b[:o.n_vars]).all()
+
+
+@pytest.mark.parametrize("variant", ["grow", "no_elim", "cl_lim", "sub_lim", "simp_gc"])
+def test_simp_settings_variants(po, emu, variant):
+    st = po.default_settings()
+    if variant == "grow": st.grow = 8
+    if variant == "no_elim": st.use_elim = 0
+    if variant == "cl_lim": st.clause_lim = 4
+    if variant == "sub_lim": st.subsumption_lim = 3
+    if variant == "simp_gc": st.simp_garbage_frac = 0.01
+    g = load_golden()
+    idx = [list(g["names"]).index(n) for n in ("2bitcomp_5.cnf.gz", "uf50-03.cnf.gz", "uuf50-02.cnf.gz")]
+    ioff, coff, lits = batch_of([golden_instance(g, i) for i in idx])
+    compare(po, emu, ioff, coff, lits, po.SIMP, settings=st, nv=int(max(g["n_vars"][i] for i in idx)), sched_seed=2)

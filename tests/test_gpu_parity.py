@@ -31,6 +31,7 @@ def assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, kind, settings
         assert list(res[i]["stats"]) == list(o.stats), (i, list(res[i]["stats"]), list(o.stats))
         assert int(res[i]["trace_hash"]) == o.trace_hash, i
         assert list(res[i]["traffic"]) == list(o.traffic), i
+        assert res[i]["n_clauses_pre"] == o.n_clauses_pre and res[i]["eliminated_vars"] == o.eliminated_vars, i
         if models is not None and o.verdict == 1:
             assert (models[i][:o.n_vars] == omodels[i][:o.n_vars]).all(), i
 
@@ -177,3 +178,59 @@ def test_single_solver_api(pkg, po):
     assert u.add_clause([pkg.mk_lit(a, False)]) and u.add_clause([pkg.mk_lit(a, True)])
     assert not u.preprocess()
     assert u.solve_limited().kind == pkg.UNSAT
+
+
+# ---------------------------------------------------------------- SimpSolver path (default settings of the reference)
+def test_golden_corpus_simp(pkg, po, eng):
+    g = load_golden()
+    n = len(g["names"])
+    insts = [golden_instance(g, i) for i in range(n)]
+    small = [i for i in range(n) if g["n_vars"][i] <= 128]
+    big = [i for i in range(n) if g["n_vars"][i] > 128]
+    for group in (small, big):
+        ioff, coff, lits = batch_of([insts[i] for i in group])
+        stride = int(max(g["n_vars"][i] for i in group))
+        res, models = eng.solve_batch(ioff, coff, lits, kind=pkg.SIMP, flags=flags(pkg), model_stride=stride)
+        for k, i in enumerate(group):
+            assert res[k]["status"] == 0, g["names"][i]
+            assert res[k]["verdict"] == int(g["simp_verdict"][i]), g["names"][i]
+            assert list(res[k]["stats"]) == [int(x) for x in g["simp_stats"][i]], g["names"][i]
+            assert int(res[k]["trace_hash"]) == int(g["simp_hash"][i]), g["names"][i]
+            assert res[k]["eliminated_vars"] == int(g["simp_elim"][i]), g["names"][i]
+            assert res[k]["n_clauses_pre"] == int(g["simp_nclauses_pre"][i]), g["names"][i]
+        assert check_models(ioff, coff, lits, res["verdict"], models) == 0   # extended models satisfy the ORIGINAL CNF
+
+
+def test_edge_cases_simp(pkg, po, eng):
+    ioff, coff, lits = batch_of([csr_of(EDGE_CASES[k]) for k in sorted(EDGE_CASES)])
+    res, models = eng.solve_batch(ioff, coff, lits, kind=pkg.SIMP, flags=flags(pkg), model_stride=64)
+    assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, po.SIMP)
+
+
+def test_synthetic_n100_simp_vs_oracle(pkg, po, eng):
+    ioff, coff, lits = synth_batch(po, SEED2, 1000, 100, 426)
+    res, models = eng.solve_batch(ioff, coff, lits, kind=pkg.SIMP, flags=flags(pkg), model_stride=100)
+    assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, po.SIMP)
+    assert check_models(ioff, coff, lits, res["verdict"], models) == 0
+
+
+def test_single_solver_api_simp(pkg, po):
+    g = load_golden()
+    i = list(g["names"]).index("2bitcomp_5.cnf.gz")
+    off, lits = golden_instance(g, i)
+    s = pkg.SimpSolver()
+    for c in range(len(off) - 1):
+        cl = [int(x) for x in lits[off[c]:off[c + 1]]]
+        for l in cl:
+            while pkg.lit_var(l) >= s.n_vars():
+                s.new_var(None, True)
+        s.add_clause(cl)
+    assert s.preprocess()
+    assert s.n_clauses() == int(g["simp_nclauses_pre"][i])
+    r = s.solve_limited()
+    assert r.kind == pkg.SAT
+    assert [r.stats[k] for k in pkg.STAT_NAMES] == [int(x) for x in g["simp_stats"][i]]
+    model = np.full(s.n_vars(), 2, np.uint8)
+    for l in r.model:
+        model[pkg.lit_var(l)] = 0 if pkg.lit_sign(l) else 1
+    assert po.check_model(off, lits, model)
