@@ -173,6 +173,12 @@ int b200sat_engine_generate_ksat(b200sat_engine *e, uint64_t seed_base, uint32_t
  * unless a slab overflow forces a retry pass (which synchronises). */
 int b200sat_engine_solve(b200sat_engine *e, const b200sat_settings *s, int kind, int flags,
                          void *stream);
+/* Asynchronous form: enqueue the solve on `stream` and return; b200sat_engine_finish() waits for it
+ * and runs the larger-slab retry passes.  Engines on different streams overlap (one batch's
+ * hardest instances no longer idle the GPU while the next batch starts). */
+int b200sat_engine_solve_async(b200sat_engine *e, const b200sat_settings *s, int kind, int flags,
+                               void *stream);
+int b200sat_engine_finish(b200sat_engine *e);
 /* Copy results (and models: n_inst*model_stride bytes, may be NULL) to the host; synchronises. */
 int b200sat_engine_download(b200sat_engine *e, b200sat_result *results, uint8_t *models,
                             uint32_t model_stride, void *stream);
@@ -194,6 +200,13 @@ int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out);
 int b200sat_solve_batch(b200sat_engine *e, const b200sat_batch *batch, const b200sat_settings *s,
                         int kind, int flags, b200sat_result *results, uint8_t *models,
                         uint32_t model_stride);
+
+/* Asynchronous end-to-end form: H2D + solve + D2H enqueued on `stream`; buffers must stay valid
+ * (and should be page-locked) until b200sat_solve_batch_finish() returns. */
+int b200sat_solve_batch_async(b200sat_engine *e, const b200sat_batch *batch, const b200sat_settings *s,
+                              int kind, int flags, b200sat_result *results, uint8_t *models,
+                              uint32_t model_stride, void *stream);
+int b200sat_solve_batch_finish(b200sat_engine *e);
 
 #ifdef __cplusplus
 }

@@ -107,6 +107,7 @@ ABI_SYMBOLS = (
     "b200sat_engine_generate_ksat", "b200sat_engine_solve", "b200sat_engine_download",
     "b200sat_engine_batch_dims", "b200sat_engine_download_batch", "b200sat_engine_configure",
     "b200sat_engine_launch_info", "b200sat_solve_batch",
+    "b200sat_engine_solve_async", "b200sat_engine_finish", "b200sat_solve_batch_async", "b200sat_solve_batch_finish",
 )
 
 _lib = None
@@ -154,6 +155,11 @@ def lib():
     L.b200sat_engine_launch_info.argtypes = [vp, C.POINTER(LaunchInfo)]
     L.b200sat_solve_batch.argtypes = [vp, C.POINTER(BatchStruct), C.POINTER(Settings), C.c_int, C.c_int,
                                       vp, u8p, C.c_uint32]
+    L.b200sat_engine_solve_async.argtypes = [vp, C.POINTER(Settings), C.c_int, C.c_int, vp]
+    L.b200sat_engine_finish.argtypes = [vp]
+    L.b200sat_solve_batch_async.argtypes = [vp, C.POINTER(BatchStruct), C.POINTER(Settings), C.c_int, C.c_int,
+                                            vp, u8p, C.c_uint32, vp]
+    L.b200sat_solve_batch_finish.argtypes = [vp]
     _lib = L
     return L
 
@@ -311,6 +317,28 @@ class Engine:
     def solve(self, settings=None, kind=CORE, flags=F_PREPROCESS | F_ZERO_STATS_ON_PRE_UNSAT, stream=None):
         s = settings if settings is not None else default_settings()
         return _check(lib().b200sat_engine_solve(self._e, C.byref(s), kind, flags, stream), allow=(E_MEM,))
+
+    def solve_async(self, settings=None, kind=CORE, flags=F_PREPROCESS | F_ZERO_STATS_ON_PRE_UNSAT, stream=None):
+        self._settings_keep = settings if settings is not None else default_settings()
+        _check(lib().b200sat_engine_solve_async(self._e, C.byref(self._settings_keep), kind, flags, stream))
+
+    def finish(self):
+        return _check(lib().b200sat_engine_finish(self._e), allow=(E_MEM,))
+
+    def solve_batch_async(self, inst_clause_off, clause_off, lits, results, models, settings=None, kind=CORE,
+                          flags=F_PREPROCESS | F_ZERO_STATS_ON_PRE_UNSAT, stream=None):
+        """results: uint8/RESULT_DTYPE ndarray of n_inst records, models: (n_inst, stride) uint8 ndarray or None;
+        all buffers should be page-locked and must stay alive until solve_batch_finish()."""
+        s = settings if settings is not None else default_settings()
+        b, keep = self._batch(inst_clause_off, clause_off, lits)
+        self._keep = (b, keep, s, results, models)
+        mp = models.ctypes.data_as(C.POINTER(C.c_uint8)) if models is not None else None
+        stride = models.shape[1] if models is not None else 0
+        _check(lib().b200sat_solve_batch_async(self._e, C.byref(b), C.byref(s), kind, flags, results.ctypes.data, mp,
+                                               stride, stream))
+
+    def solve_batch_finish(self):
+        return _check(lib().b200sat_solve_batch_finish(self._e), allow=(E_MEM,))
 
     def dims(self):
         n, nc, nl = C.c_uint32(), C.c_uint64(), C.c_uint64()

@@ -53,6 +53,39 @@ __global__ void gen_random_ksat(u64 seed_base, u32 n_inst, u32 n, u32 m, u32 k, 
     }
 }
 
+/* batch shape (largest instance) computed on the device right after the H2D copy: out = {max var id,
+ * max clause length, max clauses per instance, max literals per instance, monotonicity violations} */
+__global__ void batch_shape(const u32 *ioff, const u32 *coff, const u32 *lits, u32 n_inst, u64 nc, u64 nl, u32 *out) {
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, nt = (u64)gridDim.x * blockDim.x;
+    u32 mv = 0, ml = 0, mc = 0, mL = 0, bad = 0;
+    for (u64 k = tid; k < nl; k += nt) { u32 v = lits[k] >> 1; mv = v > mv ? v : mv; }
+    for (u64 c = tid; c < nc; c += nt) {
+        u32 a = coff[c], b = coff[c + 1];
+        if (b < a || b > nl) bad = 1; else { u32 l = b - a; ml = l > ml ? l : ml; }
+    }
+    for (u64 i = tid; i < n_inst; i += nt) {
+        u32 a = ioff[i], b = ioff[i + 1];
+        if (b < a || b > nc) bad = 1;
+        else {
+            u32 c = b - a; mc = c > mc ? c : mc;
+            u32 la = coff[a], lb = coff[b];
+            if (lb >= la) { u32 l = lb - la; mL = l > mL ? l : mL; }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        u32 t;
+        t = __shfl_xor_sync(0xFFFFFFFFu, mv, o); mv = t > mv ? t : mv;
+        t = __shfl_xor_sync(0xFFFFFFFFu, ml, o); ml = t > ml ? t : ml;
+        t = __shfl_xor_sync(0xFFFFFFFFu, mc, o); mc = t > mc ? t : mc;
+        t = __shfl_xor_sync(0xFFFFFFFFu, mL, o); mL = t > mL ? t : mL;
+        bad |= __shfl_xor_sync(0xFFFFFFFFu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out + 0, mv); atomicMax(out + 1, ml); atomicMax(out + 2, mc); atomicMax(out + 3, mL);
+        if (bad) atomicOr(out + 4, 1u);
+    }
+}
+
 __global__ void collect_failed(const b200sat_result *results, const u32 *work, u32 n_work, u32 *out_list, u32 *out_count) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_work) return;
@@ -111,11 +144,26 @@ struct b200sat_engine {
     size_t cap_slabs = 0;
     u32 *d_queue = nullptr;      /* [0] queue counter, [1] failed counter */
     u32 *d_work[2] = {nullptr, nullptr};
-    size_t cap_work = 0;
+    size_t cap_work = 0, cap_work1 = 0;
     u32 *h_pinned = nullptr;     /* small pinned staging for counters */
     void *h_stage = nullptr;     /* pinned staging for uploads */
     size_t cap_stage = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    /* in-flight asynchronous solve */
+    struct Pending {
+        bool active = false, retried = false;
+        b200sat_settings st;
+        int kind = 0, flags = 0, tier_nv = 0;
+        cudaStream_t stream = nullptr;
+        u32 attempt = 0, n_work = 0;
+        const u32 *work = nullptr;
+        u32 *next_list = nullptr;
+        float total_ms = 0.f;
+        b200sat_result *out_results = nullptr;   /* batch-async destination buffers */
+        uint8_t *out_models = nullptr;
+        uint32_t out_stride = 0;
+        bool batch = false;
+    } pend;
     /* tunables */
     int cfg_wpb = 0, cfg_bps = 0;
     u64 cfg_arena = 0, cfg_wpool = 0;
@@ -144,7 +192,7 @@ extern "C" b200sat_engine *b200sat_engine_create(int device) {
     e->num_sms = prop.multiProcessorCount;
     e->smem_optin = prop.sharedMemPerBlockOptin;
     memset(&e->info, 0, sizeof e->info);
-    if (cudaMalloc((void **)&e->d_queue, 64) != cudaSuccess || cudaMallocHost((void **)&e->h_pinned, 64) != cudaSuccess ||
+    if (cudaMalloc((void **)&e->d_queue, 128) != cudaSuccess || cudaMallocHost((void **)&e->h_pinned, 128) != cudaSuccess ||
         cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
         set_err(B200SAT_E_CUDA, "engine allocation failed");
         delete e;
@@ -178,9 +226,25 @@ static int alloc_outputs(b200sat_engine *e) {
     e->model_stride = e->shape.max_vars ? e->shape.max_vars : 1;
     if ((rc = ensure(e->d_models, e->cap_models, (size_t)e->n_inst * e->model_stride))) return rc;
     if ((rc = ensure(e->d_work[0], e->cap_work, (size_t)e->n_inst))) return rc;
-    size_t dummy = 0;
-    if (e->d_work[1]) { cudaFree(e->d_work[1]); e->d_work[1] = nullptr; }
-    if ((rc = ensure(e->d_work[1], dummy, e->cap_work))) return rc;
+    if ((rc = ensure(e->d_work[1], e->cap_work1, (size_t)e->n_inst))) return rc;
+    return 0;
+}
+
+static int device_shape(b200sat_engine *e, cudaStream_t stream) {
+    e->shape = BatchShape{0, 0, 0, 0};
+    if (e->n_inst == 0) return 0;
+    u32 *d_out = e->d_queue + 8;
+    CK(cudaMemsetAsync(d_out, 0, 20, stream));
+    batch_shape<<<e->num_sms * 4, 256, 0, stream>>>(e->d_ioff, e->d_coff, e->d_lits, e->n_inst, e->n_clauses, e->n_lits, d_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_pinned + 8, d_out, 20, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const u32 *h = e->h_pinned + 8;
+    if (h[4]) return set_err(B200SAT_E_ARG, "CSR offsets are not monotone / out of range");
+    e->shape.max_vars = e->n_lits ? h[0] + 1 : 0;
+    e->shape.max_clause_len = h[1];
+    e->shape.max_clauses = h[2];
+    e->shape.max_lits = h[3];
     return 0;
 }
 
@@ -192,19 +256,6 @@ extern "C" int b200sat_engine_upload(b200sat_engine *e, const b200sat_batch *b, 
     const u64 nc = n ? b->inst_clause_off[n] : 0;
     const u64 nl = nc ? b->clause_off[nc] : 0;
     BatchShape sh = {0, 0, 0, 0};
-    for (u32 i = 0; i < n; i++) {
-        u32 cb = b->inst_clause_off[i], ce = b->inst_clause_off[i + 1];
-        if (ce < cb) return set_err(B200SAT_E_ARG, "inst_clause_off not monotone");
-        sh.max_clauses = std::max(sh.max_clauses, ce - cb);
-        sh.max_lits = std::max<u64>(sh.max_lits, b->clause_off[ce] - b->clause_off[cb]);
-    }
-    for (u64 c = 0; c < nc; c++) {
-        if (b->clause_off[c + 1] < b->clause_off[c]) return set_err(B200SAT_E_ARG, "clause_off not monotone");
-        sh.max_clause_len = std::max(sh.max_clause_len, b->clause_off[c + 1] - b->clause_off[c]);
-    }
-    u32 mx = 0;
-    for (u64 k = 0; k < nl; k++) mx = std::max(mx, b->lits[k] >> 1);
-    sh.max_vars = nl ? mx + 1 : 0;
     int rc;
     if ((rc = ensure(e->d_ioff, e->cap_ioff, (size_t)n + 1))) return rc;
     if ((rc = ensure(e->d_coff, e->cap_coff, (size_t)nc + 1))) return rc;
@@ -221,7 +272,8 @@ extern "C" int b200sat_engine_upload(b200sat_engine *e, const b200sat_batch *b, 
             CK(cudaMemcpyAsync(e->d_ioff, b->inst_clause_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, stream));
             CK(cudaMemcpyAsync(e->d_coff, b->clause_off, ((size_t)nc + 1) * 4, cudaMemcpyHostToDevice, stream));
             if (nl) CK(cudaMemcpyAsync(e->d_lits, b->lits, (size_t)nl * 4, cudaMemcpyHostToDevice, stream));
-            e->n_inst = n; e->n_clauses = nc; e->n_lits = nl; e->shape = sh;
+            e->n_inst = n; e->n_clauses = nc; e->n_lits = nl;
+            if ((rc = device_shape(e, stream))) return rc;
             return alloc_outputs(e);
         }
     }
@@ -241,7 +293,9 @@ extern "C" int b200sat_engine_upload(b200sat_engine *e, const b200sat_batch *b, 
     CK(cudaMemcpyAsync(e->d_ioff, hs, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(e->d_coff, hs + n + 1, ((size_t)nc + 1) * 4, cudaMemcpyHostToDevice, stream));
     if (nl) CK(cudaMemcpyAsync(e->d_lits, hs + n + 1 + nc + 1, (size_t)nl * 4, cudaMemcpyHostToDevice, stream));
-    e->n_inst = n; e->n_clauses = nc; e->n_lits = nl; e->shape = sh;
+    e->n_inst = n; e->n_clauses = nc; e->n_lits = nl;
+    (void)sh;
+    if ((rc = device_shape(e, stream))) return rc;
     return alloc_outputs(e);
 }
 
@@ -271,6 +325,8 @@ static kernel_fn pick_kernel(int tier_nv, bool count, int kind, size_t &smem_per
     return count ? b200sat_pick_c1s0(tier_nv, &smem_per_warp) : b200sat_pick_c0s0(tier_nv, &smem_per_warp);
 }
 
+extern "C" int b200sat_engine_finish(b200sat_engine *e);
+
 static int check_settings(const b200sat_settings *s, int kind) {
     if (!s) return set_err(B200SAT_E_ARG, "null settings");
     if (s->use_rcheck) return set_err(B200SAT_E_ARG, "use_rcheck is not supported (SURVEY.md 8f-4)");
@@ -283,100 +339,134 @@ static int check_settings(const b200sat_settings *s, int kind) {
     return 0;
 }
 
-extern "C" int b200sat_engine_solve(b200sat_engine *e, const b200sat_settings *s, int kind, int flags, void *stream_) {
+/* enqueue one attempt (kernel + failure collection + count read-back) on the pending stream; no host sync */
+static int launch_attempt(b200sat_engine *e) {
+    b200sat_engine::Pending &pd = e->pend;
+    cudaStream_t stream = pd.stream;
+    int rc;
+    const bool count = (pd.flags & B200SAT_F_COUNT_TRAFFIC) != 0;
+    if (pd.attempt == 3) pd.tier_nv = 0; /* last resort: var state in HBM too, biggest slabs */
+    Layout L = plan_layout(e->shape, pd.tier_nv, pd.kind, pd.attempt, e->cfg_arena, e->cfg_wpool);
+    size_t spw = 0;
+    kernel_fn fn = pick_kernel(pd.tier_nv, count, pd.kind, spw);
+    /* launch shape: as many resident warps per SM as shared memory and registers allow */
+    int best_wpb = 1, best_bps = 1, best_warps = 0;
+    const int cand[] = {1, 2};
+    for (int ci = 0; ci < 2; ci++) {
+        int wpb = e->cfg_wpb > 0 ? e->cfg_wpb : cand[ci];
+        if (wpb > 2) return set_err(B200SAT_E_ARG, "warps_per_block must be 1 or 2 (launch bounds)");
+        size_t smem = spw * wpb;
+        if (smem > e->smem_optin) { if (e->cfg_wpb > 0) return set_err(B200SAT_E_ARG, "warps_per_block needs too much shared memory"); continue; }
+        CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        int bps = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void *)fn, wpb * 32, smem));
+        if (e->cfg_bps > 0 && bps > e->cfg_bps) bps = e->cfg_bps;
+        if (bps * wpb > best_warps) { best_warps = bps * wpb; best_wpb = wpb; best_bps = bps; }
+        if (e->cfg_wpb > 0) break;
+    }
+    if (best_warps == 0) return set_err(B200SAT_E_CUDA, "kernel does not fit on the device");
+    u32 grid = (u32)(e->num_sms * best_bps);
+    u32 need_blocks = (pd.n_work + best_wpb - 1) / best_wpb;
+    if (grid > need_blocks) grid = need_blocks;
+    u64 warps_total = (u64)grid * best_wpb;
+    if (warps_total * L.slab_bytes > e->cap_slabs) { /* bound the slab memory: at most ~60% of free HBM */
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = (size_t)((double)(free_b + e->cap_slabs) * 0.6);
+        if (warps_total * L.slab_bytes > budget) {
+            u64 fit = budget / L.slab_bytes;
+            if (fit == 0) return set_err(B200SAT_E_MEM, "an instance needs a slab larger than the free device memory");
+            if (fit < (u64)best_wpb) best_wpb = 1;
+            grid = (u32)std::max<u64>(1, fit / best_wpb);
+            warps_total = (u64)grid * best_wpb;
+        }
+    }
+    size_t smem = spw * best_wpb;
+    CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   /* give shared memory only what the resident blocks need; the rest of the 256 KB stays L1 for the slab traffic */
+        int per_sm = (int)((grid + e->num_sms - 1) / e->num_sms);
+        if (per_sm > best_bps) per_sm = best_bps;
+        size_t need = (size_t)per_sm * (smem + 1024);
+        int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
+    if (warps_total * L.slab_bytes > e->cap_slabs) {
+        CK(cudaStreamSynchronize(stream)); /* the old slabs may still be in use by an earlier launch on this stream */
+        if ((rc = ensure(e->d_slabs, e->cap_slabs, (size_t)(warps_total * L.slab_bytes)))) return rc;
+    }
+    CK(cudaMemsetAsync(e->d_queue, 0, 8, stream));
+    KParams P;
+    memset(&P, 0, sizeof P);
+    P.inst_clause_off = e->d_ioff; P.clause_off = e->d_coff; P.lits = e->d_lits;
+    P.work = pd.work; P.n_work = pd.n_work; P.queue = e->d_queue;
+    P.results = e->d_results; P.models = e->d_models; P.model_stride = e->model_stride;
+    P.slabs = e->d_slabs; P.L = L; P.st = pd.st; P.kind = pd.kind; P.flags = pd.flags; P.attempt = pd.attempt + 1;
+    CK(cudaEventRecord(e->ev0, stream));
+    fn<<<grid, best_wpb * 32, smem, stream>>>(P);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->ev1, stream));
+    pd.next_list = e->d_work[pd.attempt & 1];
+    collect_failed<<<(pd.n_work + 255) / 256, 256, 0, stream>>>(e->d_results, pd.work, pd.n_work, pd.next_list, e->d_queue + 1);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_pinned, e->d_queue + 1, 4, cudaMemcpyDeviceToHost, stream));
+    e->info.grid = grid; e->info.block = best_wpb * 32; e->info.smem_bytes = (u32)smem;
+    e->info.warps_total = (u32)warps_total; e->info.tier = L.tier; e->info.slab_bytes = L.slab_bytes;
+    e->info.launches += 1;
+    return 0;
+}
+
+/* Asynchronous solve of the resident batch: enqueues the first attempt on `stream` and returns.
+ * b200sat_engine_finish() waits for it and runs the larger-slab retry passes if any instance needs one. */
+extern "C" int b200sat_engine_solve_async(b200sat_engine *e, const b200sat_settings *s, int kind, int flags, void *stream_) {
     if (!e) return set_err(B200SAT_E_ARG, "null engine");
     int rc = check_settings(s, kind);
     if (rc) return rc;
-    cudaStream_t stream = (cudaStream_t)stream_;
+    if (e->pend.active) { rc = b200sat_engine_finish(e); if (rc && rc != B200SAT_E_MEM) return rc; }
     CK(cudaSetDevice(e->device));
     e->info.launches = 0;
     e->info.last_kernel_ms = 0.f;
     if (e->n_inst == 0) return 0;
-    const bool count = (flags & B200SAT_F_COUNT_TRAFFIC) != 0;
-    int tier_nv = pick_tier_nv(e->shape.max_vars, e->shape.max_clauses);
-    u32 n_work = e->n_inst;
-    const u32 *work = nullptr;
-    float total_ms = 0.f;
-    for (u32 attempt = 0; attempt < 5 && n_work > 0; attempt++) {
-        if (attempt == 3) tier_nv = 0; /* last resort: var state in HBM too, biggest slabs */
-        Layout L = plan_layout(e->shape, tier_nv, kind, attempt, e->cfg_arena, e->cfg_wpool);
-        size_t spw = 0;
-        kernel_fn fn = pick_kernel(tier_nv, count, kind, spw);
-        /* launch shape: as many resident warps per SM as shared memory and registers allow */
-        int best_wpb = 1, best_bps = 1, best_warps = 0;
-        const int cand[] = {1, 2};
-        for (int ci = 0; ci < 2; ci++) {
-            int wpb = e->cfg_wpb > 0 ? e->cfg_wpb : cand[ci];
-            if (wpb > 2) return set_err(B200SAT_E_ARG, "warps_per_block must be 1 or 2 (launch bounds)");
-            size_t smem = spw * wpb;
-            if (smem > e->smem_optin) { if (e->cfg_wpb > 0) return set_err(B200SAT_E_ARG, "warps_per_block needs too much shared memory"); continue; }
-            CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            int bps = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void *)fn, wpb * 32, smem));
-            if (e->cfg_bps > 0 && bps > e->cfg_bps) bps = e->cfg_bps;
-            if (bps * wpb > best_warps) { best_warps = bps * wpb; best_wpb = wpb; best_bps = bps; }
-            if (e->cfg_wpb > 0) break;
-        }
-        if (best_warps == 0) return set_err(B200SAT_E_CUDA, "kernel does not fit on the device");
-        u32 grid = (u32)(e->num_sms * best_bps);
-        u32 need_blocks = (n_work + best_wpb - 1) / best_wpb;
-        if (grid > need_blocks) grid = need_blocks;
-        /* bound the slab memory: at most ~60% of free HBM */
-        size_t free_b = 0, total_b = 0;
-        CK(cudaMemGetInfo(&free_b, &total_b));
-        size_t budget = (size_t)((double)(free_b + e->cap_slabs) * 0.6);
-        u64 warps_total = (u64)grid * best_wpb;
-        if (warps_total * L.slab_bytes > budget) {
-            u64 fit = budget / L.slab_bytes;
-            if (fit < (u64)best_wpb) {
-                if (attempt == 0 || true) { /* cannot give even one block its slabs */
-                    if (fit == 0) return set_err(B200SAT_E_MEM, "an instance needs a slab larger than the free device memory");
-                    best_wpb = 1;
-                }
-            }
-            grid = (u32)std::max<u64>(1, fit / best_wpb);
-            warps_total = (u64)grid * best_wpb;
-        }
-        size_t smem = spw * best_wpb;
-        CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        {   /* give shared memory only what the resident blocks need; the rest of the 256 KB stays L1 for the slab traffic */
-            int per_sm = (int)((grid + e->num_sms - 1) / e->num_sms);
-            if (per_sm > best_bps) per_sm = best_bps;
-            size_t need = (size_t)per_sm * (smem + 1024);
-            int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
-            if (pct > 100) pct = 100;
-            cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        }
-        if ((rc = ensure(e->d_slabs, e->cap_slabs, (size_t)(warps_total * L.slab_bytes)))) return rc;
-        CK(cudaMemsetAsync(e->d_queue, 0, 8, stream));
-        KParams P;
-        memset(&P, 0, sizeof P);
-        P.inst_clause_off = e->d_ioff; P.clause_off = e->d_coff; P.lits = e->d_lits;
-        P.work = work; P.n_work = n_work; P.queue = e->d_queue;
-        P.results = e->d_results; P.models = e->d_models; P.model_stride = e->model_stride;
-        P.slabs = e->d_slabs; P.L = L; P.st = *s; P.kind = kind; P.flags = flags; P.attempt = attempt + 1;
-        CK(cudaEventRecord(e->ev0, stream));
-        fn<<<grid, best_wpb * 32, smem, stream>>>(P);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(e->ev1, stream));
-        u32 *next_list = e->d_work[attempt & 1];
-        collect_failed<<<(n_work + 255) / 256, 256, 0, stream>>>(e->d_results, work, n_work, next_list, e->d_queue + 1);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(e->h_pinned, e->d_queue + 1, 4, cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
+    b200sat_engine::Pending &pd = e->pend;
+    pd.st = *s; pd.kind = kind; pd.flags = flags; pd.stream = (cudaStream_t)stream_;
+    pd.attempt = 0; pd.n_work = e->n_inst; pd.work = nullptr; pd.total_ms = 0.f; pd.retried = false;
+    pd.tier_nv = pick_tier_nv(e->shape.max_vars, e->shape.max_clauses);
+    rc = launch_attempt(e);
+    if (rc) return rc;
+    pd.active = true;
+    return 0;
+}
+
+extern "C" int b200sat_engine_finish(b200sat_engine *e) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    b200sat_engine::Pending &pd = e->pend;
+    if (!pd.active) return 0;
+    CK(cudaSetDevice(e->device));
+    for (;;) {
+        CK(cudaStreamSynchronize(pd.stream));
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
-        total_ms += ms;
-        e->info.grid = grid; e->info.block = best_wpb * 32; e->info.smem_bytes = (u32)smem;
-        e->info.warps_total = (u32)warps_total; e->info.tier = L.tier; e->info.slab_bytes = L.slab_bytes;
-        e->info.launches += 1;
-        n_work = e->h_pinned[0];
-        work = next_list;
+        pd.total_ms += ms;
+        u32 left = e->h_pinned[0];
+        if (left == 0 || pd.attempt >= 4) { pd.n_work = left; break; }
+        pd.retried = true;
+        pd.n_work = left;
+        pd.work = pd.next_list;
+        pd.attempt++;
+        int rc = launch_attempt(e);
+        if (rc) { pd.active = false; return rc; }
     }
-    e->info.last_kernel_ms = total_ms;
-    if (n_work > 0) return set_err(B200SAT_E_MEM, "instances outgrew the largest slab (status in results)");
+    pd.active = false;
+    e->info.last_kernel_ms = pd.total_ms;
+    if (pd.n_work > 0) return set_err(B200SAT_E_MEM, "instances outgrew the largest slab (status in results)");
     return 0;
+}
+
+extern "C" int b200sat_engine_solve(b200sat_engine *e, const b200sat_settings *s, int kind, int flags, void *stream_) {
+    int rc = b200sat_engine_solve_async(e, s, kind, flags, stream_);
+    if (rc) return rc;
+    return b200sat_engine_finish(e);
 }
 
 extern "C" int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out) {
@@ -423,14 +513,60 @@ extern "C" int b200sat_engine_download_batch(b200sat_engine *e, uint32_t *ioff, 
     return 0;
 }
 
+static int enqueue_download(b200sat_engine *e, b200sat_result *results, uint8_t *models, uint32_t model_stride, cudaStream_t stream) {
+    if (e->n_inst == 0) return 0;
+    if (results) CK(cudaMemcpyAsync(results, e->d_results, (size_t)e->n_inst * sizeof(b200sat_result), cudaMemcpyDeviceToHost, stream));
+    if (models) {
+        if (model_stride == e->model_stride)
+            CK(cudaMemcpyAsync(models, e->d_models, (size_t)e->n_inst * model_stride, cudaMemcpyDeviceToHost, stream));
+        else
+            CK(cudaMemcpy2DAsync(models, model_stride, e->d_models, e->model_stride, std::min(model_stride, e->model_stride),
+                                 e->n_inst, cudaMemcpyDeviceToHost, stream));
+    }
+    return 0;
+}
+
+/* Asynchronous end-to-end call: H2D of the CSR batch, solve, D2H of results/models, all enqueued on
+ * `stream`.  The caller's buffers must stay valid (and should be page-locked) until
+ * b200sat_solve_batch_finish() returns.  Two engines on two streams pipeline consecutive batches. */
+extern "C" int b200sat_solve_batch_async(b200sat_engine *e, const b200sat_batch *batch, const b200sat_settings *s, int kind, int flags,
+                                         b200sat_result *results, uint8_t *models, uint32_t model_stride, void *stream_) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    int rc;
+    if (e->pend.active) { rc = b200sat_engine_finish(e); if (rc && rc != B200SAT_E_MEM) return rc; }
+    rc = b200sat_engine_upload(e, batch, stream_);
+    if (rc) return rc;
+    rc = b200sat_engine_solve_async(e, s, kind, flags, stream_);
+    if (rc) return rc;
+    e->pend.batch = true; e->pend.out_results = results; e->pend.out_models = models; e->pend.out_stride = model_stride;
+    return enqueue_download(e, results, models, model_stride, (cudaStream_t)stream_);
+}
+
+extern "C" int b200sat_solve_batch_finish(b200sat_engine *e) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    b200sat_engine::Pending &pd = e->pend;
+    const bool was_batch = pd.batch;
+    pd.batch = false;
+    int src = b200sat_engine_finish(e);
+    if (src && src != B200SAT_E_MEM) return src;
+    if (was_batch) {
+        if (pd.retried) { /* results changed after the first download: fetch them again */
+            int rc = enqueue_download(e, pd.out_results, pd.out_models, pd.out_stride, pd.stream);
+            if (rc) return rc;
+        }
+        CK(cudaStreamSynchronize(pd.stream));
+        if (pd.out_models && pd.out_stride > e->model_stride)
+            for (u32 i = 0; i < e->n_inst; i++)
+                memset(pd.out_models + (size_t)i * pd.out_stride + e->model_stride, 2, pd.out_stride - e->model_stride);
+    }
+    return src;
+}
+
 extern "C" int b200sat_solve_batch(b200sat_engine *e, const b200sat_batch *batch, const b200sat_settings *s, int kind, int flags,
                                    b200sat_result *results, uint8_t *models, uint32_t model_stride) {
-    int rc = b200sat_engine_upload(e, batch, nullptr);
+    int rc = b200sat_solve_batch_async(e, batch, s, kind, flags, results, models, model_stride, nullptr);
     if (rc) return rc;
-    int src = b200sat_engine_solve(e, s, kind, flags, nullptr);
-    if (src && src != B200SAT_E_MEM) return src;
-    rc = b200sat_engine_download(e, results, models, model_stride, nullptr);
-    return rc ? rc : src;
+    return b200sat_solve_batch_finish(e);
 }
 
 /* ------------------------------------------------------------------ host: single-solver mirror of `trait Solver` */
