@@ -154,6 +154,8 @@ typedef struct b200sat_result {
     uint64_t stats[8];         /* b200sat_stats order                                   */
     uint64_t traffic[8];       /* visited, kept, deref, tail, moves, implied, analysis words, learnt words */
     uint64_t trace_hash;       /* FNV-1a over conflicts when B200SAT_F_TRACE_HASH       */
+    uint32_t exported;         /* portfolio: clauses this replica appended to its ring  */
+    uint32_t imported;         /* portfolio: clauses this replica took from the rings   */
 } b200sat_result;
 
 typedef struct b200sat_engine b200sat_engine;
@@ -200,6 +202,27 @@ int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out);
 int b200sat_solve_batch(b200sat_engine *e, const b200sat_batch *batch, const b200sat_settings *s,
                         int kind, int flags, b200sat_result *results, uint8_t *models,
                         uint32_t model_stride);
+
+/* ------------------------------------------------------------------ portfolio (new: SURVEY.md 8e)
+ * Many seed/heuristic-diversified replicas of ONE instance (instance 0 of the resident batch), one
+ * warp each.  Replicas exchange short learnt clauses (units, binaries, LBD <= 2) through one
+ * append-only ring per GPU; rings of other GPUs are mapped with CUDA IPC and read/written over
+ * NVLink P2P.  The first replica that finishes raises a `done` word in every ring and the others
+ * stop at their next conflict (the Budget / interrupt analogue, budget.rs:5-34).  Replica 0 keeps the
+ * base settings: with sharing off its trace is bit-exact the single-instance one. */
+enum { B200SAT_PF_SHARE = 1, B200SAT_PF_IGNORE_DONE = 2 };
+/* settings of global replica `replica` derived from `base` (replica 0 = base) -- SURVEY.md T19 */
+void b200sat_diversify(const b200sat_settings *base, uint32_t replica, b200sat_settings *out);
+int  b200sat_engine_ring_create(b200sat_engine *e, uint32_t payload_words, uint32_t n_rings, uint32_t my_slot);
+int  b200sat_engine_ring_reset(b200sat_engine *e, void *stream);            /* zero the local ring */
+int  b200sat_engine_ring_ipc_handle(b200sat_engine *e, uint8_t handle[64]); /* cudaIpcMemHandle_t of the local ring */
+int  b200sat_engine_ring_open_peer(b200sat_engine *e, uint32_t slot, const uint8_t handle[64]);
+/* Launch n_replicas replicas (global ids replica_base ...) of instance 0 of the resident batch (CoreSolver).
+ * Results (one b200sat_result + model per REPLICA) are fetched with b200sat_engine_download_replicas. */
+int  b200sat_portfolio_solve(b200sat_engine *e, const b200sat_settings *base, uint32_t n_replicas,
+                             uint32_t replica_base, uint32_t share_flags, int flags, void *stream);
+int  b200sat_engine_download_replicas(b200sat_engine *e, b200sat_result *results, uint8_t *models,
+                                      uint32_t model_stride, void *stream);
 
 /* Asynchronous end-to-end form: H2D + solve + D2H enqueued on `stream`; buffers must stay valid
  * (and should be page-locked) until b200sat_solve_batch_finish() returns. */

@@ -67,6 +67,7 @@ class Result(C.Structure):
         ("n_clauses_ingest", C.c_uint32), ("n_clauses_pre", C.c_uint32), ("eliminated_vars", C.c_uint32),
         ("pre_ok", C.c_uint32), ("attempts", C.c_uint32),
         ("stats", C.c_uint64 * 8), ("traffic", C.c_uint64 * 8), ("trace_hash", C.c_uint64),
+        ("exported", C.c_uint32), ("imported", C.c_uint32),
     ]
 
     def stats_dict(self):
@@ -76,7 +77,8 @@ class Result(C.Structure):
 RESULT_DTYPE = np.dtype([
     ("verdict", np.int32), ("status", np.int32), ("n_vars", np.uint32), ("n_clauses_ingest", np.uint32),
     ("n_clauses_pre", np.uint32), ("eliminated_vars", np.uint32), ("pre_ok", np.uint32), ("attempts", np.uint32),
-    ("stats", np.uint64, (8,)), ("traffic", np.uint64, (8,)), ("trace_hash", np.uint64)])
+    ("stats", np.uint64, (8,)), ("traffic", np.uint64, (8,)), ("trace_hash", np.uint64),
+    ("exported", np.uint32), ("imported", np.uint32)])
 assert RESULT_DTYPE.itemsize == C.sizeof(Result)
 
 
@@ -108,7 +110,10 @@ ABI_SYMBOLS = (
     "b200sat_engine_batch_dims", "b200sat_engine_download_batch", "b200sat_engine_configure",
     "b200sat_engine_launch_info", "b200sat_solve_batch",
     "b200sat_engine_solve_async", "b200sat_engine_finish", "b200sat_solve_batch_async", "b200sat_solve_batch_finish",
+    "b200sat_diversify", "b200sat_engine_ring_create", "b200sat_engine_ring_reset", "b200sat_engine_ring_ipc_handle",
+    "b200sat_engine_ring_open_peer", "b200sat_portfolio_solve", "b200sat_engine_download_replicas",
 )
+PF_SHARE, PF_IGNORE_DONE = 1, 2
 
 _lib = None
 
@@ -160,6 +165,14 @@ def lib():
     L.b200sat_solve_batch_async.argtypes = [vp, C.POINTER(BatchStruct), C.POINTER(Settings), C.c_int, C.c_int,
                                             vp, u8p, C.c_uint32, vp]
     L.b200sat_solve_batch_finish.argtypes = [vp]
+    L.b200sat_diversify.argtypes = [C.POINTER(Settings), C.c_uint32, C.POINTER(Settings)]
+    L.b200sat_diversify.restype = None
+    L.b200sat_engine_ring_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.b200sat_engine_ring_reset.argtypes = [vp, vp]
+    L.b200sat_engine_ring_ipc_handle.argtypes = [vp, u8p]
+    L.b200sat_engine_ring_open_peer.argtypes = [vp, C.c_uint32, u8p]
+    L.b200sat_portfolio_solve.argtypes = [vp, C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp]
+    L.b200sat_engine_download_replicas.argtypes = [vp, vp, u8p, C.c_uint32, vp]
     _lib = L
     return L
 
@@ -340,6 +353,37 @@ class Engine:
     def solve_batch_finish(self):
         return _check(lib().b200sat_solve_batch_finish(self._e), allow=(E_MEM,))
 
+    # ---- portfolio mode
+    def ring_create(self, payload_words=1 << 20, n_rings=1, my_slot=0):
+        _check(lib().b200sat_engine_ring_create(self._e, payload_words, n_rings, my_slot))
+
+    def ring_reset(self, stream=None):
+        _check(lib().b200sat_engine_ring_reset(self._e, stream))
+
+    def ring_ipc_handle(self):
+        buf = (C.c_uint8 * 64)()
+        _check(lib().b200sat_engine_ring_ipc_handle(self._e, buf))
+        return bytes(buf)
+
+    def ring_open_peer(self, slot, handle):
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        _check(lib().b200sat_engine_ring_open_peer(self._e, slot, buf))
+
+    def portfolio_solve(self, n_replicas, replica_base=0, share=PF_SHARE, settings=None, flags=0, stream=None,
+                        model_stride=None):
+        """Run n_replicas diversified replicas of instance 0 of the resident batch; returns (results, models)
+        with one row per replica.  The winner is any replica whose verdict is not INTERRUPTED."""
+        s = settings if settings is not None else default_settings()
+        _check(lib().b200sat_portfolio_solve(self._e, C.byref(s), n_replicas, replica_base, share, flags, stream))
+        res = np.zeros(n_replicas, dtype=RESULT_DTYPE)
+        models = None
+        mp = None
+        if model_stride:
+            models = np.full((n_replicas, model_stride), 2, dtype=np.uint8)
+            mp = models.ctypes.data_as(C.POINTER(C.c_uint8))
+        _check(lib().b200sat_engine_download_replicas(self._e, res.ctypes.data, mp, model_stride or 0, stream))
+        return res, models
+
     def dims(self):
         n, nc, nl = C.c_uint32(), C.c_uint64(), C.c_uint64()
         _check(lib().b200sat_engine_batch_dims(self._e, C.byref(n), C.byref(nc), C.byref(nl)))
@@ -388,6 +432,13 @@ class Engine:
         _check(lib().b200sat_solve_batch(self._e, C.byref(b), C.byref(s), kind, flags, res.ctypes.data, mp,
                                          model_stride), allow=(E_MEM,))
         return res, models
+
+
+def diversify(base, replica):
+    """Settings of global replica `replica` (b200sat_diversify)."""
+    out = Settings()
+    lib().b200sat_diversify(C.byref(base), replica, C.byref(out))
+    return out
 
 
 def shard_range(n_items, rank, world_size):

@@ -90,7 +90,7 @@ __global__ void collect_failed(const b200sat_result *results, const u32 *work, u
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_work) return;
     u32 inst = work ? work[i] : i;
-    if (results[inst].status != B200SAT_OK) out_list[atomicAdd(out_count, 1u)] = inst;
+    if (results[inst].status < 0) out_list[atomicAdd(out_count, 1u)] = inst; /* > 0: cancelled portfolio replica */
 }
 
 /* ------------------------------------------------------------------ host: errors */
@@ -149,6 +149,13 @@ struct b200sat_engine {
     void *h_stage = nullptr;     /* pinned staging for uploads */
     size_t cap_stage = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    /* portfolio: clause-exchange rings (slot my_ring is ours, the others are peer mappings) */
+    u32 *rings[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ring_is_peer[8] = {false, false, false, false, false, false, false, false};
+    u32 n_rings = 0, my_ring = 0, ring_words = 0;
+    b200sat_settings *d_replica_settings = nullptr;
+    size_t cap_replica_settings = 0;
+    u32 n_replicas = 0;
     /* in-flight asynchronous solve */
     struct Pending {
         bool active = false, retried = false;
@@ -163,6 +170,7 @@ struct b200sat_engine {
         uint8_t *out_models = nullptr;
         uint32_t out_stride = 0;
         bool batch = false;
+        u32 portfolio = 0, replica_base = 0, share = 0;
     } pend;
     /* tunables */
     int cfg_wpb = 0, cfg_bps = 0;
@@ -206,6 +214,9 @@ extern "C" void b200sat_engine_destroy(b200sat_engine *e) {
     cudaSetDevice(e->device);
     cudaFree(e->d_ioff); cudaFree(e->d_coff); cudaFree(e->d_lits); cudaFree(e->d_results); cudaFree(e->d_models);
     cudaFree(e->d_slabs); cudaFree(e->d_queue); cudaFree(e->d_work[0]); cudaFree(e->d_work[1]);
+    cudaFree(e->d_replica_settings);
+    for (u32 r = 0; r < 8; r++)
+        if (e->rings[r]) { if (e->ring_is_peer[r]) cudaIpcCloseMemHandle(e->rings[r]); else cudaFree(e->rings[r]); }
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -403,6 +414,10 @@ static int launch_attempt(b200sat_engine *e) {
     P.work = pd.work; P.n_work = pd.n_work; P.queue = e->d_queue;
     P.results = e->d_results; P.models = e->d_models; P.model_stride = e->model_stride;
     P.slabs = e->d_slabs; P.L = L; P.st = pd.st; P.kind = pd.kind; P.flags = pd.flags; P.attempt = pd.attempt + 1;
+    P.portfolio = pd.portfolio; P.replica_base = pd.replica_base; P.share = pd.share;
+    P.n_rings = e->n_rings; P.my_ring = e->my_ring; P.ring_words = e->ring_words;
+    for (u32 r = 0; r < 8; r++) P.rings[r] = e->rings[r];
+    P.replica_settings = e->d_replica_settings;
     CK(cudaEventRecord(e->ev0, stream));
     fn<<<grid, best_wpb * 32, smem, stream>>>(P);
     CK(cudaGetLastError());
@@ -431,6 +446,7 @@ extern "C" int b200sat_engine_solve_async(b200sat_engine *e, const b200sat_setti
     b200sat_engine::Pending &pd = e->pend;
     pd.st = *s; pd.kind = kind; pd.flags = flags; pd.stream = (cudaStream_t)stream_;
     pd.attempt = 0; pd.n_work = e->n_inst; pd.work = nullptr; pd.total_ms = 0.f; pd.retried = false;
+    pd.portfolio = 0; pd.replica_base = 0; pd.share = 0;
     pd.tier_nv = pick_tier_nv(e->shape.max_vars, e->shape.max_clauses);
     rc = launch_attempt(e);
     if (rc) return rc;
@@ -567,6 +583,105 @@ extern "C" int b200sat_solve_batch(b200sat_engine *e, const b200sat_batch *batch
     int rc = b200sat_solve_batch_async(e, batch, s, kind, flags, results, models, model_stride, nullptr);
     if (rc) return rc;
     return b200sat_solve_batch_finish(e);
+}
+
+/* ------------------------------------------------------------------ host: portfolio */
+extern "C" void b200sat_diversify(const b200sat_settings *base, uint32_t g, b200sat_settings *out) {
+    diversify_settings(base, g, out);
+}
+
+extern "C" int b200sat_engine_ring_create(b200sat_engine *e, uint32_t payload_words, uint32_t n_rings, uint32_t my_slot) {
+    if (!e || n_rings == 0 || n_rings > 8 || my_slot >= n_rings) return set_err(B200SAT_E_ARG, "bad ring arguments");
+    CK(cudaSetDevice(e->device));
+    if (e->rings[my_slot] && !e->ring_is_peer[my_slot]) cudaFree(e->rings[my_slot]);
+    e->rings[my_slot] = nullptr;
+    CK(cudaMalloc((void **)&e->rings[my_slot], ((size_t)payload_words + RING_PAYLOAD) * 4));
+    CK(cudaMemset(e->rings[my_slot], 0, ((size_t)payload_words + RING_PAYLOAD) * 4));
+    e->ring_is_peer[my_slot] = false;
+    e->n_rings = n_rings; e->my_ring = my_slot; e->ring_words = payload_words;
+    return 0;
+}
+extern "C" int b200sat_engine_ring_reset(b200sat_engine *e, void *stream) {
+    if (!e || !e->rings[e->my_ring]) return set_err(B200SAT_E_ARG, "no ring");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemsetAsync(e->rings[e->my_ring], 0, ((size_t)e->ring_words + RING_PAYLOAD) * 4, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200sat_engine_ring_ipc_handle(b200sat_engine *e, uint8_t handle[64]) {
+    if (!e || !e->rings[e->my_ring]) return set_err(B200SAT_E_ARG, "no ring");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, e->rings[e->my_ring]));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+extern "C" int b200sat_engine_ring_open_peer(b200sat_engine *e, uint32_t slot, const uint8_t handle[64]) {
+    if (!e || slot >= e->n_rings || slot == e->my_ring) return set_err(B200SAT_E_ARG, "bad peer slot");
+    CK(cudaSetDevice(e->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    e->rings[slot] = (u32 *)p;
+    e->ring_is_peer[slot] = true;
+    return 0;
+}
+
+extern "C" int b200sat_portfolio_solve(b200sat_engine *e, const b200sat_settings *base, uint32_t n_replicas, uint32_t replica_base,
+                                       uint32_t share_flags, int flags, void *stream_) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    int rc = check_settings(base, B200SAT_CORE);
+    if (rc) return rc;
+    if (e->n_inst < 1 || n_replicas == 0) return set_err(B200SAT_E_ARG, "portfolio needs a resident instance and >= 1 replica");
+    if (e->pend.active) { rc = b200sat_engine_finish(e); if (rc && rc != B200SAT_E_MEM) return rc; }
+    CK(cudaSetDevice(e->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (e->n_rings == 0) { /* single-GPU portfolio without an explicit ring: make a private one */
+        if ((rc = b200sat_engine_ring_create(e, 1u << 20, 1, 0))) return rc;
+    }
+    for (u32 r = 0; r < e->n_rings; r++) if (!e->rings[r]) return set_err(B200SAT_E_ARG, "a ring slot is not mapped");
+    std::vector<b200sat_settings> hs(n_replicas);
+    for (u32 i = 0; i < n_replicas; i++) b200sat_diversify(base, replica_base + i, &hs[i]);
+    if ((rc = ensure(e->d_replica_settings, e->cap_replica_settings, (size_t)n_replicas))) return rc;
+    CK(cudaMemcpyAsync(e->d_replica_settings, hs.data(), n_replicas * sizeof(b200sat_settings), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream)); /* hs is a local */
+    /* outputs are per replica */
+    if ((rc = ensure(e->d_results, e->cap_results, (size_t)std::max(n_replicas, e->n_inst)))) return rc;
+    if ((rc = ensure(e->d_models, e->cap_models, (size_t)std::max(n_replicas, e->n_inst) * e->model_stride))) return rc;
+    if ((rc = ensure(e->d_work[0], e->cap_work, (size_t)std::max(n_replicas, e->n_inst)))) return rc;
+    if ((rc = ensure(e->d_work[1], e->cap_work1, (size_t)std::max(n_replicas, e->n_inst)))) return rc;
+    e->n_replicas = n_replicas;
+    e->info.launches = 0;
+    e->info.last_kernel_ms = 0.f;
+    b200sat_engine::Pending &pd = e->pend;
+    pd.st = *base; pd.kind = B200SAT_CORE; pd.flags = flags; pd.stream = stream;
+    pd.attempt = 0; pd.n_work = n_replicas; pd.work = nullptr; pd.total_ms = 0.f; pd.retried = false; pd.batch = false;
+    pd.portfolio = n_replicas; pd.replica_base = replica_base; pd.share = share_flags;
+    /* the slab is sized for the one instance; BatchShape of a 1-instance batch is that instance */
+    pd.tier_nv = pick_tier_nv(e->shape.max_vars, e->shape.max_clauses);
+    rc = launch_attempt(e);
+    if (rc) return rc;
+    pd.active = true;
+    /* no larger-slab retry ladder in portfolio mode: a replica that runs out of memory just drops out */
+    CK(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->info.last_kernel_ms = ms;
+    pd.active = false;
+    return 0;
+}
+
+extern "C" int b200sat_engine_download_replicas(b200sat_engine *e, b200sat_result *results, uint8_t *models, uint32_t model_stride,
+                                                void *stream_) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(cudaSetDevice(e->device));
+    if (e->n_replicas == 0) return 0;
+    if (results) CK(cudaMemcpyAsync(results, e->d_results, (size_t)e->n_replicas * sizeof(b200sat_result), cudaMemcpyDeviceToHost, stream));
+    if (models) CK(cudaMemcpy2DAsync(models, model_stride, e->d_models, e->model_stride, std::min(model_stride, e->model_stride),
+                                     e->n_replicas, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
 }
 
 /* ------------------------------------------------------------------ host: single-solver mirror of `trait Solver` */

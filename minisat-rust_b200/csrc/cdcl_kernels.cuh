@@ -33,6 +33,12 @@ template <bool SIMP, class VT, bool COUNT> __device__ __forceinline__ void warp_
         w = __shfl_sync(FULL_MASK, w, 0);
         if (w >= P.n_work) break;
         u32 inst = P.work ? P.work[w] : w;
+        S.res_index = inst;
+        if (P.portfolio) { /* replica w of instance 0 with its own diversified settings */
+            S.res_index = w;
+            S.stp = P.replica_settings + w;
+            inst = 0;
+        }
 #if B200SAT_KERNEL_TU_SIMP
         if (SIMP) { solve_simp(S, inst); continue; }
 #endif

@@ -61,5 +61,26 @@ static inline Layout plan_layout(const BatchShape &sh, int tier_nv, int kind, u3
     return L;
 }
 
+/* settings of global replica g of a portfolio (the seed alone changes nothing with the
+ * default settings, so the diversification switches randomness on and varies decay / restart / phase) */
+static inline void diversify_settings(const b200sat_settings *base, u32 g, b200sat_settings *out) {
+    *out = *base;
+    if (g == 0) return; /* replica 0 = the reference configuration */
+    double seed = base->random_seed + 7919.0 * (double)g;
+    while (seed >= 2147483646.0) seed -= 2147483646.0;
+    out->random_seed = seed < 1.0 ? 1.0 : seed;
+    switch (g % 4) {
+    case 1: out->random_var_freq = 0.02; break;
+    case 2: out->rnd_init_act = 1; break;
+    case 3: out->random_var_freq = 0.05; out->rnd_init_act = 1; break;
+    default: out->rnd_init_act = 1; out->random_var_freq = 0.01; break;
+    }
+    static const double decays[4] = {0.0, 0.92, 0.88, 0.97};
+    static const double first_scale[4] = {1.0, 0.5, 2.0, 0.3};
+    if ((g / 4) % 4 != 0) out->var_decay = decays[(g / 4) % 4];
+    out->restart_first = base->restart_first * first_scale[(g / 16) % 4];
+    if ((g / 64) % 2 == 1) out->phase_saving = 1;
+}
+
 } // namespace b200sat
 #endif

@@ -131,7 +131,20 @@ struct KParams {
     i32 kind;
     i32 flags;
     u32 attempt;
+    /* portfolio mode: every work item is a diversified replica of instance 0 */
+    u32 portfolio;            /* 0 = batch mode, else number of replicas launched on this GPU          */
+    u32 replica_base;         /* global index of this GPU's first replica                              */
+    u32 share;                /* PF_SHARE: exchange short learnts, PF_IGNORE_DONE: run every replica out */
+    u32 n_rings, my_ring;     /* clause-exchange rings, one per GPU (peer-mapped over NVLink)          */
+    u32 ring_words;           /* payload capacity of one ring                                          */
+    u32 *rings[8];
+    const b200sat_settings *replica_settings; /* [portfolio] diversified settings                      */
 };
+
+enum : u32 { PF_SHARE = 1, PF_IGNORE_DONE = 2 };
+/* ring header words */
+enum : u32 { RING_HEAD = 0, RING_DONE = 1, RING_EXPORTS = 2, RING_PAYLOAD = 16 };
+static const u32 ST_CANCELLED = 20;
 
 } // namespace b200sat
 #endif

@@ -52,6 +52,7 @@ struct Scal {
     i32 size_adjust_cnt;
     u32 simp_db_assigns, simp_db_assigns_set, status, dec_vars, heap_n, cur_arena, cur_wpool, eliminated_vars;
     u32 remove_satisfied, extra_clause_field, elim_n;
+    u32 ring_cursor[8], exported, imported;
 };
 
 /* ------------------------------------------------------------------ var-state tiers */
@@ -170,13 +171,16 @@ template <class VT, bool COUNT> struct WarpSolver {
     static const u32 VT_MAXLEN = VT::MAXLEN;
     VT V;
     const KParams &P;
+    const b200sat_settings *stp;   /* P.st, or this replica's diversified settings in portfolio mode */
+    u32 res_index;                 /* slot in results/models (= instance id, or replica id)          */
     u32 lane;
     u8 *slab;
     u32 *arena;   /* active arena half */
     uint2 *wpool; /* active watcher pool half */
     u32 nvars, trail_n, qhead, nlevels;
 
-    DEV WarpSolver(const KParams &p, u32 ln) : P(p), lane(ln) {}
+    DEV WarpSolver(const KParams &p, u32 ln) : P(p), stp(&p.st), res_index(0), lane(ln) {}
+    DEV const b200sat_settings &st() const { return *stp; }
 
     DEV Scal &sc() const { return V.sc(); }
     DEV u32 *learnts() const { return (u32 *)(slab + P.L.off_learnts); }
@@ -786,7 +790,7 @@ template <class VT, bool COUNT> struct WarpSolver {
         /* minimisation (conflict.rs:139-152); retain() visits position 0 too */
         u32 tcn = 0;
         u32 n_min = n_out;
-        const i32 ccmin = P.st.ccmin_mode;
+        const i32 ccmin = st().ccmin_mode;
         if (ccmin != 0) {
             u32 j = 0;
             for (u32 i = 0; i < n_out; i++) {
@@ -843,7 +847,7 @@ template <class VT, bool COUNT> struct WarpSolver {
             const u32 lt = lanemask_lt(lane);
             const u32 target = V.lim()[target_level];
             const u32 top = nlevels;
-            const i32 ps = P.st.phase_saving;
+            const i32 ps = st().phase_saving;
             u8 *vf = V.vflags();
             for (i32 hi = (i32)trail_n; hi > (i32)target; hi -= 32) {
                 i32 k = hi - 1 - (i32)lane;
@@ -883,9 +887,9 @@ template <class VT, bool COUNT> struct WarpSolver {
         if (lane == 0) {
             bool got = false;
             u32 v = 0;
-            const bool use_rand = (P.st.random_var_freq != 0.0) || P.st.rnd_pol;
+            const bool use_rand = (st().random_var_freq != 0.0) || st().rnd_pol;
             if (use_rand) {
-                if (drand() < P.st.random_var_freq && sc().heap_n > 0) {
+                if (drand() < st().random_var_freq && sc().heap_n > 0) {
                     v = V.heap()[(u32)(drand() * (double)sc().heap_n)];
                     if (V.assign()[v] == LB_UNDEF && (V.vflags()[v] & VF_DEC)) { sc().rnd_decisions++; got = true; }
                 }
@@ -900,7 +904,7 @@ template <class VT, bool COUNT> struct WarpSolver {
                 u32 f = V.vflags()[v];
                 u32 sign;
                 if (f & VF_UPOL_SET) sign = (f & VF_UPOL_VAL) ? 1 : 0;
-                else if (P.st.rnd_pol) sign = drand() < 0.5 ? 1 : 0;
+                else if (st().rnd_pol) sign = drand() < 0.5 ? 1 : 0;
                 else sign = (f & VF_POL) ? 1 : 0;
                 next = (v << 1) | sign;
             }
@@ -1151,7 +1155,7 @@ template <class VT, bool COUNT> struct WarpSolver {
     }
     /* search.rs:577-581 (+ a capacity-driven trigger of our own; GC is trace-neutral during search) */
     DEV void try_garbage_collect() {
-        bool ref_trigger = (double)sc().lc_wasted > (double)sc().lc_size * P.st.garbage_frac;
+        bool ref_trigger = (double)sc().lc_wasted > (double)sc().lc_size * st().garbage_frac;
         bool cap_trigger = sc().lc_wasted > 0 && sc().arena_top > (P.L.arena_cap / 4) * 3;
         if (ref_trigger || cap_trigger) garbage_collect();
     }
@@ -1192,6 +1196,88 @@ template <class VT, bool COUNT> struct WarpSolver {
         __syncwarp();
     }
 
+    /* -------------------------------------------------------------- portfolio: clause exchange + first-finisher cancel
+     * (no reference analogue).  Each GPU owns an append-only ring in its HBM:
+     * [head][done][...][payload: hdr = 0x80000000 | replica<<8 | len, lits...].  Replicas append short learnt
+     * clauses (units, binaries, LBD <= 2) and, at restart boundaries (ground level), import what the other
+     * replicas -- on this GPU and, through peer-mapped pointers over NVLink, on the other GPUs -- appended. */
+    DEV static u32 ld_vol(const u32 *p) { return *(const volatile u32 *)p; }
+    DEV bool cancelled() {
+        if (!P.portfolio || (P.share & PF_IGNORE_DONE)) return false;
+        return ld_vol(P.rings[P.my_ring] + RING_DONE) != 0;
+    }
+    DEV void announce_done() {
+        if (!P.portfolio) return;
+        if (lane == 0) {
+            __threadfence_system();
+            for (u32 r = 0; r < P.n_rings; r++) atomicCAS(P.rings[r] + RING_DONE, 0u, 1u + P.replica_base + res_index);
+        }
+        __syncwarp();
+    }
+    /* called with the learnt clause in ol()[0..n) BEFORE backtracking (levels still valid) */
+    DEV void export_clause(u32 n) {
+        if (n > 30) return;
+        const u32 *out = ol();
+        u32 lit = lane < n ? out[lane] : 0;
+        u32 lbd = 0;
+        if (n > 2) {
+            u32 lv = lane < n ? (u32)V.level()[lit >> 1] : (0x80000000u | lane);
+            u32 peers = __match_any_sync(FULL_MASK, lv);
+            lbd = __popc(__ballot_sync(FULL_MASK, lane < n && (u32)__ffs(peers) - 1 == lane));
+            if (lbd > 2) return;
+        }
+        u32 *ring = P.rings[P.my_ring];
+        u32 pos = 0;
+        if (lane == 0) pos = atomicAdd(ring + RING_HEAD, n + 1);
+        pos = bcast(pos);
+        if (pos + n + 1 > P.ring_words) return; /* ring full: stop exporting */
+        u32 *pay = ring + RING_PAYLOAD + pos;
+        if (lane < n) pay[1 + lane] = lit;
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+            *(volatile u32 *)pay = 0x80000000u | (((P.replica_base + res_index) & 0x7FFFFFu) << 8) | n;
+            sc().exported++;
+        }
+        __syncwarp();
+    }
+    /* at ground level with an empty propagation queue; false = the formula is UNSAT */
+    DEV bool import_clauses() {
+        const u32 me = (P.replica_base + res_index) & 0x7FFFFFu;
+        for (u32 r = 0; r < P.n_rings; r++) {
+            const u32 *ring = P.rings[r];
+            u32 cur = sc().ring_cursor[r];
+            u32 got = 0;
+            for (;;) {
+                if (cur + 1 > P.ring_words) break;
+                u32 hdr = ld_vol(ring + RING_PAYLOAD + cur);
+                if (!(hdr & 0x80000000u)) break; /* not committed yet */
+                u32 n = hdr & 0xFF;
+                u32 src = (hdr >> 8) & 0x7FFFFFu;
+                if (src != me) {
+                    __threadfence();
+                    u32 *t = tmp();
+                    if (lane < n) t[lane] = ld_vol(ring + RING_PAYLOAD + cur + 1 + lane);
+                    __syncwarp();
+                    u32 cr = CREF_UNDEF;
+                    u32 res = add_clause(t, n, cr, true);
+                    if (failed()) return true;
+                    got++;
+                    if (res == 0) { /* the imported clause is falsified at ground level: UNSAT */
+                        if (lane == 0) sc().imported += got;
+                        __syncwarp();
+                        return false;
+                    }
+                }
+                cur += n + 1;
+            }
+            __syncwarp();
+            if (lane == 0) { sc().ring_cursor[r] = cur; sc().imported += got; }
+            __syncwarp();
+        }
+        return true;
+    }
+
     /* -------------------------------------------------------------- conflict handling: search.rs:263-304,503-517 */
     /* returns false on a ground-level conflict (UNSAT) or on abort (check failed()) */
     DEV bool propagate_learn_backtrack() {
@@ -1204,6 +1290,10 @@ template <class VT, bool COUNT> struct WarpSolver {
             u32 bt;
             u32 n = analyze(confl, bt);
             if (failed()) return false;
+            if (P.portfolio) {
+                if (P.share & PF_SHARE) export_clause(n);
+                if (cancelled()) { fail(ST_CANCELLED); return false; }
+            }
             cancel_until(bt);
             u32 reason = CREF_UNDEF;
             const u32 *out = ol();
@@ -1230,9 +1320,9 @@ template <class VT, bool COUNT> struct WarpSolver {
                 /* LearningGuard::bump search.rs:96-110 */
                 sc().size_adjust_cnt -= 1;
                 if (sc().size_adjust_cnt == 0) {
-                    sc().size_adjust_confl *= P.st.size_adjust_inc;
+                    sc().size_adjust_confl *= st().size_adjust_inc;
                     sc().size_adjust_cnt = (i32)sc().size_adjust_confl;
-                    sc().max_learnts *= P.st.size_inc;
+                    sc().max_learnts *= st().size_inc;
                 }
             }
             __syncwarp();
@@ -1279,19 +1369,26 @@ template <class VT, bool COUNT> struct WarpSolver {
     DEV u32 search() {
         if (lane == 0) {
             sc().solves++;
-            double ml = (double)sc().num_clauses * P.st.size_factor;       /* LearningGuard::reset search.rs:89-94 */
-            double lo = (double)P.st.min_learnts_lim;
+            double ml = (double)sc().num_clauses * st().size_factor;       /* LearningGuard::reset search.rs:89-94 */
+            double lo = (double)st().min_learnts_lim;
             sc().max_learnts = ml > lo ? ml : lo;
-            sc().size_adjust_confl = (double)P.st.size_adjust_start_confl;
-            sc().size_adjust_cnt = P.st.size_adjust_start_confl;
+            sc().size_adjust_confl = (double)st().size_adjust_start_confl;
+            sc().size_adjust_cnt = st().size_adjust_start_confl;
         }
         __syncwarp();
         u32 curr_restarts = 0;
         for (;;) {
-            double base = P.st.luby_restart ? luby(P.st.restart_inc, curr_restarts) : powi(P.st.restart_inc, (i32)curr_restarts);
-            u64 ctg = (u64)(base * P.st.restart_first);
+            double base = st().luby_restart ? luby(st().restart_inc, curr_restarts) : powi(st().restart_inc, (i32)curr_restarts);
+            u64 ctg = (u64)(base * st().restart_first);
             u32 r = search_loop(ctg);
-            if (r == LR_RESTART) { curr_restarts++; continue; }
+            if (r == LR_RESTART) {
+                curr_restarts++;
+                if (P.portfolio && (P.share & PF_SHARE)) {
+                    if (!import_clauses()) return LR_UNSAT;
+                    if (failed()) return LR_ABORT;
+                }
+                continue;
+            }
             return r;
         }
     }
@@ -1314,13 +1411,15 @@ template <class VT, bool COUNT> struct WarpSolver {
             s.clauses_literals = s.learnts_literals = s.lc_size = s.lc_wasted = s.simp_db_props = 0;
             s.trace_hash = 1469598103934665603ull;
             s.var_inc = 1.0; s.cla_inc = 1.0; s.max_learnts = 0.0; s.size_adjust_confl = 0.0;
-            s.seed = P.st.random_seed;
-            s.inv_var_decay = 1.0 / P.st.var_decay;
-            s.inv_cla_decay = 1.0 / P.st.clause_decay;
+            s.seed = st().random_seed;
+            s.inv_var_decay = 1.0 / st().var_decay;
+            s.inv_cla_decay = 1.0 / st().clause_decay;
             s.arena_top = 0; s.wpool_top = 0; s.n_learnts = 0; s.n_clauses = 0; s.num_clauses = 0; s.num_learnts = 0;
             s.size_adjust_cnt = 0; s.simp_db_assigns = 0; s.simp_db_assigns_set = 0; s.status = ST_OK;
             s.dec_vars = nvars; s.heap_n = nvars; s.cur_arena = 0; s.cur_wpool = 0; s.eliminated_vars = 0;
-            s.remove_satisfied = P.st.remove_satisfied; s.extra_clause_field = 0;
+            s.remove_satisfied = st().remove_satisfied; s.extra_clause_field = 0; s.elim_n = 0;
+            for (int i = 0; i < 8; i++) s.ring_cursor[i] = 0;
+            s.exported = 0; s.imported = 0;
         }
         arena = arena_half(0);
         wpool = wpool_half(0);
@@ -1339,7 +1438,7 @@ template <class VT, bool COUNT> struct WarpSolver {
         }
         if (lane == 0) V.lim()[0] = 0;
         __syncwarp();
-        if (P.st.rnd_init_act) { /* decision_heuristic.rs:70-88: activity drawn at var creation, heap insert in creation order */
+        if (st().rnd_init_act) { /* decision_heuristic.rs:70-88: activity drawn at var creation, heap insert in creation order */
             if (lane == 0) {
                 sc().heap_n = 0;
                 for (u32 v = 0; v < nvars; v++) {
@@ -1376,7 +1475,7 @@ template <class VT, bool COUNT> struct WarpSolver {
     }
 
     /* Searcher::add_clause search.rs:342-386.  0 = UNSAT, 1 = consumed, 2 = added (cref in out_cr) */
-    DEV u32 add_clause(const u32 *src, u32 len, u32 &out_cr) {
+    DEV u32 add_clause(const u32 *src, u32 len, u32 &out_cr, bool as_learnt = false) {
         u32 nk = 0;
         bool consumed = false;
         u32 cr = CREF_UNDEF;
@@ -1408,7 +1507,7 @@ template <class VT, bool COUNT> struct WarpSolver {
                 u32 o = __shfl_sync(FULL_MASK, key, j);
                 if (o < key) rank++;
             }
-            cr = alloc_clause(nk, sc().extra_clause_field ? (u32)H_EXTRA : 0u);
+            cr = alloc_clause(nk, as_learnt ? (u32)(H_LEARNT | H_EXTRA) : (sc().extra_clause_field ? (u32)H_EXTRA : 0u));
             if (cr == CREF_UNDEF) return 0;
             if (kept) arena[cr + 1 + rank] = lit;
         } else {
@@ -1455,6 +1554,21 @@ template <class VT, bool COUNT> struct WarpSolver {
             }
         }
         __syncwarp();
+        if (as_learnt) { /* imported clause: stored like a learnt one (clause_db.rs:93-100) */
+            if (sc().n_learnts >= P.L.learnts_cap) { fail(ST_MEM_ARENA); return 0; }
+            if (lane == 0) {
+                arena[cr + 1 + nk] = f2u(0.0f);
+                learnts()[sc().n_learnts] = cr;
+                sc().n_learnts++;
+                sc().num_learnts++;
+                sc().learnts_literals += nk;
+            }
+            __syncwarp();
+            bump_cla(cr, nk);
+            if (!attach(cr)) return 0;
+            out_cr = cr;
+            return 2;
+        }
         if (sc().extra_clause_field) { /* clause_db.rs:78-91 + formula/util.rs:5-11 */
             u32 a = 0;
             for (u32 i = lane; i < nk; i += 32) a |= 1u << ((arena[cr + 1 + i] >> 1) & 31);
@@ -1511,15 +1625,17 @@ template <class VT, bool COUNT> struct WarpSolver {
         }
         __syncwarp();
         write_result(inst, verdict, n_ingest, n_pre, pre_ok);
+        if (P.portfolio && !failed() && verdict != B200SAT_INTERRUPTED) announce_done();
     }
 
     DEV void write_result(u32 inst, i32 verdict, u32 n_ingest, u32 n_pre, u32 pre_ok) {
-        b200sat_result *r = P.results + inst;
+        (void)inst;
+        b200sat_result *r = P.results + res_index;
         const Scal &s = sc();
         bool zero = !pre_ok && (P.flags & B200SAT_F_ZERO_STATS_ON_PRE_UNSAT);
         if (lane == 0) {
             r->verdict = s.status == ST_OK ? verdict : B200SAT_INTERRUPTED;
-            r->status = s.status == ST_OK ? B200SAT_OK : -(i32)(100 + s.status);
+            r->status = s.status == ST_OK ? B200SAT_OK : (s.status == ST_CANCELLED ? 1 : -(i32)(100 + s.status));
             r->n_vars = nvars;
             r->n_clauses_ingest = n_ingest;
             r->n_clauses_pre = n_pre;
@@ -1536,9 +1652,11 @@ template <class VT, bool COUNT> struct WarpSolver {
             r->stats[7] = zero ? 0 : s.max_literals - s.tot_literals;
             for (int i = 0; i < 8; i++) r->traffic[i] = s.traffic[i];
             r->trace_hash = s.trace_hash;
+            r->exported = s.exported;
+            r->imported = s.imported;
         }
         if (P.models && s.status == ST_OK && verdict == B200SAT_SAT) { /* formula/util.rs:35-41 */
-            u8 *m = P.models + (size_t)inst * P.model_stride;
+            u8 *m = P.models + (size_t)res_index * P.model_stride;
             for (u32 v = lane; v < P.model_stride; v += 32) m[v] = v < nvars ? V.assign()[v] : (u8)LB_UNDEF;
         }
         __syncwarp();

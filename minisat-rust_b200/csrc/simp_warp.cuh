@@ -516,7 +516,7 @@ template <class WS, bool COUNT> struct SeqSimp {
 
     /* simplify.rs:423-523; false = Err */
     DEV bool backward_subsumption_check() {
-        const i32 sub_lim = S.P.st.subsumption_lim;
+        const i32 sub_lim = S.st().subsumption_lim;
         for (;;) {
             bool is_clause = false, have = false;
             u32 sub_cr = CREF_UNDEF, unit = 0;
@@ -628,8 +628,8 @@ template <class WS, bool COUNT> struct SeqSimp {
                 if ((l >> 1) == v) { if (l & 1) { nneg++; pn[SL.cand_cap - nneg] = cr; } else pn[npos++] = cr; break; }
             }
         }
-        const u64 max_resolvents = S.P.st.grow + npos + nneg;
-        const i32 cl_lim = S.P.st.clause_lim;
+        const u64 max_resolvents = S.st().grow + npos + nneg;
+        const i32 cl_lim = S.st().clause_lim;
         u32 nres = 0, rtop = 0;
         for (u32 a = 0; a < npos; a++)
             for (u32 b = 0; b < nneg; b++) {
@@ -739,7 +739,7 @@ template <class WS, bool COUNT> struct SeqSimp {
         S.arena = dst;
     }
     DEV void simp_try_gc() { /* simplify.rs:526-532 */
-        if ((double)sc().lc_wasted > (double)sc().lc_size * S.P.st.simp_garbage_frac) seq_gc(true);
+        if ((double)sc().lc_wasted > (double)sc().lc_size * S.st().simp_garbage_frac) seq_gc(true);
     }
 
     /* decision_heuristic.rs:146-156 (scalar) */
@@ -784,7 +784,7 @@ template <class WS, bool COUNT> struct SeqSimp {
         if ((sc().simp_db_assigns_set && sc().simp_db_assigns == S.trail_n) || sc().propagations < sc().simp_db_props) return;
         sc().n_learnts = seq_remove_satisfied_list(S.learnts(), sc().n_learnts);
         if (sc().remove_satisfied) sc().n_clauses = seq_remove_satisfied_list(S.clauses(), sc().n_clauses);
-        if ((double)sc().lc_wasted > (double)sc().lc_size * S.P.st.garbage_frac) seq_gc(false); /* search.rs:577-581 */
+        if ((double)sc().lc_wasted > (double)sc().lc_size * S.st().garbage_frac) seq_gc(false); /* search.rs:577-581 */
         seq_rebuild_order_heap();
         sc().simp_db_assigns_set = 1;
         sc().simp_db_assigns = S.trail_n;
@@ -801,7 +801,7 @@ template <class WS, bool COUNT> struct SeqSimp {
             u32 var;
             while (eh_pop(var)) {
                 if (is_elim(var) || S.V.assign()[var] != LB_UNDEF) continue;
-                if (S.P.st.use_elim && S.V.assign()[var] == LB_UNDEF && !is_frozen(var)) {
+                if (S.st().use_elim && S.V.assign()[var] == LB_UNDEF && !is_frozen(var)) {
                     if (!eliminate_var(var)) return false;
                     if (!backward_subsumption_check()) return false;
                 }
@@ -906,7 +906,7 @@ template <class VT, bool COUNT> DEV void solve_simp(WarpSolver<VT, COUNT> &S, u3
     }
     __syncwarp();
     S.write_result(inst, verdict, n_ingest, n_pre, pre_ok);
-    if (P.models && !S.failed() && verdict == B200SAT_SAT && P.st.extend_model) {
+    if (P.models && !S.failed() && verdict == B200SAT_SAT && S.st().extend_model) {
         if (S.lane == 0) {
             SeqSimp<WarpSolver<VT, COUNT>, COUNT> Z(S);
             Z.bind_ptrs();

@@ -112,9 +112,12 @@ struct Job {
     int tier_nv;
     u32 inst;
     bool count;
+    bool replica = false;
 };
 
 template <class VT, bool COUNT> void run_one(WarpSolver<VT, COUNT> &S, const Job *j) {
+    S.res_index = j->inst;
+    if (j->replica) { S.stp = j->P.replica_settings + j->inst; S.solve_core(0); return; }
 #ifdef B200SAT_HAVE_SIMP
     if (j->P.kind == B200SAT_SIMP) { solve_simp(S, j->inst); return; }
 #endif
@@ -139,6 +142,47 @@ template <bool COUNT> void entry_g(void *user, int lane) {
 } // namespace
 
 extern "C" {
+
+/* Portfolio mode under the emulator: the replicas of ONE instance run one after another (a replica sees the
+ * clauses earlier replicas exported to the shared ring).  share: PF_SHARE | PF_IGNORE_DONE bits. */
+int emu_portfolio(const uint32_t *clause_off, const uint32_t *lits, uint32_t n_clauses, const b200sat_settings *base,
+                  uint32_t n_replicas, uint32_t share, int flags, uint64_t sched_seed, b200sat_result *results,
+                  uint8_t *models, uint32_t model_stride) {
+    BatchShape sh = {0, n_clauses, clause_off[n_clauses], 0};
+    for (u32 c = 0; c < n_clauses; c++) { u32 len = clause_off[c + 1] - clause_off[c]; if (len > sh.max_clause_len) sh.max_clause_len = len; }
+    for (u32 k = 0; k < clause_off[n_clauses]; k++) if ((lits[k] >> 1) + 1 > sh.max_vars) sh.max_vars = (lits[k] >> 1) + 1;
+    int tier_nv = pick_tier_nv(sh.max_vars, sh.max_clauses);
+    Layout L = plan_layout(sh, tier_nv, B200SAT_CORE, 0, 0, 0);
+    std::vector<u64> slab((L.slab_bytes + 7) / 8 + 2);
+    std::vector<u64> smem(32 * 1024);
+    const u32 ring_words = 1u << 18;
+    std::vector<u32> ring(ring_words + RING_PAYLOAD, 0);
+    std::vector<b200sat_settings> rs(n_replicas);
+    for (u32 i = 0; i < n_replicas; i++) diversify_settings(base, i, &rs[i]);
+    u32 ioff[2] = {0, n_clauses};
+    u32 queue = 0;
+    Job j;
+    memset(&j.P, 0, sizeof j.P);
+    j.P.inst_clause_off = ioff; j.P.clause_off = clause_off; j.P.lits = lits;
+    j.P.n_work = n_replicas; j.P.queue = &queue; j.P.results = results; j.P.models = models; j.P.model_stride = model_stride;
+    j.P.slabs = (u8 *)slab.data(); j.P.L = L; j.P.st = *base; j.P.kind = B200SAT_CORE; j.P.flags = flags; j.P.attempt = 1;
+    j.P.portfolio = n_replicas; j.P.replica_base = 0; j.P.share = share; j.P.n_rings = 1; j.P.my_ring = 0;
+    j.P.ring_words = ring_words; j.P.rings[0] = ring.data(); j.P.replica_settings = rs.data();
+    j.smem = smem.data(); j.tier_nv = tier_nv;
+    for (u32 r = 0; r < n_replicas; r++) {
+        j.inst = r; /* replica id: entry_* maps it to instance 0 */
+        j.replica = true;
+        void (*fn)(void *, int) = nullptr;
+        switch (tier_nv) {
+        case 128: fn = entry_s<128, false>; break;
+        case 256: fn = entry_s<256, false>; break;
+        case 1024: fn = entry_s<1024, false>; break;
+        default: fn = entry_g<false>; break;
+        }
+        simt::run_warp(fn, &j, sched_seed ? sched_seed + r : 0);
+    }
+    return 0;
+}
 
 /* tier_nv: 128/256/512/1024 = shared-memory tier, 0 = global tier, -1 = auto.
  * sched_seed: 0 = lanes run in ascending order, else adversarial ordering.

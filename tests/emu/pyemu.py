@@ -34,6 +34,7 @@ class Result(C.Structure):
         ("n_clauses_ingest", C.c_uint32), ("n_clauses_pre", C.c_uint32), ("eliminated_vars", C.c_uint32),
         ("pre_ok", C.c_uint32), ("attempts", C.c_uint32),
         ("stats", C.c_uint64 * 8), ("traffic", C.c_uint64 * 8), ("trace_hash", C.c_uint64),
+        ("exported", C.c_uint32), ("imported", C.c_uint32),
     ]
 
 
@@ -55,6 +56,9 @@ def lib():
                                       C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Result),
                                       C.POINTER(C.c_uint8), C.c_uint32]
         L.emu_solve_batch.restype = C.c_int
+        L.emu_portfolio.argtypes = [u32p, u32p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64,
+                                    C.POINTER(Result), C.POINTER(C.c_uint8), C.c_uint32]
+        L.emu_portfolio.restype = C.c_int
         _lib = L
     return _lib
 
@@ -81,4 +85,15 @@ def solve_batch(inst_clause_off, clause_off, lits, settings, kind=0, flags=1 | 4
                                arena_words, wpool_entries, sched_seed, res, mp, model_stride)
     if rc != 0:
         raise RuntimeError("emulator: solver kind not compiled in")
+    return res, models
+
+
+def portfolio(clause_off, lits, settings, n_replicas, share=1, flags=8, sched_seed=0, model_stride=0):
+    """Replicas of one instance run one after another against a shared ring (see emu_harness.cpp)."""
+    off, offp = _u32(clause_off)
+    li, lip = _u32(lits)
+    res = (Result * n_replicas)()
+    models = np.full((n_replicas, max(model_stride, 1)), 2, dtype=np.uint8)
+    lib().emu_portfolio(offp, lip, len(off) - 1, C.addressof(settings), n_replicas, share, flags, sched_seed, res,
+                        models.ctypes.data_as(C.POINTER(C.c_uint8)), model_stride)
     return res, models

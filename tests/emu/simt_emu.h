@@ -100,6 +100,9 @@ static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 static inline float __uint_as_float(uint32_t x) { float f; memcpy(&f, &x, 4); return f; }
 static inline uint32_t __float_as_uint(float f) { uint32_t x; memcpy(&x, &f, 4); return x; }
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> static inline T atomicCAS(T *p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
+static inline void __threadfence() {}
+static inline void __threadfence_system() {}
 template <class T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 
 #endif

@@ -144,3 +144,39 @@ def test_simp_settings_variants(po, emu, variant):
     idx = [list(g["names"]).index(n) for n in ("2bitcomp_5.cnf.gz", "uf50-03.cnf.gz", "uuf50-02.cnf.gz")]
     ioff, coff, lits = batch_of([golden_instance(g, i) for i in idx])
     compare(po, emu, ioff, coff, lits, po.SIMP, settings=st, nv=int(max(g["n_vars"][i] for i in idx)), sched_seed=2)
+
+
+# ---------------------------------------------------------------- portfolio mode
+def test_portfolio_replica0_exact_and_sharing_sound(po, emu):
+    """Replica 0 keeps the reference trace; diversified replicas that import the short learnt clauses of
+    earlier replicas still return the oracle's verdict and valid models (sharing is sound)."""
+    g = load_golden()
+    st = po.default_settings()
+    st.restart_first = 6.0          # many restart boundaries -> many import points
+    for name in ("uuf50-01.cnf.gz", "uf50-03.cnf.gz", "uf50-07.cnf.gz", "uuf50-05.cnf.gz"):
+        i = list(g["names"]).index(name)
+        off, lits = golden_instance(g, i)
+        nv = int(g["n_vars"][i])
+        o, _ = po.solve_csr(off, lits, kind=po.CORE, settings=st)
+        for share in (2, 3):        # PF_IGNORE_DONE alone / with PF_SHARE
+            res, models = emu.portfolio(off, lits, st, 8, share=share, model_stride=nv, sched_seed=5)
+            assert list(res[0].stats) == list(o.stats) and res[0].trace_hash == o.trace_hash, name
+            for k in range(8):
+                assert res[k].status == 0 and res[k].verdict == o.verdict, (name, k)
+                if res[k].verdict == 1:
+                    assert po.check_model(off, lits, models[k]), (name, k)
+            if share == 3:
+                assert sum(r.exported for r in res) > 0
+                assert sum(r.imported for r in res) > 0, name
+            else:
+                assert sum(r.exported for r in res) == 0 and sum(r.imported for r in res) == 0
+
+
+def test_portfolio_first_finisher_cancels_the_rest(po, emu):
+    g = load_golden()
+    i = list(g["names"]).index("uuf50-02.cnf.gz")
+    off, lits = golden_instance(g, i)
+    res, _ = emu.portfolio(off, lits, po.default_settings(), 4, share=1)   # done flag honoured
+    assert res[0].status == 0 and res[0].verdict == 0
+    # the emulator runs replicas one after another: replica 0 finishes, the others see `done` at their first conflict
+    assert all(r.status == 1 and r.verdict == 2 for r in res[1:])

@@ -234,3 +234,35 @@ def test_single_solver_api_simp(pkg, po):
     for l in r.model:
         model[pkg.lit_var(l)] = 0 if pkg.lit_sign(l) else 1
     assert po.check_model(off, lits, model)
+
+
+# ---------------------------------------------------------------- portfolio mode
+def test_portfolio_single_gpu(pkg, po):
+    g = load_golden()
+    for name in ("uf250-068.cnf.gz", "uuf50-04.cnf.gz", "4blocksb.cnf.gz"):
+        i = list(g["names"]).index(name)
+        off, lits = golden_instance(g, i)
+        nv = int(g["n_vars"][i])
+        ioff, coff, li = batch_of([(off, lits)])
+        e = pkg.Engine(0)
+        e.upload(ioff, coff, li)
+        # sharing off, every replica runs to completion: replica 0 is bit-exact the single-instance trace
+        res, models = e.portfolio_solve(64, share=pkg.PF_IGNORE_DONE, flags=pkg.F_TRACE_HASH, model_stride=nv)
+        assert list(res[0]["stats"]) == [int(x) for x in g["core_stats"][i]], name
+        assert int(res[0]["trace_hash"]) == int(g["core_hash"][i]), name
+        assert (res["status"] == 0).all() and (res["verdict"] == int(g["core_verdict"][i])).all(), name
+        assert len(set(int(x) for x in res["stats"][:, 4])) > 4          # the replicas really are diversified
+        for k in range(64):
+            if res[k]["verdict"] == 1:
+                assert po.check_model(off, lits, models[k]), (name, k)
+        # sharing on + first-finisher cancellation
+        e.ring_reset()
+        res, models = e.portfolio_solve(64, share=pkg.PF_SHARE, model_stride=nv)
+        done = [k for k in range(64) if res[k]["verdict"] != pkg.INTERRUPTED]
+        assert done, name
+        for k in done:
+            assert res[k]["status"] == 0 and res[k]["verdict"] == int(g["core_verdict"][i]), (name, k)
+            if res[k]["verdict"] == 1:
+                assert po.check_model(off, lits, models[k]), (name, k)
+        assert all(res[k]["status"] in (0, 1) for k in range(64))
+        e.close()
