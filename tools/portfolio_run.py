@@ -64,7 +64,8 @@ def main():
     ioff, coff, lits = eng.download_batch()
     ok_models = True
     if len(done) and res[done[0]]["verdict"] == pkg.SAT:
-        from tests.common import check_models
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+        from common import check_models
         ok_models = check_models(ioff, coff, lits, np.array([1]), models[done[:1]]) == 0
     mine = {"rank": rank, "seconds": secs, "finished_replicas": [int(rank * a.replicas + k) for k in done[:4]],
             "verdicts": sorted(set(int(v) for v in res["verdict"][done])), "model_ok": bool(ok_models),
