@@ -488,9 +488,20 @@ template <class VT, bool COUNT> struct WarpSolver {
                             else {
                                 len = hd.x >> H_SHIFT;
                                 out = (fv == 0) ? OUT_CONFL : OUT_UNIT;
-                                for (; kf < len; kf++) {
-                                    u32 l = (kf == 2) ? hd.w : arena[w.x + 1 + kf];
-                                    if (!is_false(l)) { lk = l; out = OUT_MOVE; break; }
+                                /* tail scan, 128 bits (4 literals) per load; literal k lives in word k+1 of the block */
+                                if (kf == 2 && len > 2) {
+                                    if (!is_false(hd.w)) { lk = hd.w; out = OUT_MOVE; } else kf = 3;
+                                }
+                                while (out != OUT_MOVE && kf < len) {
+                                    const u32 gb = (kf + 1) & ~3u;
+                                    const uint4 q = ld4(arena + w.x + gb);
+                                    const u32 qs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                                    for (u32 t = 0; t < 4; t++) {
+                                        const u32 k2 = gb + t - 1;
+                                        if (out != OUT_MOVE && k2 >= kf && k2 < len && !is_false(qs[t])) { lk = qs[t]; kf = k2; out = OUT_MOVE; }
+                                    }
+                                    if (out != OUT_MOVE) kf = gb + 3;
                                 }
                             }
                         }

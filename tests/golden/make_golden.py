@@ -27,11 +27,11 @@ PICK = (["cnf/uf20-0%d.cnf.gz" % i for i in (1, 2, 3, 4, 5, 6, 7, 8)] +
          "cnf/2bitadd_12.cnf.gz", "cnf/4blocksb.cnf.gz"])
 
 
-def main():
+def build(pick, out_name):
     names, insts = [], []
     out = {k: [] for k in ("core_verdict", "core_stats", "core_hash", "core_traffic", "simp_verdict", "simp_stats",
                            "simp_hash", "simp_elim", "simp_nclauses_pre", "n_vars", "name_verdict")}
-    for rel in PICK:
+    for rel in pick:
         path = os.path.join(REF, rel)
         if not os.path.exists(path):
             print("skip", rel)
@@ -58,12 +58,19 @@ def main():
         alll.append(lits)
         base += int(off[-1])
         ioff.append(ioff[-1] + len(off) - 1)
-    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "corpus_sample.npz"),
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), out_name),
                         names=np.array(names), inst_clause_off=np.array(ioff, np.uint32),
                         clause_off=np.concatenate(coffs), lits=np.concatenate(alll),
                         **{k: np.array(v, dtype=np.uint64 if "hash" in k or "stats" in k or "traffic" in k else np.int64)
                            for k, v in out.items()})
-    print("wrote", len(names), "instances")
+    print("wrote", len(names), "instances to", out_name)
+
+
+def main():
+    build(PICK, "corpus_sample.npz")
+    # config 1 at reduced size: every 12th bundled uf20/uf50/uuf50 instance (tests/minisat.rs walks every 4th)
+    wide = sorted(os.path.relpath(f, REF) for f in glob.glob(os.path.join(REF, "cnf", "u*.cnf.gz")))[::12]
+    build(wide, "corpus_wide.npz")
 
 
 if __name__ == "__main__":

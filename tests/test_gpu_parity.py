@@ -266,3 +266,24 @@ def test_portfolio_single_gpu(pkg, po):
                 assert po.check_model(off, lits, models[k]), (name, k)
         assert all(res[k]["status"] in (0, 1) for k in range(64))
         e.close()
+
+
+@pytest.mark.parametrize("kind_name", ["core", "simp"])
+def test_config1_wide_corpus(pkg, po, eng, kind_name):
+    """BASELINE.json configs[0] at reduced size: every 12th bundled uf20/uf50/uuf50 instance, one launch,
+    verdict + 8 stats + trace hash == oracle, verdict == SATLIB file-name class, models verified."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "corpus_wide.npz"))
+    kind = pkg.CORE if kind_name == "core" else pkg.SIMP
+    ioff, coff, lits = g["inst_clause_off"], g["clause_off"], g["lits"]
+    res, models = eng.solve_batch(ioff, coff, lits, kind=kind, flags=flags(pkg), model_stride=int(g["n_vars"].max()))
+    n = len(g["names"])
+    assert (res["status"] == 0).all()
+    assert (res["verdict"] == g[kind_name + "_verdict"]).all()
+    assert (res["verdict"] == g["name_verdict"]).all()
+    assert (res["stats"] == g[kind_name + "_stats"]).all()
+    assert (res["trace_hash"] == g[kind_name + "_hash"]).all()
+    if kind_name == "simp":
+        assert (res["eliminated_vars"] == g["simp_elim"]).all() and (res["n_clauses_pre"] == g["simp_nclauses_pre"]).all()
+    assert check_models(ioff, coff, lits, res["verdict"], models) == 0
+    assert n > 200
