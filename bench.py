@@ -284,6 +284,13 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if a.solver == "core" and n == 100 and B == 10000:
+                traffic = float(tj["dram_bytes_per_launch"])   # from the committed ncu --set full capture of this workload
+        except Exception:
+            pass
         value = world * B * a.steps / (dev_ms * 1e-3)
         # roofline of the dominant kernel (cdcl_warp) on rank 0.  With NS launches in flight the GPU is shared,
         # so `achieved` is the aggregate: algorithmic bytes of all K launches / device time of the timed region;
@@ -304,7 +311,7 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "cdcl_warp_smem", "launches_in_flight": NS,
+                         "traffic": traffic, "kernel": "cdcl_warp_smem", "launches_in_flight": NS,
                          "kernel_ms_per_launch_overlapped": k_ms, "kernel_ms_per_launch_solo": solo_ms,
                          "achieved_solo_launch": alg_bytes / (solo_ms * 1e-3) / 1e9,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_propagation": alg_bytes / max(props, 1.0),

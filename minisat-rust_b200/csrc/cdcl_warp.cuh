@@ -158,6 +158,11 @@ DEV u32 warp_excl_scan(u32 x, u32 lane, u32 &total) {
     return v - x;
 }
 DEV uint4 ld4(const u32 *p) { return *reinterpret_cast<const uint4 *>(p); }
+#if defined(__CUDACC__) && defined(B200SAT_PREFETCH_REASONS)
+DEV void prefetch_l1(const void *p) { asm volatile("prefetch.L1 [%0];" ::"l"(p)); }
+#else
+DEV void prefetch_l1(const void *) {}
+#endif
 DEV float u2f(u32 x) { return __uint_as_float(x); }
 DEV u32 f2u(float x) { return __float_as_uint(x); }
 
@@ -756,7 +761,12 @@ template <class VT, bool COUNT> struct WarpSolver {
                     u32 f = vf[v];
                     if ((f & VF_SEEN) == SEEN_UNDEF) {
                         u32 lv = V.level()[v];
-                        if (lv > GROUND) { fresh = true; iscur = lv >= cur; vf[v] = (u8)(f | SEEN_SOURCE); }
+                        if (lv > GROUND) {
+                            fresh = true; iscur = lv >= cur; vf[v] = (u8)(f | SEEN_SOURCE);
+                            /* its reason clause is read soon (current level: by this walk, lower levels: by minimisation) */
+                            const u32 rr = V.reason()[v];
+                            if (rr != CREF_UNDEF) prefetch_l1(arena + rr);
+                        }
                     }
                 }
                 u32 fm = __ballot_sync(FULL_MASK, fresh);

@@ -1,7 +1,8 @@
 #!/bin/bash
-# A/B timing of library variants (development aid)
+# A/B timing of library variants (development aid): args = variant names under minisat-rust_b200/variants, or "base"
 for v in "$@"; do
   echo "== $v"
-  B200SAT_LIB=/root/repo/minisat-rust_b200/variants/$v.so timeout 100 python tools/gpu_one.py 3000 100 1 2 2>&1 | tail -1 | sed 's/.*last_kernel_ms/low-occ ms/'
-  B200SAT_LIB=/root/repo/minisat-rust_b200/variants/$v.so timeout 100 python tools/gpu_one.py 10000 100 0 0 2>&1 | tail -1 | sed "s/'slab_bytes.*last_kernel_ms/ full ms/"
+  if [ "$v" = base ]; then unset B200SAT_LIB; else export B200SAT_LIB=/root/repo/minisat-rust_b200/variants/$v.so; fi
+  timeout 100 python tools/gpu_one.py 10000 100 0 0 2>&1 | tail -1 | sed "s/.*last_kernel_ms/ n100 full ms/"
+  timeout 200 python tools/gpu_one.py 16 250 0 0 2>&1 | tail -1 | sed "s/.*last_kernel_ms/ n250 x16 ms/"
 done
