@@ -52,7 +52,7 @@ struct Scal {
     i32 size_adjust_cnt;
     u32 simp_db_assigns, simp_db_assigns_set, status, dec_vars, heap_n, cur_arena, cur_wpool, eliminated_vars;
     u32 remove_satisfied, extra_clause_field, elim_n;
-    u32 ring_cursor[8], exported, imported;
+    u32 ring_cursor[8], exported, imported, simp_cur_opool;
 };
 
 /* ------------------------------------------------------------------ var-state tiers */

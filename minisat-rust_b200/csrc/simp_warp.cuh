@@ -72,6 +72,7 @@ template <class WS, bool COUNT> struct SeqSimp {
         opool = base + SL.o_opool[0];
         eheap_n = n_touched = sq_head = sq_tail = bwdsub_assigns = elits_n = esizes_n = opool_top = cur_opool = n_created = 0;
         eliminated_vars = 0;
+        if (S.lane == 0) sc().simp_cur_opool = 0;
         t_vis = t_kept = t_deref = t_tail = t_moves = t_impl = 0;
     }
 
@@ -346,6 +347,7 @@ template <class WS, bool COUNT> struct SeqSimp {
             top += ncap;
         }
         opool = dst; cur_opool = h; opool_top = top;
+        sc().simp_cur_opool = h;
         return true;
     }
     DEV bool occ_push(u32 v, u32 cr) {
@@ -811,6 +813,276 @@ template <class WS, bool COUNT> struct SeqSimp {
         }
         return true;
     }
+    /* ============================================================ warp-cooperative drivers
+     * The functions below are executed by ALL lanes with uniform control flow.  The data-parallel
+     * parts (candidate subsumption tests, clause classification, resolvent merges) run one item per
+     * lane on a snapshot; their effects are then applied by lane 0 strictly in the reference's order,
+     * so queue order, heap tie-breaking and GC timing are unchanged.  Lane 0 owns the simplifier's
+     * scalar state (the SeqSimp counters of the other lanes are not meaningful). */
+    DEV void refresh_views() { /* lane 0 may have garbage-collected / compacted: re-derive the shared views */
+        __syncwarp();
+        S.arena = S.arena_half(sc().cur_arena);
+        opool = base + SL.o_opool[sc().simp_cur_opool & 1];
+    }
+    DEV u32 merge_len(u32 v, u32 pr, u32 qr, bool &ok) const { /* merge() without the stores */
+        const u32 *ar = S.arena;
+        u32 np = ar[pr] >> H_SHIFT, nq = ar[qr] >> H_SHIFT;
+        const u32 *longer = ar + pr + 1, *shorter = ar + qr + 1;
+        u32 nl = np, ns = nq;
+        if (np < nq) { longer = ar + qr + 1; nl = nq; shorter = ar + pr + 1; ns = np; }
+        u32 n_out = 0;
+        ok = true;
+        for (u32 i = 0; i < ns; i++) {
+            u32 q = shorter[i];
+            if ((q >> 1) != v) {
+                bool add = true;
+                for (u32 j = 0; j < nl; j++) {
+                    if ((longer[j] >> 1) == (q >> 1)) {
+                        if (longer[j] == (q ^ 1)) { ok = false; return 0; }
+                        add = false;
+                        break;
+                    }
+                }
+                if (add) n_out++;
+            }
+        }
+        for (u32 j = 0; j < nl; j++) if ((longer[j] >> 1) != v) n_out++;
+        return n_out;
+    }
+
+    /* simplify.rs:423-523; false = Err (uniform) */
+    DEV bool u_backward_subsumption_check() {
+        const u32 lane = S.lane;
+        const i32 sub_lim = S.st().subsumption_lim;
+        u32 *bl = S.V.bl();
+        for (;;) {
+            u32 have = 0, is_clause = 0, sub_cr = CREF_UNDEF, unit = 0, nc = 0, lstart = 0, err = 0;
+            if (lane == 0) {
+                for (;;) { /* SubsumptionQueue::pop subsumption_queue.rs:23-42 */
+                    if (sq_len() > 0) {
+                        u32 cr = sq[sq_head % SL.sq_cap];
+                        sq_head++;
+                        if (!(arena()[cr] & H_DELETED)) { is_clause = 1; sub_cr = cr; have = 1; break; }
+                    } else {
+                        u32 ground_end = S.nlevels > 1 ? (u32)S.V.lim()[1] : S.trail_n;
+                        if (bwdsub_assigns < ground_end) { unit = S.V.trail()[bwdsub_assigns++]; have = 1; }
+                        break;
+                    }
+                }
+                if (have) {
+                    u32 lookup_var;
+                    if (!is_clause) lookup_var = unit >> 1;
+                    else { /* simplify.rs:459-476: occurrence list with the fewest entries, dead ones included */
+                        u32 n = arena()[sub_cr] >> H_SHIFT;
+                        u32 best = arena()[sub_cr + 1] >> 1;
+                        for (u32 i = 1; i < n; i++) {
+                            u32 v = arena()[sub_cr + 1 + i] >> 1;
+                            if (olen[v] < olen[best]) best = v;
+                        }
+                        lookup_var = best;
+                    }
+                    occ_lookup(lookup_var);
+                    nc = olen[lookup_var];
+                    lstart = ostart[lookup_var];
+                    if (nc > SL.cand_cap) { fail(ST_MEM_SIMP); err = 1; }
+                }
+            }
+            have = bcast(have); err = bcast(err);
+            if (err) return false;
+            if (!have) break;
+            is_clause = bcast(is_clause); sub_cr = bcast(sub_cr); unit = bcast(unit); nc = bcast(nc); lstart = bcast(lstart);
+            refresh_views();
+            for (u32 i = lane; i < nc; i += 32) cand[i] = opool[lstart + i]; /* snapshot, simplify.rs:478 */
+            __syncwarp();
+            u32 stop = 0;
+            for (u32 c0 = 0; c0 < nc && !stop; c0 += 32) {
+                const u32 ci = c0 + lane;
+                u32 code = SUB_DIFFERENT, l = 0;
+                if (ci < nc) {
+                    const u32 cj = cand[ci];
+                    if (!(is_clause && cj == sub_cr)) {
+                        const u32 hj = S.arena[cj];
+                        if (!(hj & H_DELETED) && (sub_lim == -1 || (i32)(hj >> H_SHIFT) < sub_lim))
+                            code = is_clause ? subsumes(sub_cr, cj, l) : unit_subsumes(unit, cj, l);
+                    }
+                }
+                const u32 m = __ballot_sync(FULL_MASK, code != SUB_DIFFERENT);
+                if (!m) continue;
+                bl[lane] = code | (l << 2);
+                __syncwarp();
+                u32 e = 0;
+                if (lane == 0) {
+                    u32 mm = m;
+                    while (mm) {
+                        const u32 k = (u32)__ffs(mm) - 1;
+                        mm &= mm - 1;
+                        if (is_clause && (arena()[sub_cr] & H_DELETED)) { stop = 1; break; }
+                        const u32 cjk = cand[c0 + k];
+                        if (arena()[cjk] & H_DELETED) continue;
+                        const u32 pk = bl[k];
+                        if ((pk & 3) == SUB_EXACT) {
+                            smudge_clause(cjk);
+                            unwatch_lazy(cjk);
+                            remove_clause(cjk);
+                        } else {
+                            if (!sq_push(cjk)) { e = 1; break; }
+                            if (!strengthen_clause(cjk, (pk >> 2) ^ 1)) { e = 1; break; }
+                        }
+                    }
+                }
+                e = bcast(e); stop = bcast(stop);
+                __syncwarp();
+                if (e) return false;
+            }
+        }
+        return true;
+    }
+
+    /* simplify.rs:338-420; false = Err (uniform) */
+    DEV bool u_eliminate_var(u32 v) {
+        const u32 lane = S.lane;
+        const u32 lt = lanemask_lt(lane);
+        u32 nc = 0, lstart = 0, err = 0;
+        if (lane == 0) {
+            occ_lookup(v);
+            nc = olen[v];
+            lstart = ostart[v];
+            if (nc > SL.cand_cap) { fail(ST_MEM_SIMP); err = 1; }
+        }
+        err = bcast(err);
+        if (err) return false;
+        nc = bcast(nc); lstart = bcast(lstart);
+        refresh_views();
+        for (u32 i = lane; i < nc; i += 32) cls[i] = opool[lstart + i];
+        __syncwarp();
+        /* split by the sign of v; pos grows from the front of pn, neg from the back (clause order kept) */
+        u32 npos = 0, nneg = 0;
+        for (u32 c0 = 0; c0 < nc; c0 += 32) {
+            const u32 i = c0 + lane;
+            u32 cr = 0, sgn = 2;
+            if (i < nc) {
+                cr = cls[i];
+                const u32 n = S.arena[cr] >> H_SHIFT;
+                for (u32 k = 0; k < n; k++) {
+                    const u32 l = S.arena[cr + 1 + k];
+                    if ((l >> 1) == v) { sgn = l & 1; break; }
+                }
+            }
+            const u32 pm = __ballot_sync(FULL_MASK, sgn == 0), nm = __ballot_sync(FULL_MASK, sgn == 1);
+            if (sgn == 0) pn[npos + __popc(pm & lt)] = cr;
+            if (sgn == 1) pn[SL.cand_cap - 1 - (nneg + __popc(nm & lt))] = cr;
+            npos += __popc(pm); nneg += __popc(nm);
+        }
+        __syncwarp();
+        const u64 max_resolvents = S.st().grow + npos + nneg;
+        const i32 cl_lim = S.st().clause_lim;
+        const u32 npairs = npos * nneg;
+        /* pass 1: length / tautology of every resolvent, one pair per lane, limits checked in pair order */
+        u32 nres = 0, rtop = 0;
+        for (u32 t0 = 0; t0 < npairs; t0 += 32) {
+            const u32 t = t0 + lane;
+            bool ok = false;
+            u32 len = 0;
+            if (t < npairs) len = merge_len(v, pn[t / nneg], pn[SL.cand_cap - 1 - (t % nneg)], ok);
+            const u32 okm = __ballot_sync(FULL_MASK, ok);
+            const u32 rank = __popc(okm & lt);
+            const bool viol = ok && ((u64)(nres + rank + 1) > max_resolvents || !(cl_lim == -1 || (i32)len <= cl_lim));
+            if (__ballot_sync(FULL_MASK, viol)) return true; /* too many / too long resolvents: keep the variable */
+            u32 tot;
+            warp_excl_scan(ok ? len : 0, lane, tot);
+            nres += __popc(okm);
+            rtop += tot;
+        }
+        if (rtop > SL.rbuf_cap || nres + 2 > SL.roff_cap) { S.fail(ST_MEM_SIMP); return false; }
+        /* pass 2: materialise the resolvents in pair order */
+        u32 rr = 0, ro = 0;
+        for (u32 t0 = 0; t0 < npairs; t0 += 32) {
+            const u32 t = t0 + lane;
+            bool ok = false;
+            u32 len = 0;
+            if (t < npairs) len = merge_len(v, pn[t / nneg], pn[SL.cand_cap - 1 - (t % nneg)], ok);
+            const u32 okm = __ballot_sync(FULL_MASK, ok);
+            u32 tot;
+            const u32 off = ro + warp_excl_scan(ok ? len : 0, lane, tot);
+            if (ok) {
+                u32 n_out = 0;
+                merge(v, pn[t / nneg], pn[SL.cand_cap - 1 - (t % nneg)], rbuf + off, n_out);
+                const u32 idx = rr + __popc(okm & lt);
+                roff[idx] = off;
+                roff[idx + 1] = off + n_out; /* the next resolvent rewrites this slot with the same value */
+            }
+            rr += __popc(okm);
+            ro += tot;
+        }
+        __syncwarp();
+        u32 e = 0;
+        if (lane == 0) {
+            S.V.vflags()[v] |= VF_ELIM;
+            if (S.V.vflags()[v] & VF_DEC) { S.V.vflags()[v] &= (u8)~VF_DEC; sc().dec_vars--; } /* set_decision_var(v,false) */
+            eliminated_vars++;
+            if (npos > nneg) {
+                for (u32 b = 0; b < nneg && !e; b++) if (!mk_elim_clause(v, pn[SL.cand_cap - 1 - b])) e = 1;
+                if (!e && !mk_elim_unit(2 * v)) e = 1;
+            } else {
+                for (u32 a = 0; a < npos && !e; a++) if (!mk_elim_clause(v, pn[a])) e = 1;
+                if (!e && !mk_elim_unit(2 * v + 1)) e = 1;
+            }
+            for (u32 i = 0; i < nc && !e; i++) {
+                u32 cr = cls[i];
+                smudge_clause(cr);
+                unwatch_lazy(cr);
+                remove_clause(cr);
+            }
+            for (u32 r = 0; r < nres && !e; r++)
+                if (!add_clause(rbuf + roff[r], roff[r + 1] - roff[r])) e = 1;
+            if (!e) { olen[v] = 0; ocap[v] = 0; opresent[v] = 0; } /* clear_var */
+        }
+        e = bcast(e);
+        __syncwarp();
+        return e == 0;
+    }
+
+    /* simplify.rs:213-274; false = Err (uniform) */
+    DEV bool u_eliminate() {
+        const u32 lane = S.lane;
+        for (;;) {
+            u32 go = 0, e = 0;
+            if (lane == 0) {
+                u32 ground = S.nlevels > 1 ? (u32)S.V.lim()[1] : S.trail_n;
+                go = (n_touched != 0 || ground - bwdsub_assigns > 0 || eheap_n > 0) ? 1 : 0;
+                if (go && !enqueue_touched_clauses()) e = 1;
+            }
+            go = bcast(go); e = bcast(e);
+            if (e) return false;
+            if (!go) break;
+            if (!u_backward_subsumption_check()) return false;
+            for (;;) {
+                u32 got = 0, var = 0, do_elim = 0;
+                if (lane == 0) {
+                    u32 x;
+                    while (eh_pop(x)) {
+                        if (is_elim(x) || S.V.assign()[x] != LB_UNDEF) continue;
+                        got = 1; var = x;
+                        do_elim = (S.st().use_elim && !is_frozen(x)) ? 1 : 0;
+                        break;
+                    }
+                }
+                got = bcast(got);
+                if (!got) break;
+                var = bcast(var); do_elim = bcast(do_elim);
+                if (do_elim) {
+                    if (!u_eliminate_var(var)) return false;
+                    if (!u_backward_subsumption_check()) return false;
+                }
+                u32 f = 0;
+                if (lane == 0) { simp_try_gc(); f = failed() ? 1 : 0; }
+                f = bcast(f);
+                if (f) return false;
+            }
+        }
+        return true;
+    }
+
     DEV void off() { /* simplify.rs:536-544 */
         sc().remove_satisfied = 1;
         sc().extra_clause_field = 0;
@@ -843,50 +1115,58 @@ template <class WS, bool COUNT> struct SeqSimp {
 /* SimpSolver driver for one instance (../minisat.rs:123-279 + lib.rs:47-126 flags) */
 template <class VT, bool COUNT> DEV void solve_simp(WarpSolver<VT, COUNT> &S, u32 inst) {
     const KParams &P = S.P;
+    const u32 lane = S.lane;
     u32 cb, ce;
     bool setup_ok = S.setup(inst, cb, ce);
     u32 n_ingest = 0, n_pre = 0, pre_ok = 1, do_search = 0;
     i32 verdict = B200SAT_INTERRUPTED;
     if (setup_ok && P.L.simp_cap == 0) { S.fail(ST_MEM_SIMP); setup_ok = false; }
     if (setup_ok) {
-        if (S.lane == 0) {
-            SeqSimp<WarpSolver<VT, COUNT>, COUNT> Z(S);
-            Z.bind();
+        /* every lane binds the region pointers; the simplifier's counters live on lane 0 */
+        SeqSimp<WarpSolver<VT, COUNT>, COUNT> Z(S);
+        Z.bind();
+        u32 ok = 1, bad = 0, simp_alive = 1;
+        if (lane == 0) {
             S.sc().extra_clause_field = 1;   /* Simplificator::on simplify.rs:546-549 */
             S.sc().remove_satisfied = 0;
-            bool ok = true;
             /* ingest: dimacs.rs:146-167 order -- vars are created lazily, interleaved with the clauses */
             for (u32 c = cb; c < ce && !Z.failed(); c++) {
                 u32 b = P.clause_off[c], e = P.clause_off[c + 1];
                 for (u32 k = b; k < e; k++) while ((P.lits[k] >> 1) + 1 > Z.n_created) Z.init_var(Z.n_created);
-                if (!Z.add_clause(P.lits + b, e - b)) ok = false; /* SimpSolver::add_clause: no `ok` check before (minisat.rs:146-158) */
+                if (!Z.add_clause(P.lits + b, e - b)) ok = 0; /* SimpSolver::add_clause: no `ok` check before (minisat.rs:146-158) */
             }
             n_ingest = S.sc().num_clauses;
             n_pre = n_ingest;
-            bool simp_alive = true;
-            if (!Z.failed() && (P.flags & B200SAT_F_PREPROCESS)) { /* SimpSolver::preprocess minisat.rs:161-191 */
-                bool res;
-                if (ok) { ok = Z.seq_propagate() == CREF_UNDEF; if (ok) Z.seq_try_simplify(); } /* CoreSolver::preprocess */
-                if (!ok) res = false;
-                else {
-                    res = Z.eliminate();
-                    if (!res) ok = false;
-                    Z.off();
-                    simp_alive = false;
-                }
-                pre_ok = res ? 1 : 0;
-                n_pre = S.sc().num_clauses;
+            bad = Z.failed() ? 1 : 0;
+            if (!bad && (P.flags & B200SAT_F_PREPROCESS) && ok) { /* CoreSolver::preprocess minisat.rs:50-55 */
+                ok = Z.seq_propagate() == CREF_UNDEF ? 1 : 0;
+                if (ok) Z.seq_try_simplify();
+                bad = Z.failed() ? 1 : 0;
             }
-            if (!Z.failed()) {
-                if (!pre_ok) verdict = B200SAT_UNSAT;
-                else if (P.flags & B200SAT_F_NO_SOLVE) verdict = B200SAT_INTERRUPTED;
-                else if (simp_alive) { /* Simplificator::solve_limited simplify.rs:165-211 */
-                    if (Z.seq_propagate() == CREF_UNDEF) {
-                        Z.seq_try_simplify();
-                        if (Z.eliminate()) do_search = 1; else verdict = B200SAT_UNSAT;
-                    } else verdict = B200SAT_UNSAT;
-                } else do_search = 1; /* simp == None: core search, minisat.rs:241-260 (no `ok` check needed: pre_ok) */
+        }
+        ok = bcast(ok); bad = bcast(bad);
+        if (!bad && (P.flags & B200SAT_F_PREPROCESS)) { /* SimpSolver::preprocess minisat.rs:161-191 */
+            u32 res = 0;
+            if (ok) {
+                res = Z.u_eliminate() ? 1 : 0;
+                if (lane == 0) Z.off();
+                simp_alive = 0;
             }
+            pre_ok = res;
+            if (lane == 0) { n_pre = S.sc().num_clauses; bad = Z.failed() ? 1 : 0; }
+            bad = bcast(bad);
+        }
+        if (!bad) {
+            if (!pre_ok) verdict = B200SAT_UNSAT;
+            else if (P.flags & B200SAT_F_NO_SOLVE) verdict = B200SAT_INTERRUPTED;
+            else if (simp_alive) { /* Simplificator::solve_limited simplify.rs:165-211 */
+                u32 pr = 0;
+                if (lane == 0) { pr = Z.seq_propagate() == CREF_UNDEF ? 1 : 0; if (pr) Z.seq_try_simplify(); }
+                pr = bcast(pr);
+                if (pr && Z.u_eliminate()) do_search = 1; else verdict = B200SAT_UNSAT;
+            } else do_search = 1; /* simp == None: core search, minisat.rs:241-260 */
+        }
+        if (lane == 0) {
             S.sc().eliminated_vars = Z.eliminated_vars;
             S.sc().elim_n = Z.esizes_n;
             Z.flush_traffic();
@@ -894,8 +1174,7 @@ template <class VT, bool COUNT> DEV void solve_simp(WarpSolver<VT, COUNT> &S, u3
         __syncwarp();
         /* hand the lane-0 state to the whole warp */
         S.trail_n = bcast(S.trail_n); S.qhead = bcast(S.qhead); S.nlevels = bcast(S.nlevels);
-        n_ingest = bcast(n_ingest); n_pre = bcast(n_pre); pre_ok = bcast(pre_ok); do_search = bcast(do_search);
-        verdict = (i32)bcast((u32)verdict);
+        n_ingest = bcast(n_ingest); n_pre = bcast(n_pre);
         S.arena = S.arena_half(S.sc().cur_arena);
         S.wpool = S.wpool_half(S.sc().cur_wpool);
         __syncwarp();
@@ -907,11 +1186,11 @@ template <class VT, bool COUNT> DEV void solve_simp(WarpSolver<VT, COUNT> &S, u3
     __syncwarp();
     S.write_result(inst, verdict, n_ingest, n_pre, pre_ok);
     if (P.models && !S.failed() && verdict == B200SAT_SAT && S.st().extend_model) {
-        if (S.lane == 0) {
+        if (lane == 0) {
             SeqSimp<WarpSolver<VT, COUNT>, COUNT> Z(S);
             Z.bind_ptrs();
             Z.esizes_n = S.sc().elim_n;
-            Z.extend_model(P.models + (size_t)inst * P.model_stride);
+            Z.extend_model(P.models + (size_t)S.res_index * P.model_stride);
         }
         __syncwarp();
     }
