@@ -51,8 +51,8 @@ template <int NV, bool COUNT, bool SIMP> __global__ void __launch_bounds__(64, B
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 wpb = blockDim.x >> 5;
-    WarpSolver<VarsS<NV>, COUNT> S(P, lane);
-    S.V.s = reinterpret_cast<SmemVars<NV> *>(smem_raw) + warp;
+    WarpSolver<VarsS<NV, SIMP>, COUNT> S(P, lane);
+    S.V.s = reinterpret_cast<SmemVars<NV, SIMP> *>(smem_raw) + warp;
     S.slab = P.slabs + (size_t)(blockIdx.x * wpb + warp) * P.L.slab_bytes;
     warp_work_loop<SIMP>(S, P);
 }
@@ -75,9 +75,9 @@ kernel_fn B200SAT_KERNEL_TU_NAME(int tier_nv, size_t *spw) {
     using namespace b200sat;
     constexpr bool C = B200SAT_KERNEL_TU_COUNT != 0, Sp = B200SAT_KERNEL_TU_SIMP != 0;
     switch (tier_nv) {
-    case 128: *spw = sizeof(SmemVars<128>); return cdcl_warp_smem<128, C, Sp>;
-    case 256: *spw = sizeof(SmemVars<256>); return cdcl_warp_smem<256, C, Sp>;
-    case 1024: *spw = sizeof(SmemVars<1024>); return cdcl_warp_smem<1024, C, Sp>;
+    case 128: *spw = sizeof(SmemVars<128, Sp>); return cdcl_warp_smem<128, C, Sp>;
+    case 256: *spw = sizeof(SmemVars<256, Sp>); return cdcl_warp_smem<256, C, Sp>;
+    case 1024: *spw = sizeof(SmemVars<1024, Sp>); return cdcl_warp_smem<1024, C, Sp>;
     default: *spw = sizeof(SmemSmall); return cdcl_warp_glob<C, Sp>;
     }
 }

@@ -56,7 +56,16 @@ struct Scal {
 };
 
 /* ------------------------------------------------------------------ var-state tiers */
-template <int NV> struct SmemVars {
+/* SimpSolver kernels keep the elimination heap and the literal occurrence counts (the
+ * simplifier's most frequently chased words, elim_queue.rs:13-76) in shared memory too */
+template <int NV, bool SIMP> struct SimpSmem {};
+template <int NV> struct SimpSmem<NV, true> {
+    i32 nocc[2 * NV];
+    u16 eheap[NV];
+    u16 eidx[NV];
+};
+
+template <int NV, bool SIMP = false> struct SmemVars {
     double act[NV];
     u32 reason[NV];
     u32 wstart[2 * NV];
@@ -70,13 +79,15 @@ template <int NV> struct SmemVars {
     u8 vflags[NV];
     Scal sc;
     u32 bl[32];
+    SimpSmem<NV, SIMP> simp;
 };
 
-template <int NV> struct VarsS {
+template <int NV, bool SIMP = false> struct VarsS {
     typedef u16 idx_t;
     static const u32 ABSENT = 0xFFFFu;
     static const u32 MAXLEN = 0xFFF0u;
-    SmemVars<NV> *s;
+    static const bool SIMP_SMEM = SIMP;
+    SmemVars<NV, SIMP> *s;
     DEV double *act() const { return s->act; }
     DEV u32 *reason() const { return s->reason; }
     DEV u32 *wstart() const { return s->wstart; }
@@ -91,6 +102,7 @@ template <int NV> struct VarsS {
     DEV Scal &sc() const { return s->sc; }
     DEV u32 *bl() const { return s->bl; }
     DEV u32 cap() const { return NV; }
+    DEV void *simp_smem() const { return (void *)&s->simp; }
 };
 
 struct SmemSmall {
@@ -102,6 +114,8 @@ struct VarsG {
     typedef u32 idx_t;
     static const u32 ABSENT = 0xFFFFFFFFu;
     static const u32 MAXLEN = 0x3FFFFFF0u;
+    static const bool SIMP_SMEM = false;
+    DEV void *simp_smem() const { return nullptr; }
     SmemSmall *s;
     double *act_;
     u32 *reason_, *wstart_, *wlen_, *level_, *trail_, *lim_, *heap_, *hidx_;
@@ -174,6 +188,7 @@ template <class VT, bool COUNT> struct WarpSolver {
     typedef typename VT::idx_t idx_t;
     static const u32 VT_ABSENT = VT::ABSENT;
     static const u32 VT_MAXLEN = VT::MAXLEN;
+    static const bool VT_SIMP_SMEM = VT::SIMP_SMEM;
     VT V;
     const KParams &P;
     const b200sat_settings *stp;   /* P.st, or this replica's diversified settings in portfolio mode */

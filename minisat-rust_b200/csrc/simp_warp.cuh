@@ -41,7 +41,8 @@ template <class WS, bool COUNT> struct SeqSimp {
     WS &S;
     SimpLayout SL;
     u32 *base;
-    u32 *ostart, *olen, *ocap, *eheap, *eidx, *sq, *elits, *esizes, *cand, *cls, *pn, *rbuf, *roff, *tmpb, *opool;
+    u32 *ostart, *olen, *ocap, *sq, *elits, *esizes, *cand, *cls, *pn, *rbuf, *roff, *tmpb, *opool;
+    idx_t *eheap, *eidx; /* shared memory (u16) in the shared-memory tiers, slab (u32) in the global tier */
     i32 *nocc;
     u8 *odirty, *opresent, *touched;
     u32 eheap_n, n_touched, sq_head, sq_tail, bwdsub_assigns, elits_n, esizes_n, opool_top, cur_opool, n_created;
@@ -59,11 +60,21 @@ template <class WS, bool COUNT> struct SeqSimp {
         SL = simp_layout(S.P.L.nv_cap, S.P.L.clauses_cap, S.P.L.simp_lits, S.P.L.tmp_cap);
         elits = base + SL.o_elits; esizes = base + SL.o_esizes;
     }
+    DEV void bind_heap() {
+        if (WS::VT_SIMP_SMEM) {
+            char *sm = (char *)S.V.simp_smem();
+            nocc = (i32 *)sm;
+            eheap = (idx_t *)(sm + 8 * (size_t)S.V.cap());
+            eidx = eheap + S.V.cap();
+        } else {
+            eheap = (idx_t *)(base + SL.o_eheap); eidx = (idx_t *)(base + SL.o_eidx); nocc = (i32 *)(base + SL.o_nocc);
+        }
+    }
     DEV void bind() {
         base = (u32 *)(S.slab + S.P.L.off_simp);
         SL = simp_layout(S.P.L.nv_cap, S.P.L.clauses_cap, S.P.L.simp_lits, S.P.L.tmp_cap);
         ostart = base + SL.o_ostart; olen = base + SL.o_olen; ocap = base + SL.o_ocap;
-        eheap = base + SL.o_eheap; eidx = base + SL.o_eidx; nocc = (i32 *)(base + SL.o_nocc);
+        bind_heap();
         u8 *fl = (u8 *)(base + SL.o_flags);
         odirty = fl; opresent = fl + S.P.L.nv_cap; touched = fl + 2 * S.P.L.nv_cap;
         sq = base + SL.o_sq; elits = base + SL.o_elits; esizes = base + SL.o_esizes;
@@ -287,9 +298,9 @@ template <class WS, bool COUNT> struct SeqSimp {
         while (i > 0) {
             u32 p = (i - 1) >> 1;
             u32 y = eheap[p];
-            if (cx < cost(y)) { eheap[i] = y; eidx[y] = i; i = p; } else break;
+            if (cx < cost(y)) { eheap[i] = (idx_t)y; eidx[y] = (idx_t)i; i = p; } else break;
         }
-        eheap[i] = x; eidx[x] = i;
+        eheap[i] = (idx_t)x; eidx[x] = (idx_t)i;
     }
     DEV void eh_sift_down(u32 i) {
         u32 x = eheap[i];
@@ -299,15 +310,15 @@ template <class WS, bool COUNT> struct SeqSimp {
             if (l >= eheap_n) break;
             u32 r = l + 1;
             u32 c = (r < eheap_n && cost(eheap[r]) < cost(eheap[l])) ? r : l;
-            if (cost(eheap[c]) < cx) { u32 y = eheap[c]; eheap[i] = y; eidx[y] = i; i = c; } else break;
+            if (cost(eheap[c]) < cx) { u32 y = eheap[c]; eheap[i] = (idx_t)y; eidx[y] = (idx_t)i; i = c; } else break;
         }
-        eheap[i] = x; eidx[x] = i;
+        eheap[i] = (idx_t)x; eidx[x] = (idx_t)i;
     }
-    DEV bool eh_contains(u32 v) const { return eidx[v] != 0xFFFFFFFFu; }
+    DEV bool eh_contains(u32 v) const { return (u32)eidx[v] != WS::VT_ABSENT; }
     DEV void eh_insert(u32 v) {
         if (eh_contains(v)) return;
         u32 place = eheap_n++;
-        eheap[place] = v;
+        eheap[place] = (idx_t)v;
         eh_sift_up(place);
     }
     DEV void eh_update(u32 v) { /* index_map.rs:244-255: sift_down(place) then sift_up(place), same place */
@@ -320,8 +331,8 @@ template <class WS, bool COUNT> struct SeqSimp {
         if (eheap_n == 0) return false;
         out = eheap[0];
         u32 last = eheap[--eheap_n];
-        eidx[out] = 0xFFFFFFFFu;
-        if (eheap_n > 0) { eheap[0] = last; eh_sift_down(0); }
+        eidx[out] = (idx_t)WS::VT_ABSENT;
+        if (eheap_n > 0) { eheap[0] = (idx_t)last; eh_sift_down(0); }
         return true;
     }
     DEV bool is_elim(u32 v) const { return (S.V.vflags()[v] & VF_ELIM) != 0; }
@@ -406,7 +417,7 @@ template <class WS, bool COUNT> struct SeqSimp {
         ostart[v] = 0; olen[v] = 0; ocap[v] = 0;
         odirty[v] = 0; opresent[v] = 1; touched[v] = 0;
         nocc[2 * v] = 0; nocc[2 * v + 1] = 0;
-        eidx[v] = 0xFFFFFFFFu;
+        eidx[v] = (idx_t)WS::VT_ABSENT;
         n_created = v + 1;
         eh_insert(v);
     }

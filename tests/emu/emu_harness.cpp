@@ -115,21 +115,31 @@ struct Job {
     bool replica = false;
 };
 
-template <class VT, bool COUNT> void run_one(WarpSolver<VT, COUNT> &S, const Job *j) {
+template <bool SIMP, class VT, bool COUNT> void run_one(WarpSolver<VT, COUNT> &S, const Job *j) {
     S.res_index = j->inst;
-    if (j->replica) { S.stp = j->P.replica_settings + j->inst; S.solve_core(0); return; }
+    if constexpr (SIMP) {
 #ifdef B200SAT_HAVE_SIMP
-    if (j->P.kind == B200SAT_SIMP) { solve_simp(S, j->inst); return; }
+        solve_simp(S, j->inst);
 #endif
-    S.solve_core(j->inst);
+    } else {
+        if (j->replica) { S.stp = j->P.replica_settings + j->inst; S.solve_core(0); return; }
+        S.solve_core(j->inst);
+    }
 }
 
 template <int NV, bool COUNT> void entry_s(void *user, int lane) {
     Job *j = (Job *)user;
+    if (j->P.kind == B200SAT_SIMP) { /* SimpSolver kernels: elimination heap + occurrence counts in shared memory */
+        WarpSolver<VarsS<NV, true>, COUNT> S(j->P, (u32)lane);
+        S.V.s = (SmemVars<NV, true> *)j->smem;
+        S.slab = j->P.slabs;
+        run_one<true>(S, j);
+        return;
+    }
     WarpSolver<VarsS<NV>, COUNT> S(j->P, (u32)lane);
     S.V.s = (SmemVars<NV> *)j->smem;
     S.slab = j->P.slabs;
-    run_one(S, j);
+    run_one<false>(S, j);
 }
 template <bool COUNT> void entry_g(void *user, int lane) {
     Job *j = (Job *)user;
@@ -137,7 +147,7 @@ template <bool COUNT> void entry_g(void *user, int lane) {
     S.V.s = (SmemSmall *)j->smem;
     S.slab = j->P.slabs;
     S.V.bind(S.slab + j->P.L.off_vars, j->P.L.nv_cap);
-    run_one(S, j);
+    if (j->P.kind == B200SAT_SIMP) run_one<true>(S, j); else run_one<false>(S, j);
 }
 } // namespace
 
