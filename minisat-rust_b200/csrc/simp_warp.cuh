@@ -1123,88 +1123,119 @@ template <class WS, bool COUNT> struct SeqSimp {
     }
 };
 
+struct SimpPhaseOut { u32 trail_n, qhead, nlevels, n_ingest, n_pre, pre_ok, do_search; i32 verdict; };
+
+/* Ingest + preprocessing of one instance (everything before the search).  Deliberately NOT inlined and
+ * handed only plain values, from which it builds its own solver handle: the simplifier keeps a reference
+ * to the handle, which forces that object into local memory; when it was the search's own object the
+ * search loop lost the shared-memory address-space inference for the var state (measured: 2x slower
+ * search, 56 % long-scoreboard stalls instead of 21 %, generic LD instead of LDS in the SASS).  All
+ * lasting state lives in the slab and in shared memory. */
+template <class VT, bool COUNT>
+DEVNI SimpPhaseOut simp_phase(const KParams *Pp, VT V, u8 *slab, const b200sat_settings *stp, u32 lane_, u32 res_index,
+                              u32 nvars, u32 cb, u32 ce) {
+    WarpSolver<VT, COUNT> S(*Pp, lane_); /* state right after setup() */
+    S.V = V; S.slab = slab; S.stp = stp; S.res_index = res_index; S.nvars = nvars;
+    S.trail_n = 0; S.qhead = 0; S.nlevels = 1;
+    S.arena = S.arena_half(0);
+    S.wpool = S.wpool_half(0);
+    const KParams &P = S.P;
+    const u32 lane = S.lane;
+    SimpPhaseOut o;
+    o.n_ingest = 0; o.n_pre = 0; o.pre_ok = 1; o.do_search = 0; o.verdict = B200SAT_INTERRUPTED;
+    /* every lane binds the region pointers; the simplifier's counters live on lane 0 */
+    SeqSimp<WarpSolver<VT, COUNT>, COUNT> Z(S);
+    Z.bind();
+    u32 ok = 1, bad = 0, simp_alive = 1;
+    if (lane == 0) {
+        S.sc().extra_clause_field = 1;   /* Simplificator::on simplify.rs:546-549 */
+        S.sc().remove_satisfied = 0;
+        /* ingest: dimacs.rs:146-167 order -- vars are created lazily, interleaved with the clauses */
+        for (u32 c = cb; c < ce && !Z.failed(); c++) {
+            u32 b = P.clause_off[c], e = P.clause_off[c + 1];
+            for (u32 k = b; k < e; k++) while ((P.lits[k] >> 1) + 1 > Z.n_created) Z.init_var(Z.n_created);
+            if (!Z.add_clause(P.lits + b, e - b)) ok = 0; /* SimpSolver::add_clause: no `ok` check before (minisat.rs:146-158) */
+        }
+        o.n_ingest = S.sc().num_clauses;
+        o.n_pre = o.n_ingest;
+        bad = Z.failed() ? 1 : 0;
+        if (!bad && (P.flags & B200SAT_F_PREPROCESS) && ok) { /* CoreSolver::preprocess minisat.rs:50-55 */
+            ok = Z.seq_propagate() == CREF_UNDEF ? 1 : 0;
+            if (ok) Z.seq_try_simplify();
+            bad = Z.failed() ? 1 : 0;
+        }
+    }
+    ok = bcast(ok); bad = bcast(bad);
+    if (!bad && (P.flags & B200SAT_F_PREPROCESS)) { /* SimpSolver::preprocess minisat.rs:161-191 */
+        u32 res = 0;
+        if (ok) {
+            res = Z.u_eliminate() ? 1 : 0;
+            if (lane == 0) Z.off();
+            simp_alive = 0;
+        }
+        o.pre_ok = res;
+        if (lane == 0) { o.n_pre = S.sc().num_clauses; bad = Z.failed() ? 1 : 0; }
+        bad = bcast(bad);
+    }
+    if (!bad) {
+        if (!o.pre_ok) o.verdict = B200SAT_UNSAT;
+        else if (P.flags & B200SAT_F_NO_SOLVE) o.verdict = B200SAT_INTERRUPTED;
+        else if (simp_alive) { /* Simplificator::solve_limited simplify.rs:165-211 */
+            u32 pr = 0;
+            if (lane == 0) { pr = Z.seq_propagate() == CREF_UNDEF ? 1 : 0; if (pr) Z.seq_try_simplify(); }
+            pr = bcast(pr);
+            if (pr && Z.u_eliminate()) o.do_search = 1; else o.verdict = B200SAT_UNSAT;
+        } else o.do_search = 1; /* simp == None: core search, minisat.rs:241-260 */
+    }
+    if (lane == 0) {
+        S.sc().eliminated_vars = Z.eliminated_vars;
+        S.sc().elim_n = Z.esizes_n;
+        Z.flush_traffic();
+    }
+    __syncwarp();
+    /* hand the lane-0 scalars to the whole warp */
+    o.trail_n = bcast(S.trail_n); o.qhead = bcast(S.qhead); o.nlevels = bcast(S.nlevels);
+    o.n_ingest = bcast(o.n_ingest); o.n_pre = bcast(o.n_pre);
+    return o;
+}
+
+template <class VT, bool COUNT>
+DEVNI void simp_extend_model(const KParams *Pp, VT V, u8 *slab, u32 lane_, u32 res_index) { /* elim_clauses.rs:43-63 */
+    if (lane_ == 0) {
+        WarpSolver<VT, COUNT> S(*Pp, lane_);
+        S.V = V; S.slab = slab; S.res_index = res_index;
+        SeqSimp<WarpSolver<VT, COUNT>, COUNT> Z(S);
+        Z.bind_ptrs();
+        Z.esizes_n = S.sc().elim_n;
+        Z.extend_model(Pp->models + (size_t)res_index * Pp->model_stride);
+    }
+    __syncwarp();
+}
+
 /* SimpSolver driver for one instance (../minisat.rs:123-279 + lib.rs:47-126 flags) */
 template <class VT, bool COUNT> DEV void solve_simp(WarpSolver<VT, COUNT> &S, u32 inst) {
     const KParams &P = S.P;
-    const u32 lane = S.lane;
     u32 cb, ce;
     bool setup_ok = S.setup(inst, cb, ce);
-    u32 n_ingest = 0, n_pre = 0, pre_ok = 1, do_search = 0;
+    u32 n_ingest = 0, n_pre = 0, pre_ok = 1;
     i32 verdict = B200SAT_INTERRUPTED;
     if (setup_ok && P.L.simp_cap == 0) { S.fail(ST_MEM_SIMP); setup_ok = false; }
     if (setup_ok) {
-        /* every lane binds the region pointers; the simplifier's counters live on lane 0 */
-        SeqSimp<WarpSolver<VT, COUNT>, COUNT> Z(S);
-        Z.bind();
-        u32 ok = 1, bad = 0, simp_alive = 1;
-        if (lane == 0) {
-            S.sc().extra_clause_field = 1;   /* Simplificator::on simplify.rs:546-549 */
-            S.sc().remove_satisfied = 0;
-            /* ingest: dimacs.rs:146-167 order -- vars are created lazily, interleaved with the clauses */
-            for (u32 c = cb; c < ce && !Z.failed(); c++) {
-                u32 b = P.clause_off[c], e = P.clause_off[c + 1];
-                for (u32 k = b; k < e; k++) while ((P.lits[k] >> 1) + 1 > Z.n_created) Z.init_var(Z.n_created);
-                if (!Z.add_clause(P.lits + b, e - b)) ok = 0; /* SimpSolver::add_clause: no `ok` check before (minisat.rs:146-158) */
-            }
-            n_ingest = S.sc().num_clauses;
-            n_pre = n_ingest;
-            bad = Z.failed() ? 1 : 0;
-            if (!bad && (P.flags & B200SAT_F_PREPROCESS) && ok) { /* CoreSolver::preprocess minisat.rs:50-55 */
-                ok = Z.seq_propagate() == CREF_UNDEF ? 1 : 0;
-                if (ok) Z.seq_try_simplify();
-                bad = Z.failed() ? 1 : 0;
-            }
-        }
-        ok = bcast(ok); bad = bcast(bad);
-        if (!bad && (P.flags & B200SAT_F_PREPROCESS)) { /* SimpSolver::preprocess minisat.rs:161-191 */
-            u32 res = 0;
-            if (ok) {
-                res = Z.u_eliminate() ? 1 : 0;
-                if (lane == 0) Z.off();
-                simp_alive = 0;
-            }
-            pre_ok = res;
-            if (lane == 0) { n_pre = S.sc().num_clauses; bad = Z.failed() ? 1 : 0; }
-            bad = bcast(bad);
-        }
-        if (!bad) {
-            if (!pre_ok) verdict = B200SAT_UNSAT;
-            else if (P.flags & B200SAT_F_NO_SOLVE) verdict = B200SAT_INTERRUPTED;
-            else if (simp_alive) { /* Simplificator::solve_limited simplify.rs:165-211 */
-                u32 pr = 0;
-                if (lane == 0) { pr = Z.seq_propagate() == CREF_UNDEF ? 1 : 0; if (pr) Z.seq_try_simplify(); }
-                pr = bcast(pr);
-                if (pr && Z.u_eliminate()) do_search = 1; else verdict = B200SAT_UNSAT;
-            } else do_search = 1; /* simp == None: core search, minisat.rs:241-260 */
-        }
-        if (lane == 0) {
-            S.sc().eliminated_vars = Z.eliminated_vars;
-            S.sc().elim_n = Z.esizes_n;
-            Z.flush_traffic();
-        }
-        __syncwarp();
-        /* hand the lane-0 state to the whole warp */
-        S.trail_n = bcast(S.trail_n); S.qhead = bcast(S.qhead); S.nlevels = bcast(S.nlevels);
-        n_ingest = bcast(n_ingest); n_pre = bcast(n_pre);
+        const SimpPhaseOut o = simp_phase<VT, COUNT>(&S.P, S.V, S.slab, S.stp, S.lane, S.res_index, S.nvars, cb, ce);
+        S.trail_n = o.trail_n; S.qhead = o.qhead; S.nlevels = o.nlevels;
+        n_ingest = o.n_ingest; n_pre = o.n_pre; pre_ok = o.pre_ok; verdict = o.verdict;
         S.arena = S.arena_half(S.sc().cur_arena);
         S.wpool = S.wpool_half(S.sc().cur_wpool);
         __syncwarp();
-        if (!S.failed() && do_search) {
+        if (!S.failed() && o.do_search) {
             u32 r = S.search();
             verdict = (r == LR_SAT) ? B200SAT_SAT : (r == LR_UNSAT) ? B200SAT_UNSAT : B200SAT_INTERRUPTED;
         }
     }
     __syncwarp();
     S.write_result(inst, verdict, n_ingest, n_pre, pre_ok);
-    if (P.models && !S.failed() && verdict == B200SAT_SAT && S.st().extend_model) {
-        if (lane == 0) {
-            SeqSimp<WarpSolver<VT, COUNT>, COUNT> Z(S);
-            Z.bind_ptrs();
-            Z.esizes_n = S.sc().elim_n;
-            Z.extend_model(P.models + (size_t)S.res_index * P.model_stride);
-        }
-        __syncwarp();
-    }
+    if (P.models && !S.failed() && verdict == B200SAT_SAT && S.st().extend_model)
+        simp_extend_model<VT, COUNT>(&S.P, S.V, S.slab, S.lane, S.res_index);
 }
 
 } // namespace b200sat
