@@ -184,6 +184,9 @@ int b200sat_engine_finish(b200sat_engine *e);
 /* Copy results (and models: n_inst*model_stride bytes, may be NULL) to the host; synchronises. */
 int b200sat_engine_download(b200sat_engine *e, b200sat_result *results, uint8_t *models,
                             uint32_t model_stride, void *stream);
+/* Kernel verify_models: check every SAT model of the last solve against the ORIGINAL resident CNF on the
+ * device (dimacs.rs:90-128).  verified (n_inst bytes, may be NULL): 1 ok, 0 violated, 2 instance not SAT. */
+int b200sat_engine_verify_models(b200sat_engine *e, uint8_t *verified, uint32_t *n_violated, void *stream);
 /* Copy the resident CSR back to the host (sizes via b200sat_engine_batch_dims). */
 int b200sat_engine_batch_dims(b200sat_engine *e, uint32_t *n_inst, uint64_t *n_clauses, uint64_t *n_lits);
 int b200sat_engine_download_batch(b200sat_engine *e, uint32_t *inst_clause_off, uint32_t *clause_off,
@@ -223,6 +226,15 @@ int  b200sat_portfolio_solve(b200sat_engine *e, const b200sat_settings *base, ui
                              uint32_t replica_base, uint32_t share_flags, int flags, void *stream);
 int  b200sat_engine_download_replicas(b200sat_engine *e, b200sat_result *results, uint8_t *models,
                                       uint32_t model_stride, void *stream);
+
+/* ------------------------------------------------------------------ DIMACS I/O (host side)
+ * DIMACS(.gz) file -> CSR, following the reference's parser and its quirks (dimacs.rs:16-43,171-365).
+ * Arrays are malloc'ed; release them with b200sat_free_buffer.  Returns 0 or B200SAT_E_ARG + message. */
+int  b200sat_read_dimacs(const char *path, int strict, uint32_t **clause_off, uint32_t **lits, uint32_t *n_clauses,
+                         uint32_t *hdr_vars, uint32_t *hdr_clauses, char *err, size_t errcap);
+void b200sat_free_buffer(void *p);
+/* dimacs::write_result (dimacs.rs:46-70): "UNSAT" | "INDET" | "SAT\n<lits> 0" */
+int  b200sat_write_result(const char *path, int verdict, const uint8_t *model, uint32_t n_vars);
 
 /* Asynchronous end-to-end form: H2D + solve + D2H enqueued on `stream`; buffers must stay valid
  * (and should be page-locked) until b200sat_solve_batch_finish() returns. */

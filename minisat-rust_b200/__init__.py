@@ -112,6 +112,7 @@ ABI_SYMBOLS = (
     "b200sat_engine_solve_async", "b200sat_engine_finish", "b200sat_solve_batch_async", "b200sat_solve_batch_finish",
     "b200sat_diversify", "b200sat_engine_ring_create", "b200sat_engine_ring_reset", "b200sat_engine_ring_ipc_handle",
     "b200sat_engine_ring_open_peer", "b200sat_portfolio_solve", "b200sat_engine_download_replicas",
+    "b200sat_engine_verify_models", "b200sat_read_dimacs", "b200sat_free_buffer", "b200sat_write_result",
 )
 PF_SHARE, PF_IGNORE_DONE = 1, 2
 
@@ -173,6 +174,12 @@ def lib():
     L.b200sat_engine_ring_open_peer.argtypes = [vp, C.c_uint32, u8p]
     L.b200sat_portfolio_solve.argtypes = [vp, C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp]
     L.b200sat_engine_download_replicas.argtypes = [vp, vp, u8p, C.c_uint32, vp]
+    L.b200sat_engine_verify_models.argtypes = [vp, u8p, u32p, vp]
+    L.b200sat_read_dimacs.argtypes = [C.c_char_p, C.c_int, C.POINTER(u32p), C.POINTER(u32p), u32p, u32p, u32p,
+                                      C.c_char_p, C.c_size_t]
+    L.b200sat_free_buffer.argtypes = [vp]
+    L.b200sat_free_buffer.restype = None
+    L.b200sat_write_result.argtypes = [C.c_char_p, C.c_int, u8p, C.c_uint32]
     _lib = L
     return L
 
@@ -401,6 +408,14 @@ class Engine:
             mp = models.ctypes.data_as(C.POINTER(C.c_uint8))
         _check(lib().b200sat_engine_download(self._e, res.ctypes.data, mp, model_stride or 0, stream))
         return res, models
+
+    def verify_models(self, stream=None):
+        """On-device check of every SAT model against the original CNF -> (verified uint8[n_inst], n_violated)."""
+        n, _, _ = self.dims()
+        ver = np.zeros(max(n, 1), dtype=np.uint8)
+        nv = C.c_uint32()
+        _check(lib().b200sat_engine_verify_models(self._e, ver.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(nv), stream))
+        return ver[:n], nv.value
 
     def download_batch(self):
         n, nc, nl = self.dims()

@@ -86,6 +86,30 @@ __global__ void batch_shape(const u32 *ioff, const u32 *coff, const u32 *lits, u
     }
 }
 
+/* K5: model verification for a whole batch -- one warp per instance walks the ORIGINAL
+ * CNF and checks that every clause holds a literal that is true under the instance's model
+ * (dimacs.rs:90-128 validate_model, formula/util.rs:24-32).  verified[i]: 1 ok, 0 violated, 2 not SAT. */
+__global__ void verify_models(const u32 *ioff, const u32 *coff, const u32 *lits, const b200sat_result *results,
+                              const u8 *models, u32 model_stride, u32 n_inst, u8 *verified, u32 *n_violated) {
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_inst) return;
+    if (results[warp].status != B200SAT_OK || results[warp].verdict != B200SAT_SAT) { if (lane == 0) verified[warp] = 2; return; }
+    const u8 *m = models + (size_t)warp * model_stride;
+    const u32 cb = ioff[warp], ce = ioff[warp + 1];
+    bool bad = false;
+    for (u32 c = cb + lane; c < ce; c += 32) {
+        bool sat = false;
+        for (u32 k = coff[c]; k < coff[c + 1]; k++) {
+            const u32 l = lits[k], v = l >> 1;
+            const u8 val = v < model_stride ? m[v] : (u8)2;
+            if (val != 2 && (val == 1) == ((l & 1) == 0)) { sat = true; break; }
+        }
+        if (!sat) bad = true;
+    }
+    const u32 any = __ballot_sync(0xFFFFFFFFu, bad);
+    if (lane == 0) { verified[warp] = any ? 0 : 1; if (any) atomicAdd(n_violated, 1u); }
+}
+
 __global__ void collect_failed(const b200sat_result *results, const u32 *work, u32 n_work, u32 *out_list, u32 *out_count) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_work) return;
@@ -138,6 +162,8 @@ struct b200sat_engine {
     size_t cap_results = 0;
     u8 *d_models = nullptr;
     size_t cap_models = 0;
+    u8 *d_verified = nullptr;
+    size_t cap_verified = 0;
     u32 model_stride = 0;
     /* work */
     u8 *d_slabs = nullptr;
@@ -214,7 +240,7 @@ extern "C" void b200sat_engine_destroy(b200sat_engine *e) {
     cudaSetDevice(e->device);
     cudaFree(e->d_ioff); cudaFree(e->d_coff); cudaFree(e->d_lits); cudaFree(e->d_results); cudaFree(e->d_models);
     cudaFree(e->d_slabs); cudaFree(e->d_queue); cudaFree(e->d_work[0]); cudaFree(e->d_work[1]);
-    cudaFree(e->d_replica_settings);
+    cudaFree(e->d_replica_settings); cudaFree(e->d_verified);
     for (u32 r = 0; r < 8; r++)
         if (e->rings[r]) { if (e->ring_is_peer[r]) cudaIpcCloseMemHandle(e->rings[r]); else cudaFree(e->rings[r]); }
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
@@ -508,6 +534,25 @@ extern "C" int b200sat_engine_download(b200sat_engine *e, b200sat_result *result
     CK(cudaStreamSynchronize(stream));
     if (models && model_stride > e->model_stride)
         for (u32 i = 0; i < e->n_inst; i++) memset(models + (size_t)i * model_stride + e->model_stride, 2, model_stride - e->model_stride);
+    return 0;
+}
+
+extern "C" int b200sat_engine_verify_models(b200sat_engine *e, uint8_t *verified, uint32_t *n_violated, void *stream_) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(cudaSetDevice(e->device));
+    if (n_violated) *n_violated = 0;
+    if (e->n_inst == 0) return 0;
+    int rc;
+    if ((rc = ensure(e->d_verified, e->cap_verified, (size_t)e->n_inst))) return rc;
+    CK(cudaMemsetAsync(e->d_queue + 2, 0, 4, stream));
+    verify_models<<<(e->n_inst * 32 + 255) / 256, 256, 0, stream>>>(e->d_ioff, e->d_coff, e->d_lits, e->d_results, e->d_models,
+                                                                     e->model_stride, e->n_inst, e->d_verified, e->d_queue + 2);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_pinned + 2, e->d_queue + 2, 4, cudaMemcpyDeviceToHost, stream));
+    if (verified) CK(cudaMemcpyAsync(verified, e->d_verified, e->n_inst, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (n_violated) *n_violated = e->h_pinned[2];
     return 0;
 }
 

@@ -17,6 +17,7 @@ exactly the add_clause sequence the reference parser would issue.
 """
 import gzip
 import io
+import os
 
 import numpy as np
 
@@ -170,7 +171,23 @@ def read_csr_text(text, validate=False):
 
 
 def read_csr(path, validate=False):
-    return read_csr_text(_read_text(path), validate)
+    """File -> CSR through the library's C++ reader (b200sat_read_dimacs); same quirks as `read_csr_text`."""
+    import ctypes as C
+    from . import lib
+    u32p = C.POINTER(C.c_uint32)
+    offp, litp = u32p(), u32p()
+    n, hv, hc = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    err = C.create_string_buffer(512)
+    rc = lib().b200sat_read_dimacs(os.fsencode(path), int(validate), C.byref(offp), C.byref(litp), C.byref(n),
+                                   C.byref(hv), C.byref(hc), err, 512)
+    if rc != 0:
+        raise ParseError(err.value.decode())
+    off = np.ctypeslib.as_array(offp, shape=(n.value + 1,)).copy()
+    nl = int(off[-1])
+    lits = np.ctypeslib.as_array(litp, shape=(max(nl, 1),))[:nl].copy()
+    lib().b200sat_free_buffer(offp)
+    lib().b200sat_free_buffer(litp)
+    return off, lits, hv.value, hc.value
 
 
 def concat_csr(instances):

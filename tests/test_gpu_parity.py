@@ -87,6 +87,8 @@ def test_config2_full_size_properties(pkg, po, eng):
     assert set(np.unique(res["verdict"])) <= {0, 1}
     ioff, coff, lits = eng.download_batch()
     assert check_models(ioff, coff, lits, res["verdict"], models) == 0
+    ver, n_bad = eng.verify_models()            # the same check on the device (kernel verify_models)
+    assert n_bad == 0 and ((ver == 1) == (res["verdict"] == 1)).all() and ((ver == 2) == (res["verdict"] != 1)).all()
     eng.solve(kind=pkg.CORE, flags=flags(pkg) & ~pkg.F_COUNT_TRAFFIC)
     res2, models2 = eng.download(model_stride=100)
     assert (res2["stats"] == res["stats"]).all() and (res2["trace_hash"] == res["trace_hash"]).all()
