@@ -213,7 +213,8 @@ int b200sat_solve_batch(b200sat_engine *e, const b200sat_batch *batch, const b20
  * NVLink P2P.  The first replica that finishes raises a `done` word in every ring and the others
  * stop at their next conflict (the Budget / interrupt analogue, budget.rs:5-34).  Replica 0 keeps the
  * base settings: with sharing off its trace is bit-exact the single-instance one. */
-enum { B200SAT_PF_SHARE = 1, B200SAT_PF_IGNORE_DONE = 2 };
+enum { B200SAT_PF_SHARE = 1 /* units + binaries */, B200SAT_PF_IGNORE_DONE = 2,
+       B200SAT_PF_SHARE_LBD2 = 4 /* also LBD <= 2 clauses of <= 8 literals */ };
 /* settings of global replica `replica` derived from `base` (replica 0 = base) -- SURVEY.md T19 */
 void b200sat_diversify(const b200sat_settings *base, uint32_t replica, b200sat_settings *out);
 int  b200sat_engine_ring_create(b200sat_engine *e, uint32_t payload_words, uint32_t n_rings, uint32_t my_slot);

@@ -114,7 +114,7 @@ ABI_SYMBOLS = (
     "b200sat_engine_ring_open_peer", "b200sat_portfolio_solve", "b200sat_engine_download_replicas",
     "b200sat_engine_verify_models", "b200sat_read_dimacs", "b200sat_free_buffer", "b200sat_write_result",
 )
-PF_SHARE, PF_IGNORE_DONE = 1, 2
+PF_SHARE, PF_IGNORE_DONE, PF_SHARE_LBD2 = 1, 2, 4
 
 _lib = None
 

@@ -141,7 +141,7 @@ struct KParams {
     const b200sat_settings *replica_settings; /* [portfolio] diversified settings                      */
 };
 
-enum : u32 { PF_SHARE = 1, PF_IGNORE_DONE = 2 };
+enum : u32 { PF_SHARE = 1, PF_IGNORE_DONE = 2, PF_SHARE_LBD2 = 4 };
 /* ring header words */
 enum : u32 { RING_HEAD = 0, RING_DONE = 1, RING_EXPORTS = 2, RING_PAYLOAD = 16 };
 static const u32 ST_CANCELLED = 20;

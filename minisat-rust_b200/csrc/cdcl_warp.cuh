@@ -217,6 +217,7 @@ template <class VT, bool COUNT> struct WarpSolver {
     DEV bool is_false(u32 lit) const { return lval(lit) == 0; }
     DEV bool failed() const { return sc().status != ST_OK; }
     DEV void fail(u32 code) {
+        __syncwarp(); /* lagging lanes may still be reading status in failed() */
         if (lane == 0 && sc().status == ST_OK) sc().status = code;
         __syncwarp();
     }
@@ -1240,7 +1241,9 @@ template <class VT, bool COUNT> struct WarpSolver {
     DEV static u32 ld_vol(const u32 *p) { return *(const volatile u32 *)p; }
     DEV bool cancelled() {
         if (!P.portfolio || (P.share & PF_IGNORE_DONE)) return false;
-        return ld_vol(P.rings[P.my_ring] + RING_DONE) != 0;
+        u32 v = 0; /* one lane reads, all lanes agree: another GPU may raise the flag at any moment */
+        if (lane == 0) v = ld_vol(P.rings[P.my_ring] + RING_DONE);
+        return bcast(v) != 0;
     }
     DEV void announce_done() {
         if (!P.portfolio) return;
@@ -1252,7 +1255,11 @@ template <class VT, bool COUNT> struct WarpSolver {
     }
     /* called with the learnt clause in ol()[0..n) BEFORE backtracking (levels still valid) */
     DEV void export_clause(u32 n) {
-        if (n > 30) return;
+        /* PF_SHARE alone: units and binaries; PF_SHARE_LBD2 adds LBD <= 2 clauses of at most 8 literals.
+         * (Round-1 measurement: exporting every LBD <= 2 clause up to 30 literals floods the importers --
+         * 1,024 replicas each took ~80 k clauses -- and a second GPU made the run slower, not faster.) */
+        const u32 max_len = (P.share & PF_SHARE_LBD2) ? 8u : 2u;
+        if (n > max_len) return;
         const u32 *out = ol();
         u32 lit = lane < n ? out[lane] : 0;
         u32 lbd = 0;

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--index", type=int, default=0, help="instance index in the config-3 seed sequence")
     ap.add_argument("--replicas", type=int, default=2048, help="replicas per GPU")
     ap.add_argument("--no-share", action="store_true")
+    ap.add_argument("--lbd2", action="store_true", help="also exchange LBD<=2 clauses of <= 8 literals")
     ap.add_argument("--single", action="store_true", help="also time replica 0 alone (the reference configuration)")
     a = ap.parse_args()
     import torch
@@ -46,7 +47,7 @@ def main():
             if r != rank:
                 eng.ring_open_peer(r, handles[r])
         dist.barrier()
-    share = 0 if a.no_share else pkg.PF_SHARE
+    share = 0 if a.no_share else (pkg.PF_SHARE | (pkg.PF_SHARE_LBD2 if a.lbd2 else 0))
     out = {}
     if a.single and rank == 0:
         t0 = time.perf_counter()
