@@ -4,5 +4,5 @@ for v in "$@"; do
   echo "== $v"
   if [ "$v" = base ]; then unset B200SAT_LIB; else export B200SAT_LIB=/root/repo/minisat-rust_b200/variants/$v.so; fi
   timeout 100 python tools/gpu_one.py 10000 100 0 0 2>&1 | tail -1 | sed "s/.*last_kernel_ms/ n100 full ms/"
-  timeout 200 python tools/gpu_one.py 16 250 0 0 2>&1 | tail -1 | sed "s/.*last_kernel_ms/ n250 x16 ms/"
+  timeout 100 python tools/gpu_one.py 40000 100 0 0 2>&1 | tail -1 | sed "s/.*last_kernel_ms/ n100 x40k ms/"
 done
