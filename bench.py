@@ -130,7 +130,7 @@ def run_reference(a):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(a, m), "sample": sample,
                    "note": "reference arm = C++ oracle port of minisat-rust (Rust toolchain absent); CPU only"},
         "propagations_per_sec": p_tot / t_tot,
@@ -300,7 +300,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(a, m), "instances_per_gpu": B, "n_vars": n, "n_clauses": m,
                        "seed_base": hex(SEED_BASE), "l2": "256 MiB memset between steps (L2 flush)",
                        "pipeline": "%d batches in flight on %d engines/streams" % (NS, NS),

@@ -15,7 +15,11 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def pkg():
+    import subprocess
     import _b200pkg
+    lib_path = os.path.join(ROOT, "minisat-rust_b200", "libb200sat.so")
+    if not os.path.exists(lib_path):   # fresh checkout: the built .so files are git-ignored
+        subprocess.run(["make", "-C", os.path.join(ROOT, "minisat-rust_b200", "csrc")], check=True)
     return _b200pkg.load()
 
 
