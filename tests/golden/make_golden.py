@@ -73,5 +73,34 @@ def main():
     build(wide, "corpus_wide.npz")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--hard" not in sys.argv:
     main()
+
+
+def build_hard(pick, out_name):
+    """BASELINE.json configs[3]: structured tests/cnf-hard instances, SimpSolver PREPROCESSING ONLY
+    (--no-solve): the oracle's elimination result (clauses left, eliminated vars, propagations)."""
+    names, insts, rows = [], [], []
+    for rel in pick:
+        off, lits, hv, hc = po.parse_dimacs(os.path.join(REF, rel))
+        r, _ = po.solve_csr(off, lits, kind=po.SIMP, flags=po.F_PREPROCESS | po.F_NO_SOLVE)
+        names.append(os.path.basename(rel))
+        insts.append((off, lits))
+        rows.append([r.n_vars, r.n_clauses_ingest, r.n_clauses_pre, r.eliminated_vars, r.pre_ok] + list(r.stats))
+    ioff = [0]
+    coffs, alll, base = [np.zeros(1, np.uint32)], [], 0
+    for off, lits in insts:
+        coffs.append((off[1:].astype(np.uint64) + base).astype(np.uint32))
+        alll.append(lits)
+        base += int(off[-1])
+        ioff.append(ioff[-1] + len(off) - 1)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), out_name), names=np.array(names),
+                        inst_clause_off=np.array(ioff, np.uint32), clause_off=np.concatenate(coffs),
+                        lits=np.concatenate(alll), rows=np.array(rows, dtype=np.uint64))
+    print("wrote", len(names), "instances to", out_name)
+
+
+if __name__ == "__main__" and "--hard" in sys.argv:
+    build_hard(["cnf-hard/2bitadd_10.cnf.gz", "cnf-hard/3bitadd_32.cnf.gz", "cnf-hard/grieu-vmpc-s05-24s.cnf.gz",
+                "cnf-hard/e0ddr2-10-by-5-1.cnf.gz", "cnf-hard/manol-pipe-f6b.cnf.gz", "cnf-hard/stric-bmc-ibm-12.cnf.gz"],
+               "corpus_hard.npz")
