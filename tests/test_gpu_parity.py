@@ -289,3 +289,24 @@ def test_config1_wide_corpus(pkg, po, eng, kind_name):
         assert (res["eliminated_vars"] == g["simp_elim"]).all() and (res["n_clauses_pre"] == g["simp_nclauses_pre"]).all()
     assert check_models(ioff, coff, lits, res["verdict"], models) == 0
     assert n > 200
+
+
+def test_config4_cnf_hard_preprocessing(pkg, po):
+    """BASELINE.json configs[3]: SimpSolver preprocessing (backward subsumption, strengthening, BVE, simplifier GC)
+    of structured tests/cnf-hard instances (up to 39,598 vars / 193,434 clauses, global tier) with --no-solve:
+    clauses left, eliminated vars, pre_ok and the 8 stats == the oracle's elimination result."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "corpus_hard.npz"))
+    e = pkg.Engine(0)
+    for i, name in enumerate(g["names"]):
+        cb, ce = int(g["inst_clause_off"][i]), int(g["inst_clause_off"][i + 1])
+        off = g["clause_off"][cb:ce + 1].astype(np.int64)
+        lits = g["lits"][off[0]:off[-1]]
+        ioff, coff, li = batch_of([((off - off[0]).astype(np.uint32), lits)])
+        res, _ = e.solve_batch(ioff, coff, li, kind=pkg.SIMP, flags=pkg.F_PREPROCESS | pkg.F_NO_SOLVE)
+        r = res[0]
+        mine = [int(r["n_vars"]), int(r["n_clauses_ingest"]), int(r["n_clauses_pre"]), int(r["eliminated_vars"]),
+                int(r["pre_ok"])] + [int(x) for x in r["stats"]]
+        assert r["status"] == 0, name
+        assert mine == [int(x) for x in g["rows"][i]], name
+    e.close()
