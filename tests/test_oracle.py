@@ -95,3 +95,30 @@ def test_write_result_format(pkg):
     assert pkg.dimacs.result_string(pkg.SolveRes(pkg.INTERRUPTED, pkg.Stats())) == "INDET\n"
     assert pkg.dimacs.validate_model_text("p cnf 3 2\n1 -2 0\n2 3 0\n", res.model)
     assert not pkg.dimacs.validate_model_text("p cnf 3 1\n-1 2 -3 0\n", res.model)
+
+
+def test_cxx_dimacs_reader_quirks(pkg, tmp_path):
+    """b200sat_read_dimacs (csrc/dimacs_io.cpp) keeps the reference parser's quirks (dimacs.rs:171-365)."""
+    def rd(text, **kw):
+        p = tmp_path / "q.cnf"
+        p.write_text(text)
+        return pkg.dimacs.read_csr(str(p), **kw)
+    off, lits, hv, hc = rd("c x\nc y\np cnf 3 2\n+1 -2 0 3\n0\n")                 # '+' sign, clause split over lines
+    assert list(off) == [0, 2, 3] and list(lits) == [0, 3, 4] and (hv, hc) == (3, 2)
+    off, lits, hv, hc = rd("p cnf 1 1\n1 0\n")                                       # header counts are not checked ...
+    off2, _, _, _ = rd("p cnf 9 9\n1 0\n")
+    assert list(off) == list(off2)
+    for bad in ("p cnf 1 1\n1 0\n%\n0\n", "1 2 0\n", "p cnf x 1\n", "p cnf 1 1\n1 a 0\n"):
+        with pytest.raises(IOError):
+            rd(bad)
+    with pytest.raises(IOError):
+        rd("p cnf 2 3\n1 2 0\n", validate=True)                                      # ... unless --strict
+    with pytest.raises(IOError):
+        rd("p cnf 1 1\n1 2 0\n", validate=True)
+    with pytest.raises(IOError):
+        pkg.dimacs.read_csr(str(tmp_path / "missing.cnf"))
+    # text reader and C++ reader agree
+    t = "c c\np cnf 4 3\n1 -2 0\n-3 4 -1 0\nc mid\n2 0\n"
+    a = rd(t)
+    b = pkg.dimacs.read_csr_text(t)
+    assert list(a[0]) == list(b[0]) and list(a[1]) == list(b[1])
