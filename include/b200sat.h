@@ -187,6 +187,15 @@ int b200sat_engine_download(b200sat_engine *e, b200sat_result *results, uint8_t 
 /* Kernel verify_models: check every SAT model of the last solve against the ORIGINAL resident CNF on the
  * device (dimacs.rs:90-128).  verified (n_inst bytes, may be NULL): 1 ok, 0 violated, 2 instance not SAT. */
 int b200sat_engine_verify_models(b200sat_engine *e, uint8_t *verified, uint32_t *n_violated, void *stream);
+/* K4: multi-CTA backward subsumption of ONE (large) instance of the resident batch with the
+ * occurrence-list kernel set of csrc/preprocess_kernels.cu (signature filter, segmented sort of the occurrence
+ * lists, prefix-sum compaction).  Not the reference's sequential job order: the result is the order-independent
+ * set {D : some other clause C is a subset of D}; equivalence-preserving.  removed: one byte per clause of the
+ * instance (may be NULL); out_clause_off (kept+1 entries, relative offsets) / out_lits: the compacted CSR (may be
+ * NULL; size them with the instance's clause / literal counts); counts = {kept clauses, kept literals,
+ * full subset tests, removed clauses}. */
+int b200sat_engine_subsume_instance(b200sat_engine *e, uint32_t inst, uint8_t *removed, uint32_t *out_clause_off,
+                                    uint32_t *out_lits, uint32_t counts[4], float *kernel_ms, void *stream);
 /* Copy the resident CSR back to the host (sizes via b200sat_engine_batch_dims). */
 int b200sat_engine_batch_dims(b200sat_engine *e, uint32_t *n_inst, uint64_t *n_clauses, uint64_t *n_lits);
 int b200sat_engine_download_batch(b200sat_engine *e, uint32_t *inst_clause_off, uint32_t *clause_off,

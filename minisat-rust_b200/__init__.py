@@ -112,7 +112,7 @@ ABI_SYMBOLS = (
     "b200sat_engine_solve_async", "b200sat_engine_finish", "b200sat_solve_batch_async", "b200sat_solve_batch_finish",
     "b200sat_diversify", "b200sat_engine_ring_create", "b200sat_engine_ring_reset", "b200sat_engine_ring_ipc_handle",
     "b200sat_engine_ring_open_peer", "b200sat_portfolio_solve", "b200sat_engine_download_replicas",
-    "b200sat_engine_verify_models", "b200sat_read_dimacs", "b200sat_free_buffer", "b200sat_write_result",
+    "b200sat_engine_verify_models", "b200sat_engine_subsume_instance", "b200sat_read_dimacs", "b200sat_free_buffer", "b200sat_write_result",
 )
 PF_SHARE, PF_IGNORE_DONE, PF_SHARE_LBD2 = 1, 2, 4
 
@@ -175,6 +175,7 @@ def lib():
     L.b200sat_portfolio_solve.argtypes = [vp, C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp]
     L.b200sat_engine_download_replicas.argtypes = [vp, vp, u8p, C.c_uint32, vp]
     L.b200sat_engine_verify_models.argtypes = [vp, u8p, u32p, vp]
+    L.b200sat_engine_subsume_instance.argtypes = [vp, C.c_uint32, u8p, u32p, u32p, u32p, C.POINTER(C.c_float), vp]
     L.b200sat_read_dimacs.argtypes = [C.c_char_p, C.c_int, C.POINTER(u32p), C.POINTER(u32p), u32p, u32p, u32p,
                                       C.c_char_p, C.c_size_t]
     L.b200sat_free_buffer.argtypes = [vp]
@@ -416,6 +417,21 @@ class Engine:
         nv = C.c_uint32()
         _check(lib().b200sat_engine_verify_models(self._e, ver.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(nv), stream))
         return ver[:n], nv.value
+
+    def subsume_instance(self, inst, n_clauses, n_lits, stream=None):
+        """K4 multi-CTA backward subsumption of instance `inst` of the resident batch ->
+        dict(removed uint8[n_clauses], clause_off, lits (compacted CSR), kept, kept_lits, tests, removed_count, kernel_ms)."""
+        u32p = C.POINTER(C.c_uint32)
+        removed = np.zeros(max(n_clauses, 1), np.uint8)
+        ooff = np.zeros(n_clauses + 2, np.uint32)
+        olits = np.zeros(max(n_lits, 1), np.uint32)
+        counts = (C.c_uint32 * 4)()
+        ms = C.c_float()
+        _check(lib().b200sat_engine_subsume_instance(self._e, inst, removed.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                     ooff.ctypes.data_as(u32p), olits.ctypes.data_as(u32p), counts, C.byref(ms), stream))
+        kept, kept_lits = counts[0], counts[1]
+        return {"removed": removed[:n_clauses], "clause_off": ooff[:kept + 1], "lits": olits[:kept_lits], "kept": kept,
+                "kept_lits": kept_lits, "tests": counts[2], "removed_count": counts[3], "kernel_ms": ms.value}
 
     def download_batch(self):
         n, nc, nl = self.dims()

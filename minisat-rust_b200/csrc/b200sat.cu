@@ -164,6 +164,8 @@ struct b200sat_engine {
     size_t cap_models = 0;
     u8 *d_verified = nullptr;
     size_t cap_verified = 0;
+    u32 *d_pp = nullptr;          /* scratch of the K4 preprocessing kernels */
+    size_t cap_pp = 0;
     u32 model_stride = 0;
     /* work */
     u8 *d_slabs = nullptr;
@@ -240,7 +242,7 @@ extern "C" void b200sat_engine_destroy(b200sat_engine *e) {
     cudaSetDevice(e->device);
     cudaFree(e->d_ioff); cudaFree(e->d_coff); cudaFree(e->d_lits); cudaFree(e->d_results); cudaFree(e->d_models);
     cudaFree(e->d_slabs); cudaFree(e->d_queue); cudaFree(e->d_work[0]); cudaFree(e->d_work[1]);
-    cudaFree(e->d_replica_settings); cudaFree(e->d_verified);
+    cudaFree(e->d_replica_settings); cudaFree(e->d_verified); cudaFree(e->d_pp);
     for (u32 r = 0; r < 8; r++)
         if (e->rings[r]) { if (e->ring_is_peer[r]) cudaIpcCloseMemHandle(e->rings[r]); else cudaFree(e->rings[r]); }
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
@@ -553,6 +555,49 @@ extern "C" int b200sat_engine_verify_models(b200sat_engine *e, uint8_t *verified
     if (verified) CK(cudaMemcpyAsync(verified, e->d_verified, e->n_inst, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     if (n_violated) *n_violated = e->h_pinned[2];
+    return 0;
+}
+
+/* K4: multi-CTA subsumption of one large instance (csrc/preprocess_kernels.cu) */
+extern "C" size_t b200sat_pp_scratch_words(size_t nc, size_t nvars, size_t nlits);
+extern "C" int b200sat_pp_subsume_launch(const u32 *d_coff, const u32 *d_lits, u32 cb, u32 nc, u32 nvars, u32 nlits, u32 *scratch,
+                                         u8 *d_removed, u32 *d_out_coff, u32 *d_out_lits, u32 *d_counts, cudaStream_t stream);
+
+extern "C" int b200sat_engine_subsume_instance(b200sat_engine *e, uint32_t inst, uint8_t *removed, uint32_t *out_clause_off,
+                                               uint32_t *out_lits, uint32_t counts[4], float *kernel_ms, void *stream_) {
+    if (!e || inst >= e->n_inst) return set_err(B200SAT_E_ARG, "bad instance index");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(cudaSetDevice(e->device));
+    u32 io[2], lo[2];
+    CK(cudaMemcpy(io, e->d_ioff + inst, 8, cudaMemcpyDeviceToHost));
+    const u32 cb = io[0], nc = io[1] - io[0];
+    if (nc == 0) { if (counts) counts[0] = counts[1] = counts[2] = counts[3] = 0; return 0; }
+    CK(cudaMemcpy(&lo[0], e->d_coff + cb, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&lo[1], e->d_coff + cb + nc, 4, cudaMemcpyDeviceToHost));
+    const u32 nlits = lo[1] - lo[0], nvars = e->shape.max_vars;
+    int rc;
+    size_t words = b200sat_pp_scratch_words(nc, nvars, nlits) + (size_t)nc + 2 + nlits + 8;
+    if ((rc = ensure(e->d_pp, e->cap_pp, words))) return rc;
+    if ((rc = ensure(e->d_verified, e->cap_verified, (size_t)nc))) return rc;
+    u32 *scratch = e->d_pp;
+    u32 *d_out_coff = scratch + b200sat_pp_scratch_words(nc, nvars, nlits);
+    u32 *d_out_lits = d_out_coff + nc + 2;
+    u32 *d_counts = e->d_queue + 16;
+    CK(cudaEventRecord(e->ev0, stream));
+    if (b200sat_pp_subsume_launch(e->d_coff, e->d_lits, cb, nc, nvars, nlits, scratch, e->d_verified, d_out_coff, d_out_lits, d_counts, stream))
+        return set_err(B200SAT_E_CUDA, "preprocess kernel launch failed");
+    CK(cudaEventRecord(e->ev1, stream));
+    CK(cudaMemcpyAsync(e->h_pinned + 16, d_counts, 16, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const u32 kept = e->h_pinned[16], kept_lits = e->h_pinned[17];
+    if (counts) { counts[0] = kept; counts[1] = kept_lits; counts[2] = e->h_pinned[18]; counts[3] = nc - kept; }
+    if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, e->ev0, e->ev1));
+    if (removed) CK(cudaMemcpy(removed, e->d_verified, nc, cudaMemcpyDeviceToHost));
+    if (out_clause_off) {
+        CK(cudaMemcpy(out_clause_off, d_out_coff, (size_t)kept * 4, cudaMemcpyDeviceToHost));
+        out_clause_off[kept] = kept_lits;
+    }
+    if (out_lits && kept_lits) CK(cudaMemcpy(out_lits, d_out_lits, (size_t)kept_lits * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 

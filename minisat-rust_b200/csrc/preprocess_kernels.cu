@@ -1,0 +1,171 @@
+/*
+ * preprocess_kernels.cu -- K4: throughput-oriented, multi-CTA preprocessing of ONE large instance.
+ *
+ * Round-1 scope: backward subsumption over occurrence lists (the `subsumes()` test of the reference,
+ * src/sat/minisat/search/simplify/subsumes.rs:10-49, and the signature of src/sat/formula/util.rs:5-11), i.e.
+ *   pp_sig_len      thread per clause: 32-bit signature (1 << (var & 31)) and length
+ *   pp_occ_count    thread per clause: per-VARIABLE occurrence histogram (OccLists are per var, elim_queue.rs:85-151)
+ *   pp_scan         exclusive prefix sum (occurrence-list offsets / compacted clause offsets)
+ *   pp_occ_fill     thread per clause: scatter clause ids into the occurrence lists
+ *   pp_occ_sort     warp per variable: segmented sort of every occurrence list by clause id (canonical order)
+ *   pp_subsume      warp per clause C: candidates = occurrence list of C's least-occurring variable; a lane
+ *                   tests one candidate D: size filter, signature filter, then the literal subset test
+ *   pp_compact      scatter of the surviving clauses to their prefix-sum offsets (new CSR)
+ * A clause D is removed iff some other clause C is a subset of D and (|C| < |D| or C has the smaller index), so
+ * the result does not depend on scheduling order.  This is NOT the reference's sequential job order (no
+ * strengthening, no BVE here): its parity is the S* definition of SURVEY.md 8a -- the reduced formula is
+ * equivalent to the input, every removed clause has a surviving subset clause, verdicts agree -- and the
+ * clause counts are reported beside the oracle's.  The trace-exact simplifier is csrc/simp_warp.cuh.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef uint8_t u8;
+
+__global__ void pp_sig_len(const u32 *coff, const u32 *lits, u32 cb, u32 nc, u32 *sig, u32 *len, u8 *removed) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    u32 b = coff[cb + c], e = coff[cb + c + 1], s = 0;
+    for (u32 k = b; k < e; k++) s |= 1u << ((lits[k] >> 1) & 31);
+    sig[c] = s;
+    len[c] = e - b;
+    removed[c] = 0;
+}
+
+__global__ void pp_occ_count(const u32 *coff, const u32 *lits, u32 cb, u32 nc, u32 *occ_cnt) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    for (u32 k = coff[cb + c]; k < coff[cb + c + 1]; k++) atomicAdd(&occ_cnt[lits[k] >> 1], 1u);
+}
+
+/* single-block exclusive scan of n values (n up to a few million): out[i] = sum(in[0..i)), out[n] = total */
+__global__ void pp_scan(const u32 *in, u32 *out, u32 n) {
+    __shared__ u32 part[1024];
+    __shared__ u32 carry;
+    const u32 t = threadIdx.x;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (u32 base = 0; base < n; base += 1024) {
+        u32 i = base + t;
+        u32 v = i < n ? in[i] : 0;
+        part[t] = v;
+        __syncthreads();
+        for (u32 o = 1; o < 1024; o <<= 1) {
+            u32 y = t >= o ? part[t - o] : 0;
+            __syncthreads();
+            part[t] += y;
+            __syncthreads();
+        }
+        if (i < n) out[i] = carry + part[t] - v;
+        __syncthreads();
+        if (t == 0) carry += part[1023];
+        __syncthreads();
+    }
+    if (t == 0) out[n] = carry;
+}
+
+__global__ void pp_occ_fill(const u32 *coff, const u32 *lits, u32 cb, u32 nc, const u32 *occ_off, u32 *cursor, u32 *occ) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    for (u32 k = coff[cb + c]; k < coff[cb + c + 1]; k++) {
+        u32 v = lits[k] >> 1;
+        occ[occ_off[v] + atomicAdd(&cursor[v], 1u)] = c;
+    }
+}
+
+/* segmented sort: one warp per occurrence list, odd-even transposition over the segment */
+__global__ void pp_occ_sort(const u32 *occ_off, u32 *occ, u32 nvars) {
+    const u32 v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (v >= nvars) return;
+    u32 *seg = occ + occ_off[v];
+    const u32 n = occ_off[v + 1] - occ_off[v];
+    if (n > 2048) return; /* very long lists stay in scatter order (order only affects traversal, not the result) */
+    for (u32 pass = 0; pass < n; pass++) {
+        for (u32 i = (pass & 1) + 2 * lane; i + 1 < n; i += 64) {
+            u32 a = seg[i], b = seg[i + 1];
+            if (a > b) { seg[i] = b; seg[i + 1] = a; }
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ bool pp_subset(const u32 *lits, u32 cb_, u32 ce_, u32 db, u32 de) {
+    for (u32 i = cb_; i < ce_; i++) { /* subsumes.rs:27-47 without the LitSign case */
+        u32 l = lits[i];
+        bool found = false;
+        for (u32 j = db; j < de; j++) if (lits[j] == l) { found = true; break; }
+        if (!found) return false;
+    }
+    return true;
+}
+
+__global__ void pp_subsume(const u32 *coff, const u32 *lits, u32 cb, u32 nc, const u32 *sig, const u32 *len, const u32 *occ_off,
+                           const u32 *occ, u8 *removed, u32 *n_tests) {
+    const u32 c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= nc) return;
+    const u32 b = coff[cb + c], e = coff[cb + c + 1];
+    if (e == b) return;
+    u32 best = lits[b] >> 1, bestn = occ_off[best + 1] - occ_off[best];
+    for (u32 k = b + 1; k < e; k++) { /* simplify.rs:459-476: the variable with the shortest occurrence list */
+        u32 v = lits[k] >> 1, n = occ_off[v + 1] - occ_off[v];
+        if (n < bestn) { best = v; bestn = n; }
+    }
+    const u32 sc = sig[c], lc = len[c];
+    u32 tests = 0;
+    for (u32 i = lane; i < bestn; i += 32) {
+        const u32 d = occ[occ_off[best] + i];
+        if (d == c || len[d] < lc || (sc & ~sig[d]) != 0) continue; /* size + signature filter, subsumes.rs:15-21 */
+        tests++;
+        if (pp_subset(lits, b, e, coff[cb + d], coff[cb + d + 1]) && (lc < len[d] || c < d)) removed[d] = 1;
+    }
+    if (tests) atomicAdd(n_tests, tests);
+}
+
+__global__ void pp_kept_len(const u32 *len, const u8 *removed, u32 nc, u32 *kept_len, u32 *kept_flag) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    kept_len[c] = removed[c] ? 0 : len[c];
+    kept_flag[c] = removed[c] ? 0 : 1;
+}
+
+__global__ void pp_compact(const u32 *coff, const u32 *lits, u32 cb, u32 nc, const u8 *removed, const u32 *new_idx, const u32 *new_off,
+                           u32 *out_coff, u32 *out_lits) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc || removed[c]) return;
+    const u32 base = coff[cb + c], n = coff[cb + c + 1] - base, o = new_off[c];
+    out_coff[new_idx[c]] = o;
+    for (u32 k = 0; k < n; k++) out_lits[o + k] = lits[base + k];
+}
+
+/* host launcher: everything on `stream`; scratch = device buffer of at least pp_scratch_words(nc, nvars, nlits) words */
+extern "C" size_t b200sat_pp_scratch_words(size_t nc, size_t nvars, size_t nlits) {
+    return 8 * (nc + 2) + 4 * (nvars + 2) + 2 * (nlits + 2) + 64;
+}
+
+extern "C" int b200sat_pp_subsume_launch(const u32 *d_coff, const u32 *d_lits, u32 cb, u32 nc, u32 nvars, u32 nlits, u32 *scratch,
+                                         u8 *d_removed, u32 *d_out_coff, u32 *d_out_lits, u32 *d_counts /* [0] kept clauses, [1] kept lits, [2] tests */,
+                                         cudaStream_t stream) {
+    u32 *sig = scratch, *len = sig + nc + 2, *kept_len = len + nc + 2, *kept_flag = kept_len + nc + 2, *new_off = kept_flag + nc + 2,
+        *new_idx = new_off + nc + 2, *occ_cnt = new_idx + nc + 2, *occ_off = occ_cnt + nvars + 2, *cursor = occ_off + nvars + 2,
+        *occ = cursor + nvars + 2;
+    const u32 T = 256, gc = (nc + T - 1) / T;
+    cudaMemsetAsync(occ_cnt, 0, (size_t)(nvars + 2) * 4, stream);
+    cudaMemsetAsync(cursor, 0, (size_t)(nvars + 2) * 4, stream);
+    cudaMemsetAsync(d_counts, 0, 16, stream);
+    pp_sig_len<<<gc, T, 0, stream>>>(d_coff, d_lits, cb, nc, sig, len, d_removed);
+    pp_occ_count<<<gc, T, 0, stream>>>(d_coff, d_lits, cb, nc, occ_cnt);
+    pp_scan<<<1, 1024, 0, stream>>>(occ_cnt, occ_off, nvars);
+    pp_occ_fill<<<gc, T, 0, stream>>>(d_coff, d_lits, cb, nc, occ_off, cursor, occ);
+    pp_occ_sort<<<(nvars * 32 + T - 1) / T, T, 0, stream>>>(occ_off, occ, nvars);
+    pp_subsume<<<(u32)(((u64)nc * 32 + T - 1) / T), T, 0, stream>>>(d_coff, d_lits, cb, nc, sig, len, occ_off, occ, d_removed, d_counts + 2);
+    pp_kept_len<<<gc, T, 0, stream>>>(len, d_removed, nc, kept_len, kept_flag);
+    pp_scan<<<1, 1024, 0, stream>>>(kept_len, new_off, nc);
+    pp_scan<<<1, 1024, 0, stream>>>(kept_flag, new_idx, nc);
+    pp_compact<<<gc, T, 0, stream>>>(d_coff, d_lits, cb, nc, d_removed, new_idx, new_off, d_out_coff, d_out_lits);
+    cudaMemcpyAsync(d_counts + 0, new_idx + nc, 4, cudaMemcpyDeviceToDevice, stream);
+    cudaMemcpyAsync(d_counts + 1, new_off + nc, 4, cudaMemcpyDeviceToDevice, stream);
+    (void)nlits;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}

@@ -310,3 +310,86 @@ def test_config4_cnf_hard_preprocessing(pkg, po):
         assert r["status"] == 0, name
         assert mine == [int(x) for x in g["rows"][i]], name
     e.close()
+
+
+# ---------------------------------------------------------------- K4: multi-CTA subsumption of one large instance
+def _subsumption_oracle(off, lits):
+    """Order-independent reference: D removed iff another clause C is a subset of D and (|C| < |D| or C < D)."""
+    cls = [frozenset(int(x) for x in lits[off[c]:off[c + 1]]) for c in range(len(off) - 1)]
+    by_lit = {}
+    for c, s in enumerate(cls):
+        for l in s:
+            by_lit.setdefault(l, []).append(c)
+    removed = np.zeros(len(cls), np.uint8)
+    for d, sd in enumerate(cls):
+        for c in range(len(cls)):
+            if c != d and cls[c] <= sd and (len(cls[c]) < len(sd) or c < d):
+                removed[d] = 1
+                break
+    return removed
+
+
+def test_k4_subsumption_kernels(pkg, po):
+    e = pkg.Engine(0)
+    # 1. hand-made: proper subsets, duplicates, permuted duplicates, unit subsumption
+    cl = [[1, 2], [1, 2, 3], [1, 2], [-1, 2, 3], [2, 3, -1, 4], [5], [5, 6], [7, 8], [8, 7], [9, -10], [9, 10]]
+    off, lits = csr_of(cl)
+    ioff, coff, li = batch_of([(off, lits)])
+    e.upload(ioff, coff, li)
+    r = e.subsume_instance(0, len(cl), len(lits))
+    assert list(r["removed"]) == [0, 1, 1, 0, 1, 0, 1, 0, 1, 0, 0]
+    assert r["kept"] == 6 and r["removed_count"] == 5
+    kept = [cl[i] for i in range(len(cl)) if not r["removed"][i]]
+    got = [[(int(l >> 1) + 1) * (-1 if l & 1 else 1) for l in r["lits"][r["clause_off"][k]:r["clause_off"][k + 1]]] for k in range(r["kept"])]
+    assert got == kept                                   # prefix-sum compaction keeps clause order and literals
+    # 2. random instance with planted supersets: equals the brute-force definition, and stays equivalent
+    off, lits = golden_instance(load_golden(), list(load_golden()["names"]).index("uf50-04.cnf.gz"))
+    rng = np.random.default_rng(5)
+    base = [[int(x) for x in lits[off[c]:off[c + 1]]] for c in range(len(off) - 1)]
+    extra = []
+    for c in rng.choice(len(base), 120, replace=False):
+        add = [int(x) for x in rng.choice(100, 2, replace=False) if (int(x) >> 1) not in {l >> 1 for l in base[c]}]
+        extra.append(base[c] + add)
+    allc = extra[:60] + base + extra[60:] + base[:10]
+    off2 = np.cumsum([0] + [len(c) for c in allc]).astype(np.uint32)
+    lits2 = np.array([l for c in allc for l in c], np.uint32)
+    ioff, coff, li = batch_of([(off2, lits2)])
+    e.upload(ioff, coff, li)
+    r = e.subsume_instance(0, len(allc), len(lits2))
+    assert (r["removed"] == _subsumption_oracle(off2, lits2)).all()
+    assert r["removed_count"] >= 130
+    res_a, _ = e.solve_batch(ioff, coff, li, kind=pkg.CORE, model_stride=50)
+    ioff_r, coff_r, li_r = batch_of([(r["clause_off"].astype(np.uint32), r["lits"])])
+    res_b, models_b = e.solve_batch(ioff_r, coff_r, li_r, kind=pkg.CORE, model_stride=50)
+    assert res_a[0]["verdict"] == res_b[0]["verdict"] == 1
+    assert check_models(ioff, coff, li, res_b["verdict"], models_b) == 0      # a model of the reduced CNF satisfies the original
+    e.close()
+
+
+def test_k4_subsumption_on_structured_instance(pkg):
+    """grieu-vmpc-s05-24s (67,872 clauses): every removed clause has a surviving subset clause; counts are reported
+    beside the oracle's full preprocessing (which also strengthens): 49,478 clauses left there."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "corpus_hard.npz"))
+    i = list(g["names"]).index("grieu-vmpc-s05-24s.cnf.gz")
+    cb, ce = int(g["inst_clause_off"][i]), int(g["inst_clause_off"][i + 1])
+    off = g["clause_off"][cb:ce + 1].astype(np.int64)
+    lits = g["lits"][off[0]:off[-1]]
+    off = (off - off[0]).astype(np.uint32)
+    ioff, coff, li = batch_of([(off, lits)])
+    e = pkg.Engine(0)
+    e.upload(ioff, coff, li)
+    r = e.subsume_instance(0, len(off) - 1, len(lits))
+    assert r["kept"] + r["removed_count"] == len(off) - 1 and r["removed_count"] > 0
+    assert r["kept"] >= int(g["rows"][i][2])            # pure subsumption removes no more than subsumption + strengthening
+    cls = [frozenset(int(x) for x in lits[off[c]:off[c + 1]]) for c in range(len(off) - 1)]
+    kept_by_lit = {}
+    for c, s in enumerate(cls):
+        if not r["removed"][c]:
+            for l in s:
+                kept_by_lit.setdefault(l, []).append(c)
+    rem = np.nonzero(r["removed"])[0]
+    for d in rem[:: max(1, len(rem) // 400)]:
+        sd = cls[d]
+        assert any(cls[c] <= sd for l in sd for c in kept_by_lit.get(l, ())), int(d)
+    e.close()
