@@ -196,6 +196,13 @@ int b200sat_engine_verify_models(b200sat_engine *e, uint8_t *verified, uint32_t 
  * full subset tests, removed clauses}. */
 int b200sat_engine_subsume_instance(b200sat_engine *e, uint32_t inst, uint8_t *removed, uint32_t *out_clause_off,
                                     uint32_t *out_lits, uint32_t counts[4], float *kernel_ms, void *stream);
+/* Same kernel set plus self-subsuming strengthening, iterated to a fixpoint (strengthen != 0): clause D loses the
+ * literal !l when some clause C with l in C has (C minus l) inside (D minus !l) (simplify.rs:276-301 semantics, not its
+ * job order).  counts = {kept clauses, kept literals, rounds, strengthened literals, empty clause derived (UNSAT),
+ * removed clauses}. */
+int b200sat_engine_simplify_instance(b200sat_engine *e, uint32_t inst, int strengthen, uint8_t *removed,
+                                     uint32_t *out_clause_off, uint32_t *out_lits, uint32_t counts[6],
+                                     float *kernel_ms, void *stream);
 /* Copy the resident CSR back to the host (sizes via b200sat_engine_batch_dims). */
 int b200sat_engine_batch_dims(b200sat_engine *e, uint32_t *n_inst, uint64_t *n_clauses, uint64_t *n_lits);
 int b200sat_engine_download_batch(b200sat_engine *e, uint32_t *inst_clause_off, uint32_t *clause_off,

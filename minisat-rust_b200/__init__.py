@@ -112,7 +112,7 @@ ABI_SYMBOLS = (
     "b200sat_engine_solve_async", "b200sat_engine_finish", "b200sat_solve_batch_async", "b200sat_solve_batch_finish",
     "b200sat_diversify", "b200sat_engine_ring_create", "b200sat_engine_ring_reset", "b200sat_engine_ring_ipc_handle",
     "b200sat_engine_ring_open_peer", "b200sat_portfolio_solve", "b200sat_engine_download_replicas",
-    "b200sat_engine_verify_models", "b200sat_engine_subsume_instance", "b200sat_read_dimacs", "b200sat_free_buffer", "b200sat_write_result",
+    "b200sat_engine_verify_models", "b200sat_engine_subsume_instance", "b200sat_engine_simplify_instance", "b200sat_read_dimacs", "b200sat_free_buffer", "b200sat_write_result",
 )
 PF_SHARE, PF_IGNORE_DONE, PF_SHARE_LBD2 = 1, 2, 4
 
@@ -176,6 +176,7 @@ def lib():
     L.b200sat_engine_download_replicas.argtypes = [vp, vp, u8p, C.c_uint32, vp]
     L.b200sat_engine_verify_models.argtypes = [vp, u8p, u32p, vp]
     L.b200sat_engine_subsume_instance.argtypes = [vp, C.c_uint32, u8p, u32p, u32p, u32p, C.POINTER(C.c_float), vp]
+    L.b200sat_engine_simplify_instance.argtypes = [vp, C.c_uint32, C.c_int, u8p, u32p, u32p, u32p, C.POINTER(C.c_float), vp]
     L.b200sat_read_dimacs.argtypes = [C.c_char_p, C.c_int, C.POINTER(u32p), C.POINTER(u32p), u32p, u32p, u32p,
                                       C.c_char_p, C.c_size_t]
     L.b200sat_free_buffer.argtypes = [vp]
@@ -432,6 +433,22 @@ class Engine:
         kept, kept_lits = counts[0], counts[1]
         return {"removed": removed[:n_clauses], "clause_off": ooff[:kept + 1], "lits": olits[:kept_lits], "kept": kept,
                 "kept_lits": kept_lits, "tests": counts[2], "removed_count": counts[3], "kernel_ms": ms.value}
+
+    def simplify_instance(self, inst, n_clauses, n_lits, strengthen=True, stream=None):
+        """K4 subsumption (+ self-subsuming strengthening to fixpoint) of instance `inst` -> dict like subsume_instance
+        plus rounds / strengthened / unsat."""
+        u32p = C.POINTER(C.c_uint32)
+        removed = np.zeros(max(n_clauses, 1), np.uint8)
+        ooff = np.zeros(n_clauses + 2, np.uint32)
+        olits = np.zeros(max(n_lits, 1), np.uint32)
+        counts = (C.c_uint32 * 6)()
+        ms = C.c_float()
+        _check(lib().b200sat_engine_simplify_instance(self._e, inst, int(strengthen), removed.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                      ooff.ctypes.data_as(u32p), olits.ctypes.data_as(u32p), counts, C.byref(ms), stream))
+        kept, kept_lits = counts[0], counts[1]
+        return {"removed": removed[:n_clauses], "clause_off": ooff[:kept + 1], "lits": olits[:kept_lits], "kept": kept,
+                "kept_lits": kept_lits, "rounds": counts[2], "strengthened": counts[3], "unsat": bool(counts[4]),
+                "removed_count": counts[5], "kernel_ms": ms.value}
 
     def download_batch(self):
         n, nc, nl = self.dims()

@@ -564,6 +564,60 @@ extern "C" int b200sat_pp_subsume_launch(const u32 *d_coff, const u32 *d_lits, u
                                          u8 *d_removed, u32 *d_out_coff, u32 *d_out_lits, u32 *d_counts, cudaStream_t stream);
 
 extern "C" int b200sat_engine_subsume_instance(b200sat_engine *e, uint32_t inst, uint8_t *removed, uint32_t *out_clause_off,
+                                               uint32_t *out_lits, uint32_t counts[4], float *kernel_ms, void *stream_);
+extern "C" int b200sat_pp_simplify_launch(const u32 *d_coff, const u32 *d_lits, u32 cb, u32 nc, u32 nvars, u32 nlits, u32 lit_base,
+                                          u32 *scratch, u32 *d_work, u8 *d_removed, u32 *d_out_coff, u32 *d_out_lits, u32 *d_counts,
+                                          u32 *h_flag, u32 max_rounds, cudaStream_t stream);
+
+/* K4: subsumption + self-subsuming strengthening to fixpoint (mode 1) or subsumption only (mode 0) */
+extern "C" int b200sat_engine_simplify_instance(b200sat_engine *e, uint32_t inst, int strengthen, uint8_t *removed, uint32_t *out_clause_off,
+                                                uint32_t *out_lits, uint32_t counts[6], float *kernel_ms, void *stream_) {
+    if (!strengthen) {
+        uint32_t c4[4] = {0, 0, 0, 0};
+        int rc0 = b200sat_engine_subsume_instance(e, inst, removed, out_clause_off, out_lits, c4, kernel_ms, stream_);
+        if (counts) { counts[0] = c4[0]; counts[1] = c4[1]; counts[2] = 1; counts[3] = 0; counts[4] = 0; counts[5] = c4[3]; }
+        return rc0;
+    }
+    if (!e || inst >= e->n_inst) return set_err(B200SAT_E_ARG, "bad instance index");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(cudaSetDevice(e->device));
+    u32 io[2], lo[2];
+    CK(cudaMemcpy(io, e->d_ioff + inst, 8, cudaMemcpyDeviceToHost));
+    const u32 cb = io[0], nc = io[1] - io[0];
+    if (nc == 0) { if (counts) for (int i = 0; i < 6; i++) counts[i] = 0; return 0; }
+    CK(cudaMemcpy(&lo[0], e->d_coff + cb, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&lo[1], e->d_coff + cb + nc, 4, cudaMemcpyDeviceToHost));
+    const u32 nlits = lo[1] - lo[0], nvars = e->shape.max_vars;
+    int rc;
+    const size_t sw = b200sat_pp_scratch_words(nc, nvars, nlits);
+    size_t words = sw + ((size_t)nc + 2 + nlits + 8) + ((size_t)2 * nc + nlits + 16);
+    if ((rc = ensure(e->d_pp, e->cap_pp, words))) return rc;
+    if ((rc = ensure(e->d_verified, e->cap_verified, (size_t)nc))) return rc;
+    u32 *scratch = e->d_pp;
+    u32 *d_out_coff = scratch + sw;
+    u32 *d_out_lits = d_out_coff + nc + 2;
+    u32 *d_work = d_out_lits + nlits + 6;
+    u32 *d_counts = e->d_queue + 16;
+    CK(cudaEventRecord(e->ev0, stream));
+    if (b200sat_pp_simplify_launch(e->d_coff, e->d_lits, cb, nc, nvars, nlits, lo[0], scratch, d_work, e->d_verified, d_out_coff, d_out_lits,
+                                   d_counts, e->h_pinned + 24, 64, stream))
+        return set_err(B200SAT_E_CUDA, "preprocess kernel launch failed");
+    CK(cudaEventRecord(e->ev1, stream));
+    CK(cudaMemcpyAsync(e->h_pinned + 16, d_counts, 24, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const u32 kept = e->h_pinned[16], kept_lits = e->h_pinned[17];
+    if (counts) { for (int i = 0; i < 5; i++) counts[i] = e->h_pinned[16 + i]; counts[5] = nc - kept; }
+    if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, e->ev0, e->ev1));
+    if (removed) CK(cudaMemcpy(removed, e->d_verified, nc, cudaMemcpyDeviceToHost));
+    if (out_clause_off) {
+        CK(cudaMemcpy(out_clause_off, d_out_coff, (size_t)kept * 4, cudaMemcpyDeviceToHost));
+        out_clause_off[kept] = kept_lits;
+    }
+    if (out_lits && kept_lits) CK(cudaMemcpy(out_lits, d_out_lits, (size_t)kept_lits * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int b200sat_engine_subsume_instance(b200sat_engine *e, uint32_t inst, uint8_t *removed, uint32_t *out_clause_off,
                                                uint32_t *out_lits, uint32_t counts[4], float *kernel_ms, void *stream_) {
     if (!e || inst >= e->n_inst) return set_err(B200SAT_E_ARG, "bad instance index");
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -169,3 +169,126 @@ extern "C" int b200sat_pp_subsume_launch(const u32 *d_coff, const u32 *d_lits, u
     (void)nlits;
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
+
+
+/* ------------------------------------------------------------------ subsumption + self-subsuming strengthening to fixpoint
+ * (simplify.rs:423-523 semantics, NOT its job order).  Works on a private copy of the instance's literals:
+ * clause c = wl[wo[c] .. wo[c] + len[c]).  One round = pp2_scan_pairs (warp per clause C: for every candidate D of
+ * C's least-occurring variable classify subsumes(C, D): Exact -> removed[D], LitSign(l) -> D should lose !l,
+ * one literal per clause and round through atomicCAS) + pp2_apply (drop the literal, refresh signature/length).
+ * Every step is implied by the clause set it was computed on, so the result is equivalent to the input.
+ * Occurrence lists are not rebuilt: stale entries only cost a failed subset test. */
+__global__ void pp2_copy(const u32 *coff, const u32 *lits, u32 cb, u32 nc, u32 base, u32 *wo, u32 *wl) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    u32 b = coff[cb + c], e = coff[cb + c + 1];
+    wo[c] = b - base;
+    for (u32 k = b; k < e; k++) wl[k - base] = lits[k];
+}
+
+__device__ __forceinline__ u32 pp2_classify(const u32 *wl, u32 cb_, u32 cn, u32 db, u32 dn, u32 &flip) {
+    u32 ret = 1; /* 1 exact, 2 litsign, 0 different (subsumes.rs:27-49) */
+    for (u32 i = 0; i < cn; i++) {
+        const u32 l = wl[cb_ + i];
+        bool found = false;
+        for (u32 j = 0; j < dn; j++) {
+            const u32 d = wl[db + j];
+            if (d == l) { found = true; break; }
+            if (d == (l ^ 1)) {
+                if (ret == 1) { ret = 2; flip = d; found = true; break; }
+                return 0;
+            }
+        }
+        if (!found) return 0;
+    }
+    return ret;
+}
+
+__global__ void pp2_scan_pairs(const u32 *wo, const u32 *wl, u32 nc, const u32 *sig, const u32 *len, const u32 *occ_off, const u32 *occ,
+                               u8 *removed, u32 *drop_lit, u32 *changed) {
+    const u32 c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= nc || removed[c]) return;
+    const u32 b = wo[c], lc = len[c];
+    if (lc == 0) return;
+    u32 best = wl[b] >> 1, bestn = occ_off[best + 1] - occ_off[best];
+    for (u32 k = 1; k < lc; k++) {
+        u32 v = wl[b + k] >> 1, n = occ_off[v + 1] - occ_off[v];
+        if (n < bestn) { best = v; bestn = n; }
+    }
+    const u32 sc = sig[c];
+    for (u32 i = lane; i < bestn; i += 32) {
+        const u32 d = occ[occ_off[best] + i];
+        if (d == c || removed[d] || len[d] < lc || (sc & ~sig[d]) != 0) continue;
+        u32 flip = 0;
+        const u32 r = pp2_classify(wl, b, lc, wo[d], len[d], flip);
+        if (r == 1) { if (lc < len[d] || c < d) { removed[d] = 1; *changed = 1; } }
+        else if (r == 2) { if (atomicCAS(&drop_lit[d], 0xFFFFFFFFu, flip) == 0xFFFFFFFFu) *changed = 1; }
+    }
+}
+
+__global__ void pp2_apply(const u32 *wo, u32 *wl, u32 nc, u32 *sig, u32 *len, const u8 *removed, u32 *drop_lit, u32 *n_strengthened,
+                          u32 *empty_clause) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    const u32 dl = drop_lit[c];
+    if (dl == 0xFFFFFFFFu) return;
+    drop_lit[c] = 0xFFFFFFFFu;
+    if (removed[c]) return;
+    const u32 b = wo[c];
+    u32 n = len[c], j = 0, s = 0;
+    for (u32 k = 0; k < n; k++) {
+        const u32 l = wl[b + k];
+        if (l == dl) continue;
+        wl[b + j++] = l; /* order kept, like strengthen (simplify.rs:567-591) */
+        s |= 1u << ((l >> 1) & 31);
+    }
+    if (j != n) { len[c] = j; sig[c] = s; atomicAdd(n_strengthened, 1u); if (j == 0) *empty_clause = 1; }
+}
+
+__global__ void pp2_compact(const u32 *wo, const u32 *wl, u32 nc, const u32 *len, const u8 *removed, const u32 *new_idx, const u32 *new_off,
+                            u32 *out_coff, u32 *out_lits) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc || removed[c]) return;
+    const u32 o = new_off[c];
+    out_coff[new_idx[c]] = o;
+    for (u32 k = 0; k < len[c]; k++) out_lits[o + k] = wl[wo[c] + k];
+}
+
+/* d_counts: [0] kept clauses, [1] kept literals, [2] rounds, [3] strengthened literals, [4] empty clause derived */
+extern "C" int b200sat_pp_simplify_launch(const u32 *d_coff, const u32 *d_lits, u32 cb, u32 nc, u32 nvars, u32 nlits, u32 lit_base,
+                                          u32 *scratch, u32 *d_work /* nc + nlits + nc + 8 words */, u8 *d_removed, u32 *d_out_coff,
+                                          u32 *d_out_lits, u32 *d_counts, u32 *h_flag /* pinned */, u32 max_rounds, cudaStream_t stream) {
+    u32 *sig = scratch, *len = sig + nc + 2, *kept_len = len + nc + 2, *kept_flag = kept_len + nc + 2, *new_off = kept_flag + nc + 2,
+        *new_idx = new_off + nc + 2, *occ_cnt = new_idx + nc + 2, *occ_off = occ_cnt + nvars + 2, *cursor = occ_off + nvars + 2,
+        *occ = cursor + nvars + 2;
+    u32 *wo = d_work, *wl = wo + nc + 2, *drop = wl + nlits + 2;
+    const u32 T = 256, gc = (nc + T - 1) / T;
+    cudaMemsetAsync(occ_cnt, 0, (size_t)(nvars + 2) * 4, stream);
+    cudaMemsetAsync(cursor, 0, (size_t)(nvars + 2) * 4, stream);
+    cudaMemsetAsync(d_counts, 0, 32, stream);
+    cudaMemsetAsync(drop, 0xFF, (size_t)(nc + 2) * 4, stream);
+    pp_sig_len<<<gc, T, 0, stream>>>(d_coff, d_lits, cb, nc, sig, len, d_removed);
+    pp_occ_count<<<gc, T, 0, stream>>>(d_coff, d_lits, cb, nc, occ_cnt);
+    pp_scan<<<1, 1024, 0, stream>>>(occ_cnt, occ_off, nvars);
+    pp_occ_fill<<<gc, T, 0, stream>>>(d_coff, d_lits, cb, nc, occ_off, cursor, occ);
+    pp_occ_sort<<<(nvars * 32 + T - 1) / T, T, 0, stream>>>(occ_off, occ, nvars);
+    pp2_copy<<<gc, T, 0, stream>>>(d_coff, d_lits, cb, nc, lit_base, wo, wl);
+    u32 rounds = 0;
+    for (; rounds < max_rounds; rounds++) {
+        cudaMemsetAsync(d_counts + 5, 0, 4, stream);
+        pp2_scan_pairs<<<(u32)(((u64)nc * 32 + T - 1) / T), T, 0, stream>>>(wo, wl, nc, sig, len, occ_off, occ, d_removed, drop, d_counts + 5);
+        pp2_apply<<<gc, T, 0, stream>>>(wo, wl, nc, sig, len, d_removed, drop, d_counts + 3, d_counts + 4);
+        cudaMemcpyAsync(h_flag, d_counts + 5, 4, cudaMemcpyDeviceToHost, stream);
+        if (cudaStreamSynchronize(stream) != cudaSuccess) return -2;
+        if (!*h_flag) { rounds++; break; }
+    }
+    pp_kept_len<<<gc, T, 0, stream>>>(len, d_removed, nc, kept_len, kept_flag);
+    pp_scan<<<1, 1024, 0, stream>>>(kept_len, new_off, nc);
+    pp_scan<<<1, 1024, 0, stream>>>(kept_flag, new_idx, nc);
+    pp2_compact<<<gc, T, 0, stream>>>(wo, wl, nc, len, d_removed, new_idx, new_off, d_out_coff, d_out_lits);
+    cudaMemcpyAsync(d_counts + 0, new_idx + nc, 4, cudaMemcpyDeviceToDevice, stream);
+    cudaMemcpyAsync(d_counts + 1, new_off + nc, 4, cudaMemcpyDeviceToDevice, stream);
+    cudaMemcpyAsync(d_counts + 2, &rounds, 4, cudaMemcpyHostToDevice, stream);
+    cudaStreamSynchronize(stream);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}

@@ -393,3 +393,42 @@ def test_k4_subsumption_on_structured_instance(pkg):
         sd = cls[d]
         assert any(cls[c] <= sd for l in sd for c in kept_by_lit.get(l, ())), int(d)
     e.close()
+
+
+def test_k4_strengthening_fixpoint(pkg, po):
+    """K4 with self-subsuming strengthening iterated to a fixpoint: hand-made cases, then equivalence on bundled
+    instances (same verdict for the original and the simplified CNF; models of the simplified CNF satisfy the original)."""
+    e = pkg.Engine(0)
+    cl = [[1, 2], [-1, 2], [3, 4, 5], [-3, 4], [6, 7], [-6, 7, 8], [9, 10, 11]]
+    off, lits = csr_of(cl)
+    ioff, coff, li = batch_of([(off, lits)])
+    e.upload(ioff, coff, li)
+    r = e.simplify_instance(0, len(cl), len(lits))
+    got = sorted(sorted((int(l >> 1) + 1) * (-1 if l & 1 else 1) for l in r["lits"][r["clause_off"][k]:r["clause_off"][k + 1]])
+                 for k in range(r["kept"]))
+    # (1 2),(-1 2) -> (2) twice -> one copy; (3 4 5) loses 3 via (-3 4); (-6 7 8) loses -6 via (6 7) and is then subsumed by... (7 8) stays
+    assert got == sorted([[2], [4, 5], [-3, 4], [6, 7], [7, 8], [9, 10, 11]]), got
+    assert not r["unsat"] and r["strengthened"] >= 4
+    cl = [[1], [-1, 2], [-2]]                      # strengthening with units = unit propagation -> empty clause
+    off, lits = csr_of(cl)
+    ioff, coff, li = batch_of([(off, lits)])
+    e.upload(ioff, coff, li)
+    assert e.simplify_instance(0, len(cl), len(lits))["unsat"]
+    g = load_golden()
+    for name in ("uf50-01.cnf.gz", "uf50-06.cnf.gz", "uuf50-02.cnf.gz", "2bitcomp_5.cnf.gz", "2bitadd_11.cnf.gz", "3blocks.cnf.gz"):
+        i = list(g["names"]).index(name)
+        off, lits = golden_instance(g, i)
+        nv = int(g["n_vars"][i])
+        ioff, coff, li = batch_of([(off, lits)])
+        e.upload(ioff, coff, li)
+        r = e.simplify_instance(0, len(off) - 1, len(lits))
+        want = int(g["core_verdict"][i])
+        if r["unsat"]:
+            assert want == 0, name
+            continue
+        ioff_r, coff_r, li_r = batch_of([(r["clause_off"].astype(np.uint32), r["lits"])])
+        res, models = e.solve_batch(ioff_r, coff_r, li_r, kind=pkg.CORE, model_stride=nv)
+        assert res[0]["verdict"] == want, name
+        if want == 1:
+            assert check_models(ioff, coff, li, res["verdict"], models) == 0, name
+    e.close()

@@ -19,7 +19,8 @@ for i, name in enumerate(g["names"]):
     for it in range(3):
         r = eng.subsume_instance(0, len(off) - 1, len(lits))
         best = r["kernel_ms"] if best is None else min(best, r["kernel_ms"])
-    print(json.dumps({"instance": str(name), "clauses": len(off) - 1, "literals": int(len(lits)), "k4_removed": int(r["removed_count"]),
+    r2 = eng.simplify_instance(0, len(off) - 1, len(lits))
+    print(json.dumps({"instance": str(name), "k4_strengthen": {k: (int(v) if not isinstance(v, (bool, float)) else v) for k, v in r2.items() if k in ("kept", "kept_lits", "rounds", "strengthened", "unsat", "removed_count", "kernel_ms")}, "clauses": len(off) - 1, "literals": int(len(lits)), "k4_removed": int(r["removed_count"]),
                       "k4_kept": int(r["kept"]), "subset_tests": int(r["tests"]), "k4_kernels_ms": round(best, 3),
                       "oracle_full_preprocess_clauses_left": int(g["rows"][i][2]), "oracle_eliminated_vars": int(g["rows"][i][3])}), flush=True)
 eng.close()
