@@ -203,6 +203,14 @@ int b200sat_engine_subsume_instance(b200sat_engine *e, uint32_t inst, uint8_t *r
 int b200sat_engine_simplify_instance(b200sat_engine *e, uint32_t inst, int strengthen, uint8_t *removed,
                                      uint32_t *out_clause_off, uint32_t *out_lits, uint32_t counts[6],
                                      float *kernel_ms, void *stream);
+/* K4 bounded variable elimination (simplify.rs:338-420 semantics, not its order): rounds of independent-set
+ * selection + warp-per-variable elimination.  Buffers: out_clause_off 2*nc+1026, out_lits / out_estack 3*nlits+4096
+ * words.  out_estack holds records [var, default unit lit, round, k, (len, lits...)*k] (the variable's literal first)
+ * for model extension (elim_clauses.rs:43-63): walk the rounds backwards.  counts = {kept clauses, kept literals,
+ * eliminated vars, rounds, estack words, overflow}. */
+int b200sat_engine_bve_instance(b200sat_engine *e, uint32_t inst, uint32_t grow, int cl_lim, uint32_t max_rounds,
+                                uint32_t *out_clause_off, uint32_t *out_lits, uint32_t *out_estack,
+                                uint32_t counts[6], float *kernel_ms, void *stream);
 /* Copy the resident CSR back to the host (sizes via b200sat_engine_batch_dims). */
 int b200sat_engine_batch_dims(b200sat_engine *e, uint32_t *n_inst, uint64_t *n_clauses, uint64_t *n_lits);
 int b200sat_engine_download_batch(b200sat_engine *e, uint32_t *inst_clause_off, uint32_t *clause_off,

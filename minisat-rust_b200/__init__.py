@@ -112,7 +112,7 @@ ABI_SYMBOLS = (
     "b200sat_engine_solve_async", "b200sat_engine_finish", "b200sat_solve_batch_async", "b200sat_solve_batch_finish",
     "b200sat_diversify", "b200sat_engine_ring_create", "b200sat_engine_ring_reset", "b200sat_engine_ring_ipc_handle",
     "b200sat_engine_ring_open_peer", "b200sat_portfolio_solve", "b200sat_engine_download_replicas",
-    "b200sat_engine_verify_models", "b200sat_engine_subsume_instance", "b200sat_engine_simplify_instance", "b200sat_read_dimacs", "b200sat_free_buffer", "b200sat_write_result",
+    "b200sat_engine_verify_models", "b200sat_engine_subsume_instance", "b200sat_engine_simplify_instance", "b200sat_engine_bve_instance", "b200sat_read_dimacs", "b200sat_free_buffer", "b200sat_write_result",
 )
 PF_SHARE, PF_IGNORE_DONE, PF_SHARE_LBD2 = 1, 2, 4
 
@@ -176,6 +176,8 @@ def lib():
     L.b200sat_engine_download_replicas.argtypes = [vp, vp, u8p, C.c_uint32, vp]
     L.b200sat_engine_verify_models.argtypes = [vp, u8p, u32p, vp]
     L.b200sat_engine_subsume_instance.argtypes = [vp, C.c_uint32, u8p, u32p, u32p, u32p, C.POINTER(C.c_float), vp]
+    L.b200sat_engine_bve_instance.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, u32p, u32p, u32p, u32p,
+                                              C.POINTER(C.c_float), vp]
     L.b200sat_engine_simplify_instance.argtypes = [vp, C.c_uint32, C.c_int, u8p, u32p, u32p, u32p, C.POINTER(C.c_float), vp]
     L.b200sat_read_dimacs.argtypes = [C.c_char_p, C.c_int, C.POINTER(u32p), C.POINTER(u32p), u32p, u32p, u32p,
                                       C.c_char_p, C.c_size_t]
@@ -450,6 +452,28 @@ class Engine:
                 "kept_lits": kept_lits, "rounds": counts[2], "strengthened": counts[3], "unsat": bool(counts[4]),
                 "removed_count": counts[5], "kernel_ms": ms.value}
 
+    def bve_instance(self, inst, n_clauses, n_lits, grow=0, cl_lim=20, max_rounds=64, stream=None):
+        """K4 multi-CTA bounded variable elimination of instance `inst` -> dict(clause_off, lits, estack records, counts)."""
+        u32p = C.POINTER(C.c_uint32)
+        ooff = np.zeros(2 * n_clauses + 1030, np.uint32)
+        olits = np.zeros(3 * n_lits + 4100, np.uint32)
+        est = np.zeros(3 * n_lits + 4100, np.uint32)
+        counts = (C.c_uint32 * 6)()
+        ms = C.c_float()
+        _check(lib().b200sat_engine_bve_instance(self._e, inst, grow, cl_lim, max_rounds, ooff.ctypes.data_as(u32p),
+                                                 olits.ctypes.data_as(u32p), est.ctypes.data_as(u32p), counts, C.byref(ms), stream))
+        kept, kept_lits, ew = counts[0], counts[1], counts[4]
+        recs, w = [], 0
+        while w < ew:                      # [var, unit lit, round, k, (len, lits...)*k]
+            var, unit, rnd, k = (int(x) for x in est[w:w + 4])
+            w += 4
+            cls = []
+            for _ in range(k):
+                n = int(est[w]); cls.append([int(x) for x in est[w + 1:w + 1 + n]]); w += 1 + n
+            recs.append((rnd, var, unit, cls))
+        return {"clause_off": ooff[:kept + 1], "lits": olits[:kept_lits], "kept": kept, "kept_lits": kept_lits,
+                "eliminated": counts[2], "rounds": counts[3], "records": recs, "kernel_ms": ms.value}
+
     def download_batch(self):
         n, nc, nl = self.dims()
         ioff = np.zeros(n + 1, np.uint32)
@@ -480,6 +504,23 @@ class Engine:
         _check(lib().b200sat_solve_batch(self._e, C.byref(b), C.byref(s), kind, flags, res.ctypes.data, mp,
                                          model_stride), allow=(E_MEM,))
         return res, models
+
+
+def extend_model_k4(model, records):
+    """Model extension over the K4 eliminated-clause records (elim_clauses.rs:43-63): later rounds first; per record the
+    default unit, then every saved clause that is not satisfied flips the variable to its own literal."""
+    def is_true(l):
+        m = model[l >> 1]
+        return m != 2 and (m == 1) == ((l & 1) == 0)
+    for rnd, var, unit, cls in sorted(records, key=lambda r: -r[0]):
+        model[var] = 0 if (unit & 1) else 1
+        for c in cls:
+            if not any(is_true(l) for l in c):
+                model[c[0] >> 1] = 0 if (c[0] & 1) else 1
+    for v in range(len(model)):
+        if model[v] == 2:
+            model[v] = 0
+    return model
 
 
 def diversify(base, replica):

@@ -563,6 +563,54 @@ extern "C" size_t b200sat_pp_scratch_words(size_t nc, size_t nvars, size_t nlits
 extern "C" int b200sat_pp_subsume_launch(const u32 *d_coff, const u32 *d_lits, u32 cb, u32 nc, u32 nvars, u32 nlits, u32 *scratch,
                                          u8 *d_removed, u32 *d_out_coff, u32 *d_out_lits, u32 *d_counts, cudaStream_t stream);
 
+extern "C" size_t b200sat_bve_words(size_t nc, size_t nvars, size_t nlits);
+extern "C" int b200sat_pp_bve_launch(const u32 *d_coff, const u32 *d_lits, u32 cb, u32 nc, u32 nvars, u32 nlits, u32 lit_base, u32 *mem,
+                                     u32 grow, int cl_lim, u32 max_rounds, u32 *d_out_coff, u32 *d_out_lits, u32 **d_estack_out,
+                                     u32 *d_counts, u32 *h_pin, cudaStream_t stream);
+
+/* K4: multi-CTA bounded variable elimination of one large instance */
+extern "C" int b200sat_engine_bve_instance(b200sat_engine *e, uint32_t inst, uint32_t grow, int cl_lim, uint32_t max_rounds,
+                                           uint32_t *out_clause_off, uint32_t *out_lits, uint32_t *out_estack, uint32_t counts[6],
+                                           float *kernel_ms, void *stream_) {
+    if (!e || inst >= e->n_inst) return set_err(B200SAT_E_ARG, "bad instance index");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(cudaSetDevice(e->device));
+    u32 io[2], lo[2];
+    CK(cudaMemcpy(io, e->d_ioff + inst, 8, cudaMemcpyDeviceToHost));
+    const u32 cb = io[0], nc = io[1] - io[0];
+    if (nc == 0) { if (counts) for (int i = 0; i < 6; i++) counts[i] = 0; return 0; }
+    CK(cudaMemcpy(&lo[0], e->d_coff + cb, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&lo[1], e->d_coff + cb + nc, 4, cudaMemcpyDeviceToHost));
+    const u32 nlits = lo[1] - lo[0], nvars = e->shape.max_vars;
+    const size_t NC = 2 * (size_t)nc + 1024, NL = 3 * (size_t)nlits + 4096;
+    int rc;
+    const size_t bw = b200sat_bve_words(nc, nvars, nlits);
+    if ((rc = ensure(e->d_pp, e->cap_pp, bw + NC + 2 + NL + 64))) return rc;
+    u32 *mem = e->d_pp;
+    u32 *d_out_coff = mem + bw;
+    u32 *d_out_lits = d_out_coff + NC + 2;
+    u32 *d_counts = e->d_queue + 16;
+    u32 *d_estack = nullptr;
+    CK(cudaEventRecord(e->ev0, stream));
+    if (b200sat_pp_bve_launch(e->d_coff, e->d_lits, cb, nc, nvars, nlits, lo[0], mem, grow, cl_lim, max_rounds, d_out_coff, d_out_lits,
+                              &d_estack, d_counts, e->h_pinned + 24, stream))
+        return set_err(B200SAT_E_CUDA, "bve kernel launch failed");
+    CK(cudaEventRecord(e->ev1, stream));
+    CK(cudaMemcpyAsync(e->h_pinned + 16, d_counts, 24, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const u32 kept = e->h_pinned[16], kept_lits = e->h_pinned[17], ewords = e->h_pinned[20];
+    if (counts) for (int i = 0; i < 6; i++) counts[i] = e->h_pinned[16 + i];
+    if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, e->ev0, e->ev1));
+    if (e->h_pinned[21]) return set_err(B200SAT_E_MEM, "bve: clause store overflow");
+    if (out_clause_off) {
+        CK(cudaMemcpy(out_clause_off, d_out_coff, (size_t)kept * 4, cudaMemcpyDeviceToHost));
+        out_clause_off[kept] = kept_lits;
+    }
+    if (out_lits && kept_lits) CK(cudaMemcpy(out_lits, d_out_lits, (size_t)kept_lits * 4, cudaMemcpyDeviceToHost));
+    if (out_estack && ewords) CK(cudaMemcpy(out_estack, d_estack, (size_t)ewords * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" int b200sat_engine_subsume_instance(b200sat_engine *e, uint32_t inst, uint8_t *removed, uint32_t *out_clause_off,
                                                uint32_t *out_lits, uint32_t counts[4], float *kernel_ms, void *stream_);
 extern "C" int b200sat_pp_simplify_launch(const u32 *d_coff, const u32 *d_lits, u32 cb, u32 nc, u32 nvars, u32 nlits, u32 lit_base,

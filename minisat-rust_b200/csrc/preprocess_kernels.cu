@@ -292,3 +292,240 @@ extern "C" int b200sat_pp_simplify_launch(const u32 *d_coff, const u32 *d_lits, 
     cudaStreamSynchronize(stream);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
+
+
+/* ------------------------------------------------------------------ bounded variable elimination, multi-CTA (simplify.rs:338-420
+ * semantics, NOT its order).  Rounds of: rebuild per-variable occurrence lists over the live clauses ->
+ * bve_select (a candidate variable is selected iff it has the smallest (cost = n_occ+ * n_occ-, id) among the
+ * candidates it shares a clause with, so selected variables share no clause) -> bve_eliminate (warp per selected
+ * variable: all pos x neg resolvents by formula/util.rs:45-77 `merge`, one pair per lane; eliminated iff the number
+ * of non-tautological resolvents <= n_occ + grow and none is longer than cl_lim; resolvents appended at
+ * prefix-sum offsets, originals marked removed, the smaller side saved on the eliminated-clause stack with the
+ * variable's literal first, then the default unit -- elim_clauses.rs:20-41).  Model extension walks that stack
+ * backwards (elim_clauses.rs:43-63). */
+struct BveState {
+    u32 *wo, *len, *sig, *wl;           /* clause store: slot c = wl[wo[c] .. wo[c]+len[c]) */
+    u8 *removed;
+    u32 *n_clauses, *n_lits;            /* cursors (device) */
+    u32 clause_cap, lit_cap;
+    u32 *npos, *nneg, *occ_cnt, *occ_off, *cursor, *occ;
+    u8 *eliminated, *selected;
+    u32 *estack, *estack_n;
+    u32 estack_cap;
+    u32 *n_elim, *overflow;
+    u32 nvars;
+};
+
+__global__ void bve_count(BveState S) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= *S.n_clauses || S.removed[c]) return;
+    for (u32 k = 0; k < S.len[c]; k++) {
+        u32 l = S.wl[S.wo[c] + k];
+        atomicAdd((l & 1) ? &S.nneg[l >> 1] : &S.npos[l >> 1], 1u);
+        atomicAdd(&S.occ_cnt[l >> 1], 1u);
+    }
+}
+__global__ void bve_fill(BveState S) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= *S.n_clauses || S.removed[c]) return;
+    for (u32 k = 0; k < S.len[c]; k++) {
+        u32 v = S.wl[S.wo[c] + k] >> 1;
+        S.occ[S.occ_off[v] + atomicAdd(&S.cursor[v], 1u)] = c;
+    }
+}
+__device__ __forceinline__ bool bve_cand(const BveState &S, u32 v) {
+    const u32 p = S.npos[v], n = S.nneg[v];
+    return !S.eliminated[v] && p + n > 0 && p + n <= 64 && p * n <= 1024;
+}
+__global__ void bve_select(BveState S) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= S.nvars) return;
+    u8 sel = 0;
+    if (bve_cand(S, v)) {
+        sel = 1;
+        const u32 cv = S.npos[v] * S.nneg[v];
+        for (u32 i = S.occ_off[v]; i < S.occ_off[v + 1] && sel; i++) {
+            const u32 c = S.occ[i];
+            for (u32 k = 0; k < S.len[c]; k++) {
+                const u32 u = S.wl[S.wo[c] + k] >> 1;
+                if (u == v || !bve_cand(S, u)) continue;
+                const u32 cu = S.npos[u] * S.nneg[u];
+                if (cu < cv || (cu == cv && u < v)) { sel = 0; break; }
+            }
+        }
+    }
+    S.selected[v] = sel;
+}
+
+/* merge (formula/util.rs:45-77) of clause slots p and q on variable v: returns false for a tautology; out may be NULL */
+__device__ __forceinline__ bool bve_merge(const BveState &S, u32 v, u32 p, u32 q, u32 *out, u32 &n_out) {
+    u32 lp = S.len[p], lq = S.len[q];
+    const u32 *longer = S.wl + S.wo[p], *shorter = S.wl + S.wo[q];
+    u32 nl = lp, ns = lq;
+    if (lp < lq) { longer = S.wl + S.wo[q]; nl = lq; shorter = S.wl + S.wo[p]; ns = lp; }
+    n_out = 0;
+    for (u32 i = 0; i < ns; i++) {
+        const u32 x = shorter[i];
+        if ((x >> 1) == v) continue;
+        bool add = true;
+        for (u32 j = 0; j < nl; j++)
+            if ((longer[j] >> 1) == (x >> 1)) { if (longer[j] == (x ^ 1)) return false; add = false; break; }
+        if (add) { if (out) out[n_out] = x; n_out++; }
+    }
+    for (u32 j = 0; j < nl; j++) if ((longer[j] >> 1) != v) { if (out) out[n_out] = longer[j]; n_out++; }
+    return true;
+}
+
+__global__ void bve_eliminate(BveState S, u32 grow, int cl_lim, u32 round) {
+    const u32 v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (v >= S.nvars || !S.selected[v]) return;
+    __shared__ u32 side[8][64]; /* per warp: pos ids from the front, neg ids from the back */
+    u32 *sd = side[(threadIdx.x >> 5) & 7];
+    const u32 lt = (1u << lane) - 1;
+    const u32 ob = S.occ_off[v], on = S.occ_off[v + 1] - ob;
+    u32 npos = 0, nneg = 0;
+    for (u32 i0 = 0; i0 < on; i0 += 32) {
+        const u32 i = i0 + lane;
+        u32 c = 0, sgn = 2;
+        if (i < on) {
+            c = S.occ[ob + i];
+            for (u32 k = 0; k < S.len[c]; k++) { const u32 l = S.wl[S.wo[c] + k]; if ((l >> 1) == v) { sgn = l & 1; break; } }
+        }
+        const u32 pm = __ballot_sync(0xFFFFFFFFu, sgn == 0), nm = __ballot_sync(0xFFFFFFFFu, sgn == 1);
+        if (sgn == 0) sd[npos + __popc(pm & lt)] = c;
+        if (sgn == 1) sd[63 - (nneg + __popc(nm & lt))] = c;
+        npos += __popc(pm); nneg += __popc(nm);
+    }
+    __syncwarp();
+    const u32 npairs = npos * nneg;
+    u32 cnt = 0, sumlen = 0, maxlen = 0;
+    for (u32 t0 = 0; t0 < npairs; t0 += 32) {
+        const u32 t = t0 + lane;
+        u32 n_out = 0;
+        bool ok = false;
+        if (t < npairs) ok = bve_merge(S, v, sd[t / nneg], sd[63 - (t % nneg)], nullptr, n_out);
+        cnt += __popc(__ballot_sync(0xFFFFFFFFu, ok));
+        u32 l = ok ? n_out : 0;
+        for (int o = 16; o > 0; o >>= 1) { const u32 y = __shfl_xor_sync(0xFFFFFFFFu, l, o); l = l > y ? l : y; }
+        maxlen = maxlen > l ? maxlen : l;
+        u32 s = ok ? n_out : 0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        sumlen += s;
+    }
+    if (cnt > npos + nneg + grow || (cl_lim != -1 && (int)maxlen > cl_lim)) return; /* simplify.rs:368-383 */
+    /* eliminated-clause record: [var, unit lit, round, k, (len, lits...) * k] of the smaller side */
+    const bool save_neg = npos > nneg;
+    const u32 ks = save_neg ? nneg : npos;
+    u32 rec = 4;
+    for (u32 i = 0; i < ks; i++) rec += 1 + S.len[save_neg ? sd[63 - i] : sd[i]];
+    u32 cid0 = 0, l0 = 0, e0 = 0, okres = 1;
+    if (lane == 0) {
+        cid0 = atomicAdd(S.n_clauses, cnt);
+        l0 = atomicAdd(S.n_lits, sumlen);
+        e0 = atomicAdd(S.estack_n, rec);
+        if (cid0 + cnt > S.clause_cap || l0 + sumlen > S.lit_cap || e0 + rec > S.estack_cap) { okres = 0; *S.overflow = 1; }
+    }
+    cid0 = __shfl_sync(0xFFFFFFFFu, cid0, 0); l0 = __shfl_sync(0xFFFFFFFFu, l0, 0);
+    e0 = __shfl_sync(0xFFFFFFFFu, e0, 0); okres = __shfl_sync(0xFFFFFFFFu, okres, 0);
+    if (!okres) return; /* the reserved slots stay marked removed (initialised so by the host) */
+    u32 rr = 0, ro = 0;
+    for (u32 t0 = 0; t0 < npairs; t0 += 32) {
+        const u32 t = t0 + lane;
+        u32 n_out = 0;
+        bool ok = false;
+        if (t < npairs) ok = bve_merge(S, v, sd[t / nneg], sd[63 - (t % nneg)], nullptr, n_out);
+        const u32 okm = __ballot_sync(0xFFFFFFFFu, ok);
+        u32 incl = ok ? n_out : 0;
+        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (u32)o) incl += y; }
+        const u32 tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (ok) {
+            const u32 slot = cid0 + rr + __popc(okm & lt), off = l0 + ro + incl - n_out;
+            u32 m = 0;
+            bve_merge(S, v, sd[t / nneg], sd[63 - (t % nneg)], S.wl + off, m);
+            u32 sg = 0;
+            for (u32 k = 0; k < m; k++) sg |= 1u << ((S.wl[off + k] >> 1) & 31);
+            S.wo[slot] = off; S.len[slot] = m; S.sig[slot] = sg; S.removed[slot] = 0;
+        }
+        rr += __popc(okm); ro += tot;
+    }
+    if (lane == 0) {
+        u32 *e = S.estack + e0;
+        e[0] = v; e[1] = save_neg ? 2 * v : 2 * v + 1; e[2] = round; e[3] = ks;
+        u32 w = 4;
+        for (u32 i = 0; i < ks; i++) {
+            const u32 c = save_neg ? sd[63 - i] : sd[i];
+            const u32 n = S.len[c];
+            e[w++] = n;
+            u32 first = w;
+            for (u32 k = 0; k < n; k++) { e[w] = S.wl[S.wo[c] + k]; if ((e[w] >> 1) == v) { u32 tmp = e[first]; e[first] = e[w]; e[w] = tmp; } w++; }
+        }
+        S.eliminated[v] = 1;
+        atomicAdd(S.n_elim, 1u);
+    }
+    __syncwarp();
+    for (u32 i = lane; i < on; i += 32) S.removed[S.occ[ob + i]] = 1;
+}
+
+extern "C" size_t b200sat_bve_words(size_t nc, size_t nvars, size_t nlits) {
+    const size_t NC = 2 * nc + 1024, NL = 3 * nlits + 4096;
+    return 3 * NC + NL /* wo,len,sig,wl */ + (NC + 3) / 4 /* removed */ + 5 * (nvars + 2) + NL /* occ */ + (nvars + 3) / 2 /* flags */ +
+           NL /* estack */ + 3 * (NC + 2) /* compaction scratch */ + 64;
+}
+
+/* d_counts: [0] kept clauses [1] kept literals [2] eliminated vars [3] rounds [4] estack words [5] overflow */
+extern "C" int b200sat_pp_bve_launch(const u32 *d_coff, const u32 *d_lits, u32 cb, u32 nc, u32 nvars, u32 nlits, u32 lit_base, u32 *mem,
+                                     u32 grow, int cl_lim, u32 max_rounds, u32 *d_out_coff, u32 *d_out_lits, u32 **d_estack_out,
+                                     u32 *d_counts, u32 *h_pin /* 8 pinned words */, cudaStream_t stream) {
+    const u32 NC = 2 * nc + 1024, NL = 3 * nlits + 4096;
+    BveState S;
+    u32 *p = mem;
+    S.wo = p; p += NC; S.len = p; p += NC; S.sig = p; p += NC; S.wl = p; p += NL;
+    S.removed = (u8 *)p; p += (NC + 3) / 4;
+    S.npos = p; p += nvars + 2; S.nneg = p; p += nvars + 2; S.occ_cnt = p; p += nvars + 2; S.occ_off = p; p += nvars + 2;
+    S.cursor = p; p += nvars + 2; S.occ = p; p += NL;
+    S.eliminated = (u8 *)p; S.selected = S.eliminated + nvars + 2; p += (nvars + 3) / 2 + 2;
+    S.estack = p; p += NL;
+    u32 *kept_len = p; p += NC + 2; u32 *kept_flag = p; p += NC + 2; u32 *new_off = p; p += NC + 2;
+    S.clause_cap = NC; S.lit_cap = NL; S.estack_cap = NL; S.nvars = nvars;
+    S.n_clauses = d_counts + 8; S.n_lits = d_counts + 9; S.estack_n = d_counts + 10; S.n_elim = d_counts + 11; S.overflow = d_counts + 12;
+    const u32 T = 256;
+    cudaMemsetAsync(d_counts, 0, 64, stream);
+    cudaMemsetAsync(S.removed, 1, NC, stream);           /* unused slots count as removed */
+    cudaMemsetAsync(S.eliminated, 0, 2 * (size_t)(nvars + 2), stream);
+    pp_sig_len<<<(nc + T - 1) / T, T, 0, stream>>>(d_coff, d_lits, cb, nc, S.sig, S.len, S.removed);
+    pp2_copy<<<(nc + T - 1) / T, T, 0, stream>>>(d_coff, d_lits, cb, nc, lit_base, S.wo, S.wl);
+    cudaMemcpyAsync(S.n_clauses, &nc, 4, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(S.n_lits, &nlits, 4, cudaMemcpyHostToDevice, stream);
+    cudaStreamSynchronize(stream);
+    u32 rounds = 0, ncur = nc;
+    for (; rounds < max_rounds; rounds++) {
+        cudaMemsetAsync(S.npos, 0, (size_t)5 * (nvars + 2) * 4, stream); /* npos, nneg, occ_cnt, occ_off, cursor */
+        const u32 g = (ncur + T - 1) / T;
+        bve_count<<<g, T, 0, stream>>>(S);
+        pp_scan<<<1, 1024, 0, stream>>>(S.occ_cnt, S.occ_off, nvars);
+        bve_fill<<<g, T, 0, stream>>>(S);
+        bve_select<<<(nvars + T - 1) / T, T, 0, stream>>>(S);
+        cudaMemcpyAsync(h_pin, S.n_elim, 4, cudaMemcpyDeviceToHost, stream);
+        bve_eliminate<<<(u32)(((u64)nvars * 32 + T - 1) / T), T, 0, stream>>>(S, grow, cl_lim, rounds);
+        cudaMemcpyAsync(h_pin + 1, S.n_elim, 4, cudaMemcpyDeviceToHost, stream);
+        cudaMemcpyAsync(h_pin + 2, S.n_clauses, 4, cudaMemcpyDeviceToHost, stream);
+        cudaMemcpyAsync(h_pin + 3, S.overflow, 4, cudaMemcpyDeviceToHost, stream);
+        if (cudaStreamSynchronize(stream) != cudaSuccess) return -2;
+        ncur = h_pin[2] < NC ? h_pin[2] : NC;
+        if (h_pin[3] || h_pin[1] == h_pin[0]) { rounds++; break; }
+    }
+    const u32 g = (ncur + T - 1) / T;
+    pp_kept_len<<<g, T, 0, stream>>>(S.len, S.removed, ncur, kept_len, kept_flag);
+    pp_scan<<<1, 1024, 0, stream>>>(kept_len, new_off, ncur);
+    pp_scan<<<1, 1024, 0, stream>>>(kept_flag, kept_len, ncur); /* kept_len now holds the new clause index */
+    pp2_compact<<<g, T, 0, stream>>>(S.wo, S.wl, ncur, S.len, S.removed, kept_len, new_off, d_out_coff, d_out_lits);
+    cudaMemcpyAsync(d_counts + 0, kept_len + ncur, 4, cudaMemcpyDeviceToDevice, stream);
+    cudaMemcpyAsync(d_counts + 1, new_off + ncur, 4, cudaMemcpyDeviceToDevice, stream);
+    cudaMemcpyAsync(d_counts + 2, S.n_elim, 4, cudaMemcpyDeviceToDevice, stream);
+    cudaMemcpyAsync(d_counts + 3, &rounds, 4, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_counts + 4, S.estack_n, 4, cudaMemcpyDeviceToDevice, stream);
+    cudaMemcpyAsync(d_counts + 5, S.overflow, 4, cudaMemcpyDeviceToDevice, stream);
+    cudaStreamSynchronize(stream);
+    *d_estack_out = S.estack;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}

@@ -432,3 +432,38 @@ def test_k4_strengthening_fixpoint(pkg, po):
         if want == 1:
             assert check_models(ioff, coff, li, res["verdict"], models) == 0, name
     e.close()
+
+
+def test_k4_bve_equisatisfiable_with_model_extension(pkg, po):
+    """K4 multi-CTA bounded variable elimination: the reduced CNF has the verdict of the original, and a model of the
+    reduced CNF, extended through the eliminated-clause records, satisfies the ORIGINAL CNF (SURVEY.md 8a S*)."""
+    g = load_golden()
+    e = pkg.Engine(0)
+    eliminated_total = 0
+    for name in ("uf50-01.cnf.gz", "uf50-03.cnf.gz", "uf50-07.cnf.gz", "uuf50-01.cnf.gz", "uuf50-04.cnf.gz", "uf20-02.cnf.gz",
+                 "2bitcomp_5.cnf.gz", "2bitmax_6.cnf.gz", "2bitadd_11.cnf.gz", "3blocks.cnf.gz", "4blocksb.cnf.gz", "uf250-083.cnf.gz"):
+        i = list(g["names"]).index(name)
+        off, lits = golden_instance(g, i)
+        nv = int(g["n_vars"][i])
+        want = int(g["core_verdict"][i])
+        ioff, coff, li = batch_of([(off, lits)])
+        e.upload(ioff, coff, li)
+        r = e.bve_instance(0, len(off) - 1, len(lits))
+        eliminated_total += r["eliminated"]
+        assert len(r["records"]) == r["eliminated"], name
+        elim_vars = {rec[1] for rec in r["records"]}
+        assert not any((int(l) >> 1) in elim_vars for l in r["lits"]), name          # eliminated vars are gone
+        if r["kept"] == 0:
+            assert want == 1, name
+            model = np.full(nv, 2, np.uint8)
+        else:
+            ioff_r, coff_r, li_r = batch_of([(r["clause_off"].astype(np.uint32), r["lits"])])
+            res, models = e.solve_batch(ioff_r, coff_r, li_r, kind=pkg.CORE, model_stride=nv)
+            assert res[0]["status"] == 0 and res[0]["verdict"] == want, (name, int(res[0]["verdict"]), want)
+            if want != 1:
+                continue
+            model = models[0].copy()
+        model = pkg.extend_model_k4(model, r["records"])
+        assert po.check_model(off, lits, model), name
+    assert eliminated_total > 300       # 2bitadd / 2bitcomp / blocks eliminate hundreds of variables
+    e.close()

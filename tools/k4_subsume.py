@@ -20,6 +20,10 @@ for i, name in enumerate(g["names"]):
         r = eng.subsume_instance(0, len(off) - 1, len(lits))
         best = r["kernel_ms"] if best is None else min(best, r["kernel_ms"])
     r2 = eng.simplify_instance(0, len(off) - 1, len(lits))
+    r3 = eng.bve_instance(0, len(off) - 1, len(lits))
+    print(json.dumps({"instance": str(name), "k4_bve": {"eliminated": int(r3["eliminated"]), "rounds": int(r3["rounds"]), "kept": int(r3["kept"]),
+                                                        "kept_lits": int(r3["kept_lits"]), "kernel_ms": round(r3["kernel_ms"], 3)},
+                      "oracle_eliminated_vars": int(g["rows"][i][3]), "oracle_clauses_left": int(g["rows"][i][2])}), flush=True)
     print(json.dumps({"instance": str(name), "k4_strengthen": {k: (int(v) if not isinstance(v, (bool, float)) else v) for k, v in r2.items() if k in ("kept", "kept_lits", "rounds", "strengthened", "unsat", "removed_count", "kernel_ms")}, "clauses": len(off) - 1, "literals": int(len(lits)), "k4_removed": int(r["removed_count"]),
                       "k4_kept": int(r["kept"]), "subset_tests": int(r["tests"]), "k4_kernels_ms": round(best, 3),
                       "oracle_full_preprocess_clauses_left": int(g["rows"][i][2]), "oracle_eliminated_vars": int(g["rows"][i][3])}), flush=True)
