@@ -452,7 +452,7 @@ class Engine:
                 "kept_lits": kept_lits, "rounds": counts[2], "strengthened": counts[3], "unsat": bool(counts[4]),
                 "removed_count": counts[5], "kernel_ms": ms.value}
 
-    def bve_instance(self, inst, n_clauses, n_lits, grow=0, cl_lim=20, max_rounds=64, stream=None):
+    def bve_instance(self, inst, n_clauses, n_lits, grow=0, cl_lim=20, max_rounds=512, stream=None):
         """K4 multi-CTA bounded variable elimination of instance `inst` -> dict(clause_off, lits, estack records, counts)."""
         u32p = C.POINTER(C.c_uint32)
         ooff = np.zeros(2 * n_clauses + 1030, np.uint32)

@@ -309,7 +309,8 @@ struct BveState {
     u32 *n_clauses, *n_lits;            /* cursors (device) */
     u32 clause_cap, lit_cap;
     u32 *npos, *nneg, *occ_cnt, *occ_off, *cursor, *occ;
-    u8 *eliminated, *selected;
+    u8 *eliminated, *selected, *tried;
+    u32 *n_selected;
     u32 *estack, *estack_n;
     u32 estack_cap;
     u32 *n_elim, *overflow;
@@ -335,7 +336,7 @@ __global__ void bve_fill(BveState S) {
 }
 __device__ __forceinline__ bool bve_cand(const BveState &S, u32 v) {
     const u32 p = S.npos[v], n = S.nneg[v];
-    return !S.eliminated[v] && p + n > 0 && p + n <= 64 && p * n <= 1024;
+    return !S.eliminated[v] && !S.tried[v] && p + n > 0 && p + n <= 64 && p * n <= 1024;
 }
 __global__ void bve_select(BveState S) {
     u32 v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,6 +356,7 @@ __global__ void bve_select(BveState S) {
         }
     }
     S.selected[v] = sel;
+    if (sel) atomicAdd(S.n_selected, 1u);
 }
 
 /* merge (formula/util.rs:45-77) of clause slots p and q on variable v: returns false for a tautology; out may be NULL */
@@ -412,7 +414,10 @@ __global__ void bve_eliminate(BveState S, u32 grow, int cl_lim, u32 round) {
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
         sumlen += s;
     }
-    if (cnt > npos + nneg + grow || (cl_lim != -1 && (int)maxlen > cl_lim)) return; /* simplify.rs:368-383 */
+    if (cnt > npos + nneg + grow || (cl_lim != -1 && (int)maxlen > cl_lim)) { /* simplify.rs:368-383 */
+        if (lane == 0) S.tried[v] = 1; /* not again until the neighbourhood changed (the host resets `tried` after progress) */
+        return;
+    }
     /* eliminated-clause record: [var, unit lit, round, k, (len, lits...) * k] of the smaller side */
     const bool save_neg = npos > nneg;
     const u32 ks = save_neg ? nneg : npos;
@@ -468,7 +473,7 @@ __global__ void bve_eliminate(BveState S, u32 grow, int cl_lim, u32 round) {
 
 extern "C" size_t b200sat_bve_words(size_t nc, size_t nvars, size_t nlits) {
     const size_t NC = 2 * nc + 1024, NL = 3 * nlits + 4096;
-    return 3 * NC + NL /* wo,len,sig,wl */ + (NC + 3) / 4 /* removed */ + 5 * (nvars + 2) + NL /* occ */ + (nvars + 3) / 2 /* flags */ +
+    return 3 * NC + NL /* wo,len,sig,wl */ + (NC + 3) / 4 /* removed */ + 5 * (nvars + 2) + NL /* occ */ + 3 * (nvars + 8) / 4 + 4 /* flags */ +
            NL /* estack */ + 3 * (NC + 2) /* compaction scratch */ + 64;
 }
 
@@ -483,36 +488,42 @@ extern "C" int b200sat_pp_bve_launch(const u32 *d_coff, const u32 *d_lits, u32 c
     S.removed = (u8 *)p; p += (NC + 3) / 4;
     S.npos = p; p += nvars + 2; S.nneg = p; p += nvars + 2; S.occ_cnt = p; p += nvars + 2; S.occ_off = p; p += nvars + 2;
     S.cursor = p; p += nvars + 2; S.occ = p; p += NL;
-    S.eliminated = (u8 *)p; S.selected = S.eliminated + nvars + 2; p += (nvars + 3) / 2 + 2;
+    S.eliminated = (u8 *)p; S.selected = S.eliminated + nvars + 2; S.tried = S.selected + nvars + 2; p += 3 * (nvars + 8) / 4 + 4;
     S.estack = p; p += NL;
     u32 *kept_len = p; p += NC + 2; u32 *kept_flag = p; p += NC + 2; u32 *new_off = p; p += NC + 2;
     S.clause_cap = NC; S.lit_cap = NL; S.estack_cap = NL; S.nvars = nvars;
-    S.n_clauses = d_counts + 8; S.n_lits = d_counts + 9; S.estack_n = d_counts + 10; S.n_elim = d_counts + 11; S.overflow = d_counts + 12;
+    S.n_clauses = d_counts + 8; S.n_lits = d_counts + 9; S.estack_n = d_counts + 10; S.n_elim = d_counts + 11; S.overflow = d_counts + 12; S.n_selected = d_counts + 13;
     const u32 T = 256;
     cudaMemsetAsync(d_counts, 0, 64, stream);
     cudaMemsetAsync(S.removed, 1, NC, stream);           /* unused slots count as removed */
-    cudaMemsetAsync(S.eliminated, 0, 2 * (size_t)(nvars + 2), stream);
+    cudaMemsetAsync(S.eliminated, 0, 3 * (size_t)(nvars + 2), stream);
     pp_sig_len<<<(nc + T - 1) / T, T, 0, stream>>>(d_coff, d_lits, cb, nc, S.sig, S.len, S.removed);
     pp2_copy<<<(nc + T - 1) / T, T, 0, stream>>>(d_coff, d_lits, cb, nc, lit_base, S.wo, S.wl);
     cudaMemcpyAsync(S.n_clauses, &nc, 4, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(S.n_lits, &nlits, 4, cudaMemcpyHostToDevice, stream);
     cudaStreamSynchronize(stream);
-    u32 rounds = 0, ncur = nc;
+    u32 rounds = 0, ncur = nc, elim_at_reset = 0;
     for (; rounds < max_rounds; rounds++) {
         cudaMemsetAsync(S.npos, 0, (size_t)5 * (nvars + 2) * 4, stream); /* npos, nneg, occ_cnt, occ_off, cursor */
+        cudaMemsetAsync(S.n_selected, 0, 4, stream);
         const u32 g = (ncur + T - 1) / T;
         bve_count<<<g, T, 0, stream>>>(S);
         pp_scan<<<1, 1024, 0, stream>>>(S.occ_cnt, S.occ_off, nvars);
         bve_fill<<<g, T, 0, stream>>>(S);
         bve_select<<<(nvars + T - 1) / T, T, 0, stream>>>(S);
-        cudaMemcpyAsync(h_pin, S.n_elim, 4, cudaMemcpyDeviceToHost, stream);
         bve_eliminate<<<(u32)(((u64)nvars * 32 + T - 1) / T), T, 0, stream>>>(S, grow, cl_lim, rounds);
+        cudaMemcpyAsync(h_pin + 0, S.n_selected, 4, cudaMemcpyDeviceToHost, stream);
         cudaMemcpyAsync(h_pin + 1, S.n_elim, 4, cudaMemcpyDeviceToHost, stream);
         cudaMemcpyAsync(h_pin + 2, S.n_clauses, 4, cudaMemcpyDeviceToHost, stream);
         cudaMemcpyAsync(h_pin + 3, S.overflow, 4, cudaMemcpyDeviceToHost, stream);
         if (cudaStreamSynchronize(stream) != cudaSuccess) return -2;
         ncur = h_pin[2] < NC ? h_pin[2] : NC;
-        if (h_pin[3] || h_pin[1] == h_pin[0]) { rounds++; break; }
+        if (h_pin[3]) { rounds++; break; }
+        if (h_pin[0] == 0) {                 /* no candidate left: retry the rejected variables if anything changed since */
+            if (h_pin[1] == elim_at_reset) { rounds++; break; }
+            elim_at_reset = h_pin[1];
+            cudaMemsetAsync(S.tried, 0, nvars + 2, stream);
+        }
     }
     const u32 g = (ncur + T - 1) / T;
     pp_kept_len<<<g, T, 0, stream>>>(S.len, S.removed, ncur, kept_len, kept_flag);
