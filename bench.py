@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--solver", default="core", choices=["core", "simp"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=2, help="batches in flight (engines/streams); 1 = strictly serial steps")
+    ap.add_argument("--pipeline", type=int, default=3, help="batches in flight (engines/streams); 1 = strictly serial steps")
     return ap.parse_args()
 
 
