@@ -51,8 +51,8 @@ typedef struct b200sat_settings {
     uint8_t  luby_restart;            /* search.rs:30               1          */
     uint8_t  rnd_pol;                 /* decision_heuristic.rs:29   0          */
     uint8_t  rnd_init_act;            /* decision_heuristic.rs:30   0          */
-    uint8_t  use_rcheck;              /* search.rs:177              0 (unsupported: must be 0) */
-    uint8_t  use_asymm;               /* simplify.rs:29             0 (unsupported: must be 0) */
+    uint8_t  use_rcheck;              /* search.rs:177              0   is_implied before add_clause, search/util.rs:16-42 */
+    uint8_t  use_asymm;               /* simplify.rs:29             0   SimpSolver only, search/util.rs:44-73 */
     uint8_t  use_elim;                /* simplify.rs:30             1          */
     uint8_t  extend_model;            /* minisat.rs:117             1          */
     uint8_t  remove_satisfied;        /* clause_db.rs:13            1          */

@@ -7,9 +7,8 @@ src/sat/minisat/search.rs:398-405 search table frame).
 Log lines go to stderr (the reference logs through env_logger to stderr), the verdict line to
 stdout.  Out-of-range flag values are silently ignored, `--phase-saving` is a no-op and
 `--rsync` does not exist, exactly as in the reference.  Not reproduced in round 1: the
-per-learnt-limit progress rows inside the search table (the device does not log them) and the
-`--rcheck` / `--asymm` features (rejected with a message).  Solving runs on the GPU through the
-C ABI; there is no CPU path.
+per-learnt-limit progress rows inside the search table (the device does not log them).
+Solving runs on the GPU through the C ABI; there is no CPU path.
 """
 import argparse
 import sys

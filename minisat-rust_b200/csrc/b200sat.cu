@@ -368,8 +368,6 @@ extern "C" int b200sat_engine_finish(b200sat_engine *e);
 
 static int check_settings(const b200sat_settings *s, int kind) {
     if (!s) return set_err(B200SAT_E_ARG, "null settings");
-    if (s->use_rcheck) return set_err(B200SAT_E_ARG, "use_rcheck is not supported (SURVEY.md 8f-4)");
-    if (s->use_asymm) return set_err(B200SAT_E_ARG, "use_asymm is not supported (SURVEY.md 8f-4)");
     if (!(s->var_decay > 0 && s->clause_decay > 0)) return set_err(B200SAT_E_ARG, "decay must be > 0");
     if (kind != B200SAT_CORE && kind != B200SAT_SIMP) return set_err(B200SAT_E_ARG, "kind must be CORE or SIMP");
 #ifndef B200SAT_HAVE_SIMP
@@ -383,7 +381,8 @@ static int launch_attempt(b200sat_engine *e) {
     b200sat_engine::Pending &pd = e->pend;
     cudaStream_t stream = pd.stream;
     int rc;
-    const bool count = (pd.flags & B200SAT_F_COUNT_TRAFFIC) != 0;
+    /* the instrumented flavour also carries the CoreSolver --rcheck ingest branch (cdcl_warp.cuh solve_core) */
+    const bool count = (pd.flags & B200SAT_F_COUNT_TRAFFIC) != 0 || (pd.kind == B200SAT_CORE && pd.st.use_rcheck);
     if (pd.attempt == 3) pd.tier_nv = 0; /* last resort: var state in HBM too, biggest slabs */
     Layout L = plan_layout(e->shape, pd.tier_nv, pd.kind, pd.attempt, e->cfg_arena, e->cfg_wpool);
     size_t spw = 0;

@@ -1517,6 +1517,26 @@ template <class VT, bool COUNT> struct WarpSolver {
         return true;
     }
 
+    /* search/util.rs:16-42 (--rcheck): on a scratch decision level assume the negation of every literal
+     * and propagate; the clause is implied iff that conflicts (or one literal already holds).  Phases of
+     * the scratch level are saved as top-level ones, exactly as cancel_until does for the newest level. */
+    DEV bool is_implied(const u32 *c, u32 n) {
+        new_decision_level();
+        bool hit = false;
+        for (u32 i = 0; i < n && !hit; i++) {
+            const u32 l = c[i];
+            u32 act = 0; /* read on the lane that writes the assignment, so no lane sees a half-updated state */
+            if (lane == 0) act = is_true(l) ? 1u : (V.assign()[l >> 1] == LB_UNDEF ? 2u : 0u);
+            act = __shfl_sync(FULL_MASK, act, 0);
+            if (act == 1) hit = true;
+            else if (act == 2) assign_lit(l ^ 1, CREF_UNDEF);
+        }
+        bool result = hit;
+        if (!hit) result = propagate() != CREF_UNDEF;
+        cancel_until(GROUND);
+        return result && !failed();
+    }
+
     /* Searcher::add_clause search.rs:342-386.  0 = UNSAT, 1 = consumed, 2 = added (cref in out_cr) */
     DEV u32 add_clause(const u32 *src, u32 len, u32 &out_cr, bool as_learnt = false) {
         u32 nk = 0;
@@ -1642,6 +1662,14 @@ template <class VT, bool COUNT> struct WarpSolver {
             for (u32 c = cb; c < ce && ok; c++) { /* CoreSolver::add_clause minisat.rs:41-48 */
                 u32 b = P.clause_off[c], e = P.clause_off[c + 1];
                 u32 cr;
+                /* search.rs:343-345.  Only the instrumented kernel flavour carries this branch (the host routes
+                 * use_rcheck there): a second inlined copy of propagate() costs the plain kernel 4 % (A/B
+                 * measured), and --rcheck is a non-default diagnostic feature. */
+                if (COUNT && st().use_rcheck) {
+                    bool imp = is_implied(P.lits + b, e - b);
+                    if (failed()) break;
+                    if (imp) continue;
+                }
                 if (add_clause(P.lits + b, e - b, cr) == 0) ok = false;
                 if (failed()) break;
             }

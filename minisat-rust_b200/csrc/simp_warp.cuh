@@ -255,8 +255,64 @@ template <class WS, bool COUNT> struct SeqSimp {
         for (u32 i = 0; i < len; i++) a |= 1u << ((arena()[cr + 1 + i] >> 1) & 31);
         return a;
     }
+    /* ------------------------------------------------------------ scratch decision level (scalar)
+     * assignment.rs:99-101,116-130; phases are saved as top-level ones (search/util.rs:27,38,66).  Nothing has
+     * left the order heap while the simplifier runs, so no variable needs returning to it. */
+    DEV void seq_new_level() { S.V.lim()[S.nlevels] = (idx_t)S.trail_n; S.nlevels++; }
+    DEV void seq_backtrack_ground() {
+        const u32 target = (u32)S.V.lim()[GROUND];
+        const i32 ps = S.st().phase_saving;
+        u8 *vf = S.V.vflags();
+        for (u32 k = target; k < S.trail_n; k++) {
+            const u32 l = S.V.trail()[k], v = l >> 1;
+            if (ps >= 1) vf[v] = (u8)((vf[v] & ~VF_POL) | ((l & 1) ? VF_POL : 0));
+            S.V.assign()[v] = LB_UNDEF;
+        }
+        S.trail_n = target;
+        S.nlevels = GROUND;
+        if (S.qhead > S.trail_n) S.qhead = S.trail_n;
+    }
+    /* search/util.rs:16-42 (--rcheck) */
+    DEV bool seq_is_implied(const u32 *c, u32 n) {
+        seq_new_level();
+        bool hit = false;
+        for (u32 i = 0; i < n && !hit; i++) {
+            const u32 l = c[i];
+            if (S.is_true(l)) hit = true;
+            else if (S.V.assign()[l >> 1] == LB_UNDEF) seq_assign(l ^ 1, CREF_UNDEF);
+        }
+        bool result = hit;
+        if (!hit) result = seq_propagate() != CREF_UNDEF;
+        seq_backtrack_ground();
+        return result && !failed();
+    }
+    /* search/util.rs:44-73 (--asymm): true = the literal of `v` in `cr` can be dropped (returned in `out`) */
+    DEV bool seq_asymmetric_branching(u32 v, u32 cr, u32 &out) {
+        const u32 *ar = arena();
+        if (ar[cr] & H_DELETED) return false;
+        const u32 n = ar[cr] >> H_SHIFT;
+        for (u32 i = 0; i < n; i++) if (S.is_true(ar[cr + 1 + i])) return false;
+        seq_new_level();
+        u32 vl = LIT_NONE;
+        for (u32 i = 0; i < n; i++) {
+            const u32 l = ar[cr + 1 + i];
+            if ((l >> 1) == v) vl = l;
+            else if (S.V.assign()[l >> 1] == LB_UNDEF) seq_assign(l ^ 1, CREF_UNDEF);
+        }
+        const u32 confl = seq_propagate();
+        seq_backtrack_ground();
+        if (failed() || confl == CREF_UNDEF) return false;
+        out = vl;
+        return true;
+    }
+
     /* Searcher::add_clause search.rs:342-386 (scalar) */
     DEV u32 seq_add_clause(const u32 *src, u32 n, u32 &out_cr) {
+        if (S.st().use_rcheck) { /* search.rs:343-345 */
+            bool imp = seq_is_implied(src, n);
+            if (failed()) return ADD_UNSAT;
+            if (imp) return ADD_CONSUMED;
+        }
         if (n > SL.tmp_cap) { fail(ST_MEM_SIMP); return ADD_UNSAT; }
         u32 *ps = tmpb;
         for (u32 i = 0; i < n; i++) ps[i] = src[i];
@@ -804,6 +860,29 @@ template <class WS, bool COUNT> struct SeqSimp {
         sc().simp_db_props = sc().propagations + sc().clauses_literals + sc().learnts_literals;
     }
 
+    /* simplify.rs:303-336 (--asymm), including the reference's preserved skip after a strengthened long clause */
+    DEV bool asymm_var(u32 v) {
+        if (S.V.assign()[v] != LB_UNDEF) return true;
+        occ_lookup(v);
+        const u32 nc = olen[v];
+        if (nc == 0) return true;
+        if (nc > SL.cand_cap) { fail(ST_MEM_SIMP); return false; }
+        for (u32 i = 0; i < nc; i++) cls[i] = opool[ostart[v] + i];
+        bool bug = false;
+        for (u32 i = 0; i < nc; i++) {
+            if (bug) { bug = false; continue; }
+            const u32 cr = cls[i];
+            u32 l = LIT_NONE;
+            if (seq_asymmetric_branching(v, cr, l)) {
+                if ((arena()[cr] >> H_SHIFT) > 2) bug = true;
+                if (!sq_push(cr)) return false;
+                if (!strengthen_clause(cr, l)) return false;
+            }
+            if (failed()) return false;
+        }
+        return true;
+    }
+
     /* simplify.rs:213-274; false = Err */
     DEV bool eliminate() {
         for (;;) {
@@ -814,6 +893,13 @@ template <class WS, bool COUNT> struct SeqSimp {
             u32 var;
             while (eh_pop(var)) {
                 if (is_elim(var) || S.V.assign()[var] != LB_UNDEF) continue;
+                if (S.st().use_asymm) { /* simplify.rs:236-247 */
+                    const u8 was = S.V.vflags()[var] & VF_FROZEN;
+                    S.V.vflags()[var] |= VF_FROZEN;
+                    if (!asymm_var(var)) return false;
+                    if (!backward_subsumption_check()) return false;
+                    S.V.vflags()[var] = (u8)((S.V.vflags()[var] & ~VF_FROZEN) | was);
+                }
                 if (S.st().use_elim && S.V.assign()[var] == LB_UNDEF && !is_frozen(var)) {
                     if (!eliminate_var(var)) return false;
                     if (!backward_subsumption_check()) return false;
@@ -1080,7 +1166,23 @@ template <class WS, bool COUNT> struct SeqSimp {
                 }
                 got = bcast(got);
                 if (!got) break;
-                var = bcast(var); do_elim = bcast(do_elim);
+                var = bcast(var);
+                if (S.st().use_asymm) { /* simplify.rs:236-247: lane 0 branches, the subsumption check stays cooperative */
+                    u32 bad = 0, was = 0;
+                    if (lane == 0) {
+                        was = S.V.vflags()[var] & VF_FROZEN;
+                        S.V.vflags()[var] |= VF_FROZEN;
+                        if (!asymm_var(var)) bad = 1;
+                    }
+                    if (bcast(bad)) return false;
+                    refresh_views();
+                    if (!u_backward_subsumption_check()) return false;
+                    if (lane == 0) {
+                        S.V.vflags()[var] = (u8)((S.V.vflags()[var] & ~VF_FROZEN) | was);
+                        do_elim = (S.st().use_elim && S.V.assign()[var] == LB_UNDEF && !is_frozen(var)) ? 1 : 0;
+                    }
+                }
+                do_elim = bcast(do_elim);
                 if (do_elim) {
                     if (!u_eliminate_var(var)) return false;
                     if (!u_backward_subsumption_check()) return false;

@@ -46,9 +46,9 @@ def test_no_device_is_a_loud_error(pkg):
         s.solve_limited()
 
 
-def test_unsupported_settings_rejected(pkg):
+def test_invalid_settings_rejected(pkg):
     st = pkg.default_settings()
-    st.use_asymm = 1
+    st.var_decay = 0.0
     with pytest.raises(pkg.EngineError):
         pkg.CoreSolver(st)
 

@@ -56,9 +56,10 @@ def test_core_synthetic_adversarial_schedule(po, emu):
 
 
 @pytest.mark.parametrize("variant", ["rnd_freq", "rnd_init", "rnd_pol", "ccmin_basic", "ccmin_none", "phase_none",
-                                     "phase_limited", "no_luby", "small_restart"])
+                                     "phase_limited", "no_luby", "small_restart", "rcheck"])
 def test_core_settings_variants(po, emu, variant):
     st = po.default_settings()
+    if variant == "rcheck": st.use_rcheck = 1          # search/util.rs:16-42 on every ingested clause
     if variant == "rnd_freq": st.random_var_freq = 0.1
     if variant == "rnd_init": st.rnd_init_act = 1
     if variant == "rnd_pol": st.rnd_pol = 1
@@ -70,6 +71,16 @@ def test_core_settings_variants(po, emu, variant):
     if variant == "small_restart": st.restart_first = 5.0; st.size_adjust_start_confl = 10; st.size_factor = 0.05
     ioff, coff, lits = synth_batch(po, SEED2 + 1000, 10, 50, 213)
     compare(po, emu, ioff, coff, lits, po.CORE, settings=st, sched_seed=3)
+
+
+def test_edge_cases_with_rcheck(po, emu):
+    """Duplicate literals, tautologies, ingest-time units and the empty clause through is_implied first."""
+    st = po.default_settings()
+    st.use_rcheck = 1
+    st.use_asymm = 1
+    ioff, coff, lits = batch_of([csr_of(EDGE_CASES[k]) for k in sorted(EDGE_CASES)])
+    compare(po, emu, ioff, coff, lits, po.CORE, settings=st, nv=64, sched_seed=5)
+    compare(po, emu, ioff, coff, lits, po.SIMP, settings=st, nv=64, sched_seed=6)
 
 
 def test_core_reduce_and_gc_paths(po, emu):
@@ -132,9 +143,13 @@ def test_simp_without_preprocess_call(po, emu):
             assert (a[:o.n_vars] == b[:o.n_vars]).all()
 
 
-@pytest.mark.parametrize("variant", ["grow", "no_elim", "cl_lim", "sub_lim", "simp_gc"])
+@pytest.mark.parametrize("variant", ["grow", "no_elim", "cl_lim", "sub_lim", "simp_gc", "rcheck", "asymm",
+                                     "asymm_no_elim", "rcheck_asymm"])
 def test_simp_settings_variants(po, emu, variant):
     st = po.default_settings()
+    if "rcheck" in variant: st.use_rcheck = 1          # also applies to the resolvents BVE adds
+    if "asymm" in variant: st.use_asymm = 1            # simplify.rs:303-336 + search/util.rs:44-73
+    if variant == "asymm_no_elim": st.use_elim = 0
     if variant == "grow": st.grow = 8
     if variant == "no_elim": st.use_elim = 0
     if variant == "cl_lim": st.clause_lim = 4

@@ -114,9 +114,10 @@ def test_n250_sample_vs_oracle(pkg, po, eng):
 
 
 @pytest.mark.parametrize("variant", ["rnd_freq", "rnd_init", "rnd_pol", "ccmin_basic", "ccmin_none", "phase_none",
-                                     "phase_limited", "no_luby", "tiny_db"])
+                                     "phase_limited", "no_luby", "tiny_db", "rcheck"])
 def test_settings_variants(pkg, po, eng, variant):
     st = pkg.default_settings()
+    if variant == "rcheck": st.use_rcheck = 1
     if variant == "rnd_freq": st.random_var_freq = 0.1
     if variant == "rnd_init": st.rnd_init_act = 1
     if variant == "rnd_pol": st.rnd_pol = 1
@@ -214,6 +215,39 @@ def test_synthetic_n100_simp_vs_oracle(pkg, po, eng):
     res, models = eng.solve_batch(ioff, coff, lits, kind=pkg.SIMP, flags=flags(pkg), model_stride=100)
     assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, po.SIMP)
     assert check_models(ioff, coff, lits, res["verdict"], models) == 0
+
+
+@pytest.mark.parametrize("variant", ["rcheck", "asymm", "asymm_no_elim", "rcheck_asymm"])
+def test_simp_rcheck_asymm_variants(pkg, po, eng, variant):
+    """--rcheck / --asymm (search/util.rs:16-73, simplify.rs:236-247,303-336) on random and structured instances."""
+    import ctypes as C
+    st = pkg.default_settings()
+    if "rcheck" in variant: st.use_rcheck = 1
+    if "asymm" in variant: st.use_asymm = 1
+    if variant == "asymm_no_elim": st.use_elim = 0
+    ost = po.default_settings()
+    C.memmove(C.addressof(ost), C.addressof(st), C.sizeof(st))
+    ioff, coff, lits = synth_batch(po, SEED2 + 2000, 200, 80, 341)
+    res, models = eng.solve_batch(ioff, coff, lits, settings=st, kind=pkg.SIMP, flags=flags(pkg), model_stride=80)
+    assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, po.SIMP, settings=ost)
+    assert check_models(ioff, coff, lits, res["verdict"], models) == 0
+    g = load_golden()
+    idx = [i for i in range(len(g["names"])) if g["n_vars"][i] <= 128]
+    ioff, coff, lits = batch_of([golden_instance(g, i) for i in idx])
+    res, models = eng.solve_batch(ioff, coff, lits, settings=st, kind=pkg.SIMP, flags=flags(pkg), model_stride=128)
+    assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, po.SIMP, settings=ost)
+    for kind, okind in ((pkg.CORE, po.CORE), (pkg.SIMP, po.SIMP)):
+        ioff, coff, lits = batch_of([csr_of(EDGE_CASES[k]) for k in sorted(EDGE_CASES)])
+        res, models = eng.solve_batch(ioff, coff, lits, settings=st, kind=kind, flags=flags(pkg), model_stride=64)
+        assert_matches_oracle(pkg, po, res, models, ioff, coff, lits, okind, settings=ost)
+    # without the traffic-counter flag the host must still route CoreSolver --rcheck to the kernel flavour that has it
+    ioff, coff, lits = synth_batch(po, SEED2 + 2000, 100, 80, 341)
+    res, _ = eng.solve_batch(ioff, coff, lits, settings=st, kind=pkg.CORE,
+                             flags=pkg.F_PREPROCESS | pkg.F_ZERO_STATS_ON_PRE_UNSAT | pkg.F_TRACE_HASH, model_stride=80)
+    ores, _, _ = po.solve_batch(ioff, coff, lits, kind=po.CORE, settings=ost, threads=8)
+    for i in range(100):
+        assert res[i]["status"] == 0 and res[i]["verdict"] == ores[i].verdict
+        assert list(res[i]["stats"]) == list(ores[i].stats) and int(res[i]["trace_hash"]) == ores[i].trace_hash
 
 
 def test_single_solver_api_simp(pkg, po):
