@@ -218,10 +218,24 @@ int b200sat_engine_download_batch(b200sat_engine *e, uint32_t *inst_clause_off, 
 /* Tunables: warps per block / blocks per SM (0 = auto).  Launch facts of the last solve. */
 int b200sat_engine_configure(b200sat_engine *e, int warps_per_block, int blocks_per_sm,
                              uint64_t arena_words, uint64_t wpool_entries);
+/* Resident-instance scheduling and budgets of the following solve calls of this engine (round 2).
+ *   slice:  conflicts an instance may run before it yields its warp to instances waiting in the device work ring
+ *           (it is parked in its slab and re-queued; trace-neutral).  0 = never yield.  Default 20000.
+ *   budget: Budget{conflict_budget, propagation_budget} of budget.rs:5-34 for every instance of the batch, checked
+ *           where the reference checks it (search.rs:473-477); an instance that runs out returns
+ *           B200SAT_INTERRUPTED with status OK, backtracked to ground level, its state still resident.  < 0 = none.
+ *   interrupt: Budget::asynch_interrupt -- may be raised from another host thread while a solve call is running;
+ *           every running instance returns B200SAT_INTERRUPTED at its next check. */
+int b200sat_engine_set_slice(b200sat_engine *e, uint32_t slice_conflicts);
+int b200sat_engine_set_budget(b200sat_engine *e, int64_t conflict_budget, int64_t propagation_budget);
+int b200sat_engine_interrupt(b200sat_engine *e, int raised);
 typedef struct b200sat_launch_info {
     uint32_t grid, block, smem_bytes, warps_total, tier /*0 smem var state, 1 global*/, launches;
     uint64_t slab_bytes;
-    float    last_kernel_ms;   /* CUDA-event time of the cdcl_warp launch(es) of the last solve */
+    float    last_kernel_ms;   /* CUDA-event time of all launches (ingest + search) of the last solve */
+    float    search_ms;        /* CUDA-event time of the search kernel(s) alone (first chunk of each attempt) */
+    uint32_t suspends;         /* times an instance was parked at the end of a conflict slice and re-queued */
+    uint32_t resident_items;   /* instances whose state is resident at once (slabs allocated) */
 } b200sat_launch_info;
 int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out);
 
@@ -238,7 +252,8 @@ int b200sat_solve_batch(b200sat_engine *e, const b200sat_batch *batch, const b20
  * stop at their next conflict (the Budget / interrupt analogue, budget.rs:5-34).  Replica 0 keeps the
  * base settings: with sharing off its trace is bit-exact the single-instance one. */
 enum { B200SAT_PF_SHARE = 1 /* units + binaries */, B200SAT_PF_IGNORE_DONE = 2,
-       B200SAT_PF_SHARE_LBD2 = 4 /* also LBD <= 2 clauses of <= 8 literals */ };
+       B200SAT_PF_SHARE_LBD2 = 4 /* also LBD <= 2 clauses of <= 8 literals */,
+       B200SAT_PF_KEEP_RING = 8 /* do not clear the local ring first: the caller cleared all rings and synchronised the ranks */ };
 /* settings of global replica `replica` derived from `base` (replica 0 = base) -- SURVEY.md T19 */
 void b200sat_diversify(const b200sat_settings *base, uint32_t replica, b200sat_settings *out);
 int  b200sat_engine_ring_create(b200sat_engine *e, uint32_t payload_words, uint32_t n_rings, uint32_t my_slot);

@@ -90,7 +90,8 @@ class BatchStruct(C.Structure):
 class LaunchInfo(C.Structure):
     _fields_ = [("grid", C.c_uint32), ("block", C.c_uint32), ("smem_bytes", C.c_uint32),
                 ("warps_total", C.c_uint32), ("tier", C.c_uint32), ("launches", C.c_uint32),
-                ("slab_bytes", C.c_uint64), ("last_kernel_ms", C.c_float)]
+                ("slab_bytes", C.c_uint64), ("last_kernel_ms", C.c_float), ("search_ms", C.c_float),
+                ("suspends", C.c_uint32), ("resident_items", C.c_uint32)]
 
 
 def traffic_bytes(t):
@@ -113,8 +114,9 @@ ABI_SYMBOLS = (
     "b200sat_diversify", "b200sat_engine_ring_create", "b200sat_engine_ring_reset", "b200sat_engine_ring_ipc_handle",
     "b200sat_engine_ring_open_peer", "b200sat_portfolio_solve", "b200sat_engine_download_replicas",
     "b200sat_engine_verify_models", "b200sat_engine_subsume_instance", "b200sat_engine_simplify_instance", "b200sat_engine_bve_instance", "b200sat_read_dimacs", "b200sat_free_buffer", "b200sat_write_result",
+    "b200sat_engine_set_slice", "b200sat_engine_set_budget", "b200sat_engine_interrupt",
 )
-PF_SHARE, PF_IGNORE_DONE, PF_SHARE_LBD2 = 1, 2, 4
+PF_SHARE, PF_IGNORE_DONE, PF_SHARE_LBD2, PF_KEEP_RING = 1, 2, 4, 8
 
 _lib = None
 
@@ -159,6 +161,9 @@ def lib():
     L.b200sat_engine_download_batch.argtypes = [vp, u32p, u32p, u32p]
     L.b200sat_engine_configure.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
     L.b200sat_engine_launch_info.argtypes = [vp, C.POINTER(LaunchInfo)]
+    L.b200sat_engine_set_slice.argtypes = [vp, C.c_uint32]
+    L.b200sat_engine_set_budget.argtypes = [vp, C.c_int64, C.c_int64]
+    L.b200sat_engine_interrupt.argtypes = [vp, C.c_int]
     L.b200sat_solve_batch.argtypes = [vp, C.POINTER(BatchStruct), C.POINTER(Settings), C.c_int, C.c_int,
                                       vp, u8p, C.c_uint32]
     L.b200sat_engine_solve_async.argtypes = [vp, C.POINTER(Settings), C.c_int, C.c_int, vp]
@@ -321,6 +326,18 @@ class Engine:
 
     def configure(self, warps_per_block=0, blocks_per_sm=0, arena_words=0, wpool_entries=0):
         _check(lib().b200sat_engine_configure(self._e, warps_per_block, blocks_per_sm, arena_words, wpool_entries))
+
+    def set_slice(self, slice_conflicts):
+        """conflicts an instance runs before it yields to waiting ones (0 = never); trace-neutral"""
+        _check(lib().b200sat_engine_set_slice(self._e, slice_conflicts))
+
+    def set_budget(self, conflict_budget=-1, propagation_budget=-1):
+        """Budget (budget.rs:5-34) of every instance of the following solve calls; < 0 = none"""
+        _check(lib().b200sat_engine_set_budget(self._e, conflict_budget, propagation_budget))
+
+    def interrupt(self, raised=True):
+        """Budget::asynch_interrupt: may be called from another thread while solve() runs"""
+        _check(lib().b200sat_engine_interrupt(self._e, 1 if raised else 0))
 
     @staticmethod
     def _batch(inst_clause_off, clause_off, lits):

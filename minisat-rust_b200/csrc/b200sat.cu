@@ -110,10 +110,10 @@ __global__ void verify_models(const u32 *ioff, const u32 *coff, const u32 *lits,
     if (lane == 0) { verified[warp] = any ? 0 : 1; if (any) atomicAdd(n_violated, 1u); }
 }
 
-__global__ void collect_failed(const b200sat_result *results, const u32 *work, u32 n_work, u32 *out_list, u32 *out_count) {
+__global__ void collect_failed(const b200sat_result *results, const u32 *work, u32 n_work, bool portfolio, u32 *out_list, u32 *out_count) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_work) return;
-    u32 inst = work ? work[i] : i;
+    u32 inst = (work && !portfolio) ? work[i] : i;
     if (results[inst].status < 0) out_list[atomicAdd(out_count, 1u)] = inst; /* > 0: cancelled portfolio replica */
 }
 
@@ -170,7 +170,17 @@ struct b200sat_engine {
     /* work */
     u8 *d_slabs = nullptr;
     size_t cap_slabs = 0;
-    u32 *d_queue = nullptr;      /* [0] queue counter, [1] failed counter */
+    u32 *d_queue = nullptr;      /* [0] queue counter, [1] failed counter, [32..40) work-ring control words */
+    unsigned long long *d_ring = nullptr; /* device work ring of the search kernel */
+    size_t cap_ring = 0;
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr; /* around the search kernel alone */
+    u32 slice_conflicts = 20000;  /* conflicts an instance may run before it yields to waiting ones */
+    long long conflict_budget = -1, propagation_budget = -1;
+    int *h_interrupt = nullptr;   /* pinned, device-mapped async interrupt word (Budget::asynch_interrupt) */
+    int *d_interrupt = nullptr;
+    u32 resident_items = 0;       /* items whose state is parked in d_slabs (chunk 0 of the last solve) */
+    Layout resident_L;            /* layout the parked states were written with */
+    int resident_tier_nv = 0;
     u32 *d_work[2] = {nullptr, nullptr};
     size_t cap_work = 0, cap_work1 = 0;
     u32 *h_pinned = nullptr;     /* small pinned staging for counters */
@@ -186,7 +196,8 @@ struct b200sat_engine {
     u32 n_replicas = 0;
     /* in-flight asynchronous solve */
     struct Pending {
-        bool active = false, retried = false;
+        bool active = false, retried = false, searched = false;
+        float search_ms = 0.f;
         b200sat_settings st;
         int kind = 0, flags = 0, tier_nv = 0;
         cudaStream_t stream = nullptr;
@@ -203,6 +214,8 @@ struct b200sat_engine {
     /* tunables */
     int cfg_wpb = 0, cfg_bps = 0;
     u64 cfg_arena = 0, cfg_wpool = 0;
+    size_t cfg_slab_budget = 0;   /* bytes; 0 = 60% of the free HBM */
+    u32 import_cap = 64;          /* portfolio: imported clauses per replica and restart boundary */
     b200sat_launch_info info;
 };
 
@@ -228,8 +241,12 @@ extern "C" b200sat_engine *b200sat_engine_create(int device) {
     e->num_sms = prop.multiProcessorCount;
     e->smem_optin = prop.sharedMemPerBlockOptin;
     memset(&e->info, 0, sizeof e->info);
-    if (cudaMalloc((void **)&e->d_queue, 128) != cudaSuccess || cudaMallocHost((void **)&e->h_pinned, 128) != cudaSuccess ||
-        cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
+    memset(&e->resident_L, 0, sizeof e->resident_L);
+    if (cudaMalloc((void **)&e->d_queue, 256) != cudaSuccess || cudaMallocHost((void **)&e->h_pinned, 256) != cudaSuccess ||
+        cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
+        cudaEventCreate(&e->ev2) != cudaSuccess || cudaEventCreate(&e->ev3) != cudaSuccess ||
+        cudaHostAlloc((void **)&e->h_interrupt, 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&e->d_interrupt, e->h_interrupt, 0) != cudaSuccess || (*e->h_interrupt = 0) != 0) {
         set_err(B200SAT_E_CUDA, "engine allocation failed");
         delete e;
         return nullptr;
@@ -249,6 +266,10 @@ extern "C" void b200sat_engine_destroy(b200sat_engine *e) {
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev2) cudaEventDestroy(e->ev2);
+    if (e->ev3) cudaEventDestroy(e->ev3);
+    if (e->h_interrupt) cudaFreeHost(e->h_interrupt);
+    cudaFree(e->d_ring);
     delete e;
 }
 
@@ -256,6 +277,23 @@ extern "C" int b200sat_engine_configure(b200sat_engine *e, int warps_per_block, 
                                         uint64_t wpool_entries) {
     if (!e) return set_err(B200SAT_E_ARG, "null engine");
     e->cfg_wpb = warps_per_block; e->cfg_bps = blocks_per_sm; e->cfg_arena = arena_words; e->cfg_wpool = wpool_entries;
+    return 0;
+}
+
+extern "C" int b200sat_engine_set_slice(b200sat_engine *e, uint32_t slice_conflicts) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    e->slice_conflicts = slice_conflicts;
+    return 0;
+}
+extern "C" int b200sat_engine_set_budget(b200sat_engine *e, int64_t conflict_budget, int64_t propagation_budget) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    e->conflict_budget = conflict_budget < 0 ? -1 : conflict_budget;
+    e->propagation_budget = propagation_budget < 0 ? -1 : propagation_budget;
+    return 0;
+}
+extern "C" int b200sat_engine_interrupt(b200sat_engine *e, int raised) {
+    if (!e || !e->h_interrupt) return set_err(B200SAT_E_ARG, "null engine");
+    *(volatile int *)e->h_interrupt = raised ? 1 : 0;
     return 0;
 }
 
@@ -357,11 +395,16 @@ extern "C" int b200sat_engine_generate_ksat(b200sat_engine *e, uint64_t seed_bas
     return alloc_outputs(e);
 }
 
-static kernel_fn pick_kernel(int tier_nv, bool count, int kind, size_t &smem_per_warp) {
+static kernel_fn pick_ingest(int tier_nv, bool count, int kind, size_t &smem_per_warp, size_t &save) {
 #ifdef B200SAT_HAVE_SIMP
-    if (kind == B200SAT_SIMP) return count ? b200sat_pick_c1s1(tier_nv, &smem_per_warp) : b200sat_pick_c0s1(tier_nv, &smem_per_warp);
+    if (kind == B200SAT_SIMP)
+        return count ? b200sat_pick_ingest_c1s1(tier_nv, &smem_per_warp, &save) : b200sat_pick_ingest_c0s1(tier_nv, &smem_per_warp, &save);
 #endif
-    return count ? b200sat_pick_c1s0(tier_nv, &smem_per_warp) : b200sat_pick_c0s0(tier_nv, &smem_per_warp);
+    return count ? b200sat_pick_ingest_c1s0(tier_nv, &smem_per_warp, &save) : b200sat_pick_ingest_c0s0(tier_nv, &smem_per_warp, &save);
+}
+static kernel_fn pick_search(int tier_nv, bool count, bool portfolio, size_t &smem_per_warp, size_t &save) {
+    if (portfolio) return b200sat_pick_search_pf(tier_nv, &smem_per_warp, &save);
+    return count ? b200sat_pick_search_c1(tier_nv, &smem_per_warp, &save) : b200sat_pick_search_c0(tier_nv, &smem_per_warp, &save);
 }
 
 extern "C" int b200sat_engine_finish(b200sat_engine *e);
@@ -376,18 +419,13 @@ static int check_settings(const b200sat_settings *s, int kind) {
     return 0;
 }
 
-/* enqueue one attempt (kernel + failure collection + count read-back) on the pending stream; no host sync */
-static int launch_attempt(b200sat_engine *e) {
-    b200sat_engine::Pending &pd = e->pend;
-    cudaStream_t stream = pd.stream;
-    int rc;
-    /* the instrumented flavour also carries the CoreSolver --rcheck ingest branch (cdcl_warp.cuh solve_core) */
-    const bool count = (pd.flags & B200SAT_F_COUNT_TRAFFIC) != 0 || (pd.kind == B200SAT_CORE && pd.st.use_rcheck);
-    if (pd.attempt == 3) pd.tier_nv = 0; /* last resort: var state in HBM too, biggest slabs */
-    Layout L = plan_layout(e->shape, pd.tier_nv, pd.kind, pd.attempt, e->cfg_arena, e->cfg_wpool);
-    size_t spw = 0;
-    kernel_fn fn = pick_kernel(pd.tier_nv, count, pd.kind, spw);
-    /* launch shape: as many resident warps per SM as shared memory and registers allow */
+__global__ void init_qctl(u32 *qctl, u32 total) {
+    if (threadIdx.x < QC_WORDS) qctl[threadIdx.x] = threadIdx.x == QC_TOTAL ? total : 0u;
+}
+
+/* launch shape of one persistent kernel: as many resident warps per SM as shared memory and registers allow */
+struct LaunchShape { int wpb = 1, bps = 1; u32 grid = 0; size_t smem = 0; };
+static int shape_kernel(b200sat_engine *e, kernel_fn fn, size_t spw, u32 n_items, LaunchShape &out) {
     int best_wpb = 1, best_bps = 1, best_warps = 0;
     const int cand[] = {1, 2};
     for (int ci = 0; ci < 2; ci++) {
@@ -405,57 +443,114 @@ static int launch_attempt(b200sat_engine *e) {
     }
     if (best_warps == 0) return set_err(B200SAT_E_CUDA, "kernel does not fit on the device");
     u32 grid = (u32)(e->num_sms * best_bps);
-    u32 need_blocks = (pd.n_work + best_wpb - 1) / best_wpb;
+    u32 need_blocks = (n_items + best_wpb - 1) / best_wpb;
     if (grid > need_blocks) grid = need_blocks;
-    u64 warps_total = (u64)grid * best_wpb;
-    if (warps_total * L.slab_bytes > e->cap_slabs) { /* bound the slab memory: at most ~60% of free HBM */
-        size_t free_b = 0, total_b = 0;
-        CK(cudaMemGetInfo(&free_b, &total_b));
-        size_t budget = (size_t)((double)(free_b + e->cap_slabs) * 0.6);
-        if (warps_total * L.slab_bytes > budget) {
-            u64 fit = budget / L.slab_bytes;
-            if (fit == 0) return set_err(B200SAT_E_MEM, "an instance needs a slab larger than the free device memory");
-            if (fit < (u64)best_wpb) best_wpb = 1;
-            grid = (u32)std::max<u64>(1, fit / best_wpb);
-            warps_total = (u64)grid * best_wpb;
-        }
-    }
-    size_t smem = spw * best_wpb;
-    CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (grid == 0) grid = 1;
+    out.wpb = best_wpb; out.bps = best_bps; out.grid = grid; out.smem = spw * best_wpb;
+    CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out.smem));
     {   /* give shared memory only what the resident blocks need; the rest of the 256 KB stays L1 for the slab traffic */
         int per_sm = (int)((grid + e->num_sms - 1) / e->num_sms);
         if (per_sm > best_bps) per_sm = best_bps;
-        size_t need = (size_t)per_sm * (smem + 1024);
+        size_t need = (size_t)per_sm * (out.smem + 1024);
         int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
         if (pct > 100) pct = 100;
         cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
-    if (warps_total * L.slab_bytes > e->cap_slabs) {
-        CK(cudaStreamSynchronize(stream)); /* the old slabs may still be in use by an earlier launch on this stream */
-        if ((rc = ensure(e->d_slabs, e->cap_slabs, (size_t)(warps_total * L.slab_bytes)))) return rc;
-    }
-    CK(cudaMemsetAsync(e->d_queue, 0, 8, stream));
-    KParams P;
+    return 0;
+}
+
+static void fill_params(b200sat_engine *e, KParams &P, const Layout &L) {
+    b200sat_engine::Pending &pd = e->pend;
     memset(&P, 0, sizeof P);
     P.inst_clause_off = e->d_ioff; P.clause_off = e->d_coff; P.lits = e->d_lits;
-    P.work = pd.work; P.n_work = pd.n_work; P.queue = e->d_queue;
+    P.work = pd.work; P.queue = e->d_queue;
     P.results = e->d_results; P.models = e->d_models; P.model_stride = e->model_stride;
     P.slabs = e->d_slabs; P.L = L; P.st = pd.st; P.kind = pd.kind; P.flags = pd.flags; P.attempt = pd.attempt + 1;
     P.portfolio = pd.portfolio; P.replica_base = pd.replica_base; P.share = pd.share;
     P.n_rings = e->n_rings; P.my_ring = e->my_ring; P.ring_words = e->ring_words;
     for (u32 r = 0; r < 8; r++) P.rings[r] = e->rings[r];
     P.replica_settings = e->d_replica_settings;
+    P.qctl = e->d_queue + 32; P.ring = e->d_ring; P.slice_conflicts = e->slice_conflicts;
+    P.conflict_budget = e->conflict_budget; P.propagation_budget = e->propagation_budget;
+    P.interrupt = e->d_interrupt;
+    P.import_cap = e->import_cap;
+}
+
+/* enqueue one attempt on the pending stream, no host sync: per chunk of resident items the ingest kernel (every
+ * item's state ends parked in its own slab), then the search kernel (device work ring, conflict slices), then the
+ * failure collection + count read-back */
+static int launch_attempt(b200sat_engine *e) {
+    b200sat_engine::Pending &pd = e->pend;
+    cudaStream_t stream = pd.stream;
+    int rc;
+    const bool count = (pd.flags & B200SAT_F_COUNT_TRAFFIC) != 0;
+    if (pd.attempt == 3) pd.tier_nv = 0; /* last resort: var state in HBM too, biggest slabs */
+    size_t spw_i = 0, spw_s = 0, save = 0, save2 = 0;
+    kernel_fn fn_i = pick_ingest(pd.tier_nv, count, pd.kind, spw_i, save);
+    kernel_fn fn_s = pick_search(pd.tier_nv, count, pd.portfolio != 0, spw_s, save2);
+    Layout L = plan_layout(e->shape, pd.tier_nv, pd.kind, pd.attempt, e->cfg_arena, e->cfg_wpool, (u32)save);
+    /* resident items per chunk: every item owns a slab; bounded by ~60% of the free HBM */
+    u64 slots = pd.n_work;
+    if (slots * L.slab_bytes > e->cap_slabs) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = (size_t)((double)(free_b + e->cap_slabs) * 0.6);
+        if (e->cfg_slab_budget && e->cfg_slab_budget < budget) budget = e->cfg_slab_budget;
+        if (slots * L.slab_bytes > budget) {
+            slots = budget / L.slab_bytes;
+            if (slots == 0) return set_err(B200SAT_E_MEM, "an instance needs a slab larger than the free device memory");
+        }
+    }
+    LaunchShape shi, shs;
+    if ((rc = shape_kernel(e, fn_i, spw_i, (u32)slots, shi))) return rc;
+    if ((rc = shape_kernel(e, fn_s, spw_s, (u32)slots, shs))) return rc;
+    if (slots * L.slab_bytes > e->cap_slabs) {
+        CK(cudaStreamSynchronize(stream)); /* the old slabs may still be in use by an earlier launch on this stream */
+        if ((rc = ensure(e->d_slabs, e->cap_slabs, (size_t)(slots * L.slab_bytes)))) return rc;
+    }
+    u32 ring_cap = 64;
+    while (ring_cap < 2 * slots) ring_cap <<= 1;
+    if (ring_cap > e->cap_ring) {
+        CK(cudaStreamSynchronize(stream));
+        if ((rc = ensure(e->d_ring, e->cap_ring, (size_t)ring_cap))) return rc;
+    }
+    KParams P;
+    fill_params(e, P, L);
+    P.ring_mask = ring_cap - 1;
     CK(cudaEventRecord(e->ev0, stream));
-    fn<<<grid, best_wpb * 32, smem, stream>>>(P);
-    CK(cudaGetLastError());
+    float dummy = 0.f; (void)dummy;
+    bool first_chunk = true;
+    for (u64 base = 0; base < pd.n_work; base += slots) {
+        const u32 n_chunk = (u32)std::min<u64>(slots, pd.n_work - base);
+        P.chunk_base = (u32)base; P.n_work = n_chunk;
+        CK(cudaMemsetAsync(e->d_queue, 0, 4, stream));
+        CK(cudaMemsetAsync(e->d_ring, 0, (size_t)ring_cap * 8, stream));
+        init_qctl<<<1, 32, 0, stream>>>(P.qctl, n_chunk);
+        fn_i<<<shi.grid, shi.wpb * 32, shi.smem, stream>>>(P);
+        CK(cudaGetLastError());
+        if (!(pd.flags & B200SAT_F_NO_SOLVE)) {
+            if (first_chunk) CK(cudaEventRecord(e->ev2, stream));
+            fn_s<<<shs.grid, shs.wpb * 32, shs.smem, stream>>>(P);
+            CK(cudaGetLastError());
+            if (first_chunk) CK(cudaEventRecord(e->ev3, stream));
+            e->info.launches += 1;
+        }
+        e->info.launches += 1;
+        first_chunk = false;
+    }
     CK(cudaEventRecord(e->ev1, stream));
+    pd.searched = !(pd.flags & B200SAT_F_NO_SOLVE);
     pd.next_list = e->d_work[pd.attempt & 1];
-    collect_failed<<<(pd.n_work + 255) / 256, 256, 0, stream>>>(e->d_results, pd.work, pd.n_work, pd.next_list, e->d_queue + 1);
+    CK(cudaMemsetAsync(e->d_queue + 1, 0, 4, stream));
+    collect_failed<<<(pd.n_work + 255) / 256, 256, 0, stream>>>(e->d_results, pd.work, pd.n_work, pd.portfolio != 0, pd.next_list, e->d_queue + 1);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(e->h_pinned, e->d_queue + 1, 4, cudaMemcpyDeviceToHost, stream));
-    e->info.grid = grid; e->info.block = best_wpb * 32; e->info.smem_bytes = (u32)smem;
-    e->info.warps_total = (u32)warps_total; e->info.tier = L.tier; e->info.slab_bytes = L.slab_bytes;
-    e->info.launches += 1;
+    CK(cudaMemcpyAsync(e->h_pinned + 32, e->d_queue + 32, QC_WORDS * 4, cudaMemcpyDeviceToHost, stream));
+    e->info.grid = shs.grid; e->info.block = shs.wpb * 32; e->info.smem_bytes = (u32)shs.smem;
+    e->info.warps_total = shs.grid * shs.wpb; e->info.tier = L.tier; e->info.slab_bytes = L.slab_bytes;
+    e->info.resident_items = (u32)slots;
+    e->resident_items = (pd.n_work <= slots && pd.work == nullptr) ? pd.n_work : 0;
+    e->resident_L = L; e->resident_tier_nv = pd.tier_nv;
     return 0;
 }
 
@@ -468,11 +563,14 @@ extern "C" int b200sat_engine_solve_async(b200sat_engine *e, const b200sat_setti
     if (e->pend.active) { rc = b200sat_engine_finish(e); if (rc && rc != B200SAT_E_MEM) return rc; }
     CK(cudaSetDevice(e->device));
     e->info.launches = 0;
-    e->info.last_kernel_ms = 0.f;
-    if (e->n_inst == 0) return 0;
+    e->info.last_kernel_ms = 0.f; e->info.search_ms = 0.f; e->info.suspends = 0;
     b200sat_engine::Pending &pd = e->pend;
-    pd.st = *s; pd.kind = kind; pd.flags = flags; pd.stream = (cudaStream_t)stream_;
-    pd.attempt = 0; pd.n_work = e->n_inst; pd.work = nullptr; pd.total_ms = 0.f; pd.retried = false;
+    pd.stream = (cudaStream_t)stream_;
+    if (e->n_inst == 0) return 0;
+    pd.st = *s; pd.kind = kind; pd.flags = flags;
+    pd.attempt = 0; pd.n_work = e->n_inst; pd.work = nullptr; pd.total_ms = 0.f; pd.search_ms = 0.f; pd.retried = false;
+    /* model rows of instances that end without a model read "undefined" */
+    if (e->d_models) CK(cudaMemsetAsync(e->d_models, 2, (size_t)e->n_inst * e->model_stride, pd.stream));
     pd.portfolio = 0; pd.replica_base = 0; pd.share = 0;
     pd.tier_nv = pick_tier_nv(e->shape.max_vars, e->shape.max_clauses);
     rc = launch_attempt(e);
@@ -491,6 +589,8 @@ extern "C" int b200sat_engine_finish(b200sat_engine *e) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
         pd.total_ms += ms;
+        if (pd.searched) { CK(cudaEventElapsedTime(&ms, e->ev2, e->ev3)); pd.search_ms += ms; }
+        e->info.suspends += e->h_pinned[32 + QC_SUSPENDS];
         u32 left = e->h_pinned[0];
         if (left == 0 || pd.attempt >= 4) { pd.n_work = left; break; }
         pd.retried = true;
@@ -502,6 +602,7 @@ extern "C" int b200sat_engine_finish(b200sat_engine *e) {
     }
     pd.active = false;
     e->info.last_kernel_ms = pd.total_ms;
+    e->info.search_ms = pd.search_ms;
     if (pd.n_work > 0) return set_err(B200SAT_E_MEM, "instances outgrew the largest slab (status in results)");
     return 0;
 }
@@ -843,10 +944,16 @@ extern "C" int b200sat_portfolio_solve(b200sat_engine *e, const b200sat_settings
     if ((rc = ensure(e->d_work[1], e->cap_work1, (size_t)std::max(n_replicas, e->n_inst)))) return rc;
     e->n_replicas = n_replicas;
     e->info.launches = 0;
-    e->info.last_kernel_ms = 0.f;
+    e->info.last_kernel_ms = 0.f; e->info.search_ms = 0.f; e->info.suspends = 0;
     b200sat_engine::Pending &pd = e->pend;
     pd.st = *base; pd.kind = B200SAT_CORE; pd.flags = flags; pd.stream = stream;
-    pd.attempt = 0; pd.n_work = n_replicas; pd.work = nullptr; pd.total_ms = 0.f; pd.retried = false; pd.batch = false;
+    pd.attempt = 0; pd.n_work = n_replicas; pd.work = nullptr; pd.total_ms = 0.f; pd.search_ms = 0.f; pd.retried = false; pd.batch = false;
+    CK(cudaMemsetAsync(e->d_models, 2, (size_t)n_replicas * e->model_stride, stream));
+    /* a ring that still holds the clauses / the done flag of an earlier run would cancel every replica at once or
+     * feed this instance the learnt clauses of another one: the local ring is cleared here.  Multi-GPU callers clear
+     * every ring and synchronise the ranks themselves, then pass B200SAT_PF_KEEP_RING (tools/portfolio_run.py). */
+    if (!(share_flags & B200SAT_PF_KEEP_RING))
+        CK(cudaMemsetAsync(e->rings[e->my_ring], 0, ((size_t)e->ring_words + RING_PAYLOAD) * 4, stream));
     pd.portfolio = n_replicas; pd.replica_base = replica_base; pd.share = share_flags;
     /* the slab is sized for the one instance; BatchShape of a 1-instance batch is that instance */
     pd.tier_nv = pick_tier_nv(e->shape.max_vars, e->shape.max_clauses);
@@ -858,6 +965,9 @@ extern "C" int b200sat_portfolio_solve(b200sat_engine *e, const b200sat_settings
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     e->info.last_kernel_ms = ms;
+    CK(cudaEventElapsedTime(&ms, e->ev2, e->ev3));
+    e->info.search_ms = ms;
+    e->info.suspends = e->h_pinned[32 + QC_SUSPENDS];
     pd.active = false;
     return 0;
 }

@@ -1,21 +1,35 @@
 /*
- * cdcl_kernels.cuh -- the persistent warp-per-instance kernels.  Included by b200sat.cu for
- * the declarations only; each kern_*.cu defines B200SAT_KERNEL_TU_COUNT / _SIMP and gets the
- * kernel templates plus one `b200sat_pick_*` accessor for its COUNT x SIMP combination, so the
- * four combinations compile in parallel.
+ * cdcl_kernels.cuh -- the persistent warp-per-instance kernels (round 2: phase-specialised).
+ *
+ *   ingest_smem<NV,COUNT,SIMP> / ingest_glob<COUNT,SIMP>   add_clause* + preprocess of every work item; the state of an
+ *                                                          item that needs a search is parked in ITS slab and the item
+ *                                                          is pushed on the device work ring
+ *   search_smem<NV,COUNT,PF>  / search_glob<COUNT,PF>      pops items from the ring, resumes them from their slab, runs
+ *                                                          the CDCL search; an item that used up its conflict slice
+ *                                                          while others wait is parked again and re-queued (round-robin)
+ *
+ * The search kernels carry no ingest / simplifier code and (PF = false) no clause-exchange code, so co-resident warps
+ * share one hot loop.  Included by b200sat.cu for the declarations only; each kern_*.cu defines B200SAT_KERNEL_TU_*
+ * and gets the templates plus its `b200sat_pick_*` accessor, so the translation units compile in parallel.
  */
 #ifndef B200SAT_CDCL_KERNELS_CUH
 #define B200SAT_CDCL_KERNELS_CUH
 #include "cdcl_types.h"
 
 typedef void (*kernel_fn)(const b200sat::KParams);
-kernel_fn b200sat_pick_c0s0(int tier_nv, size_t *smem_per_warp);
-kernel_fn b200sat_pick_c1s0(int tier_nv, size_t *smem_per_warp);
-kernel_fn b200sat_pick_c0s1(int tier_nv, size_t *smem_per_warp);
-kernel_fn b200sat_pick_c1s1(int tier_nv, size_t *smem_per_warp);
+/* tier_nv: 128 / 256 / 1024 = shared-memory tier, 0 = global tier.  smem_per_warp: dynamic shared memory one warp
+ * needs; save_bytes: bytes of it that make up the parked var state (same for every kernel of a tier). */
+kernel_fn b200sat_pick_ingest_c0s0(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
+kernel_fn b200sat_pick_ingest_c1s0(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
+kernel_fn b200sat_pick_ingest_c0s1(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
+kernel_fn b200sat_pick_ingest_c1s1(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
+kernel_fn b200sat_pick_search_c0(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
+kernel_fn b200sat_pick_search_c1(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
+kernel_fn b200sat_pick_search_pf(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
 
 #ifdef B200SAT_KERNEL_TU_NAME
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include "cdcl_warp.cuh"
 #if B200SAT_KERNEL_TU_SIMP
 #include "simp_warp.cuh"
@@ -26,60 +40,126 @@ kernel_fn b200sat_pick_c1s1(int tier_nv, size_t *smem_per_warp);
 #endif
 
 namespace b200sat {
-template <bool SIMP, class VT, bool COUNT> __device__ __forceinline__ void warp_work_loop(WarpSolver<VT, COUNT> &S, const KParams &P) {
+
+template <class WS> __device__ __forceinline__ void bind_item(WS &S, const KParams &P, u32 w) {
+    S.slab = P.slabs + (size_t)(w - P.chunk_base) * P.L.slab_bytes;
+    S.res_index = P.work ? P.work[w] : w;
+    S.stp = &P.st;
+    if (P.portfolio) { /* item w = replica w of instance 0 with its own diversified settings */
+        S.res_index = w;
+        S.stp = P.replica_settings + w;
+    }
+}
+
+#if B200SAT_KERNEL_TU_PHASE == 0
+/* ---------------------------------------------------------------- ingest: a static atomic queue over the chunk */
+template <bool SIMP, class WS> __device__ __forceinline__ void ingest_loop(WS &S, const KParams &P) {
     for (;;) {
         u32 w = 0;
         if (S.lane == 0) w = atomicAdd(P.queue, 1u);
         w = __shfl_sync(FULL_MASK, w, 0);
         if (w >= P.n_work) break;
-        u32 inst = P.work ? P.work[w] : w;
-        S.res_index = inst;
-        if (P.portfolio) { /* replica w of instance 0 with its own diversified settings */
-            S.res_index = w;
-            S.stp = P.replica_settings + w;
-            inst = 0;
-        }
+        w += P.chunk_base;
+        bind_item(S, P, w);
+        if constexpr (WS::VT_GLOBAL) S.V.bind(S.slab + P.L.off_vars, P.L.nv_cap);
+        const u32 inst = P.portfolio ? 0u : S.res_index;
+        bool runnable;
 #if B200SAT_KERNEL_TU_SIMP
-        if (SIMP) { solve_simp(S, inst); continue; }
+        if (SIMP) runnable = ingest_simp(S, inst); else
 #endif
-        S.solve_core(inst);
+        runnable = S.ingest_core(inst);
+        if (runnable && !(P.flags & B200SAT_F_NO_SOLVE)) S.ring_push(w); else S.count_done();
     }
 }
-
-/* <= 64 threads per block and >= 16 blocks per SM: 64 registers per thread, 32 resident warps per SM */
-template <int NV, bool COUNT, bool SIMP> __global__ void __launch_bounds__(64, B200SAT_MINBLOCKS) cdcl_warp_smem(const __grid_constant__ KParams P) {
+template <int NV, bool COUNT, bool SIMP> __global__ void __launch_bounds__(64, 8) ingest_smem(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u32 wpb = blockDim.x >> 5;
     WarpSolver<VarsS<NV, SIMP>, COUNT> S(P, lane);
     S.V.s = reinterpret_cast<SmemVars<NV, SIMP> *>(smem_raw) + warp;
-    S.slab = P.slabs + (size_t)(blockIdx.x * wpb + warp) * P.L.slab_bytes;
-    warp_work_loop<SIMP>(S, P);
+    ingest_loop<SIMP>(S, P);
 }
-
-template <bool COUNT, bool SIMP> __global__ void __launch_bounds__(64, 8) cdcl_warp_glob(const __grid_constant__ KParams P) {
+template <bool COUNT, bool SIMP> __global__ void __launch_bounds__(64, 8) ingest_glob(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u32 wpb = blockDim.x >> 5;
     WarpSolver<VarsG, COUNT> S(P, lane);
     S.V.s = reinterpret_cast<SmemSmall *>(smem_raw) + warp;
-    S.slab = P.slabs + (size_t)(blockIdx.x * wpb + warp) * P.L.slab_bytes;
-    S.V.bind(S.slab + P.L.off_vars, P.L.nv_cap);
-    warp_work_loop<SIMP>(S, P);
+    ingest_loop<SIMP>(S, P);
 }
-
+#else
+/* ---------------------------------------------------------------- search: pops the work ring until every item is done */
+template <class WS> __device__ __forceinline__ void search_loop_ring(WS &S, const KParams &P) {
+    for (;;) {
+        u32 w = 0xFFFFFFFFu;
+        if (S.lane == 0) {
+            for (;;) {
+                const u32 h = WS::ld_vol(P.qctl + QC_HEAD), t = WS::ld_vol(P.qctl + QC_TAIL);
+                if ((i32)(t - h) > 0) {
+                    if (atomicCAS(P.qctl + QC_HEAD, h, h + 1) != h) continue;
+                    volatile unsigned long long *slot = P.ring + (h & P.ring_mask);
+                    unsigned long long e;
+                    do { e = *slot; } while ((u32)(e >> 32) != h + 1);
+                    w = (u32)e;
+                    break;
+                }
+                if (WS::ld_vol(P.qctl + QC_DONE) >= WS::ld_vol(P.qctl + QC_TOTAL)) break;
+                __nanosleep(1000);
+            }
+            __threadfence(); /* acquire: also drops this SM's stale L1 lines of the slab (CCTL.IVALL) */
+        }
+        w = __shfl_sync(FULL_MASK, w, 0);
+        if (w == 0xFFFFFFFFu) break;
+        bind_item(S, P, w);
+        if constexpr (WS::VT_GLOBAL) S.V.bind(S.slab + P.L.off_vars, P.L.nv_cap);
+        S.load_state();
+        const u32 r = S.run_search();
+        if (r == WS::SR_SUSPEND) {
+            S.save_state();
+            if (S.lane == 0) atomicAdd(P.qctl + QC_SUSPENDS, 1u);
+            S.ring_push(w);
+            continue;
+        }
+        S.finish_search(r, P.kind == B200SAT_SIMP);
+        S.count_done();
+    }
+}
+template <int NV, bool COUNT, bool PF> __global__ void __launch_bounds__(64, B200SAT_MINBLOCKS) search_smem(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSolver<VarsS<NV, false>, COUNT, PF> S(P, lane);
+    S.V.s = reinterpret_cast<SmemVars<NV, false> *>(smem_raw) + warp;
+    search_loop_ring(S, P);
+}
+template <bool COUNT, bool PF> __global__ void __launch_bounds__(64, 8) search_glob(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSolver<VarsG, COUNT, PF> S(P, lane);
+    S.V.s = reinterpret_cast<SmemSmall *>(smem_raw) + warp;
+    search_loop_ring(S, P);
+}
+#endif
 
 } // namespace b200sat
 
-kernel_fn B200SAT_KERNEL_TU_NAME(int tier_nv, size_t *spw) {
+kernel_fn B200SAT_KERNEL_TU_NAME(int tier_nv, size_t *spw, size_t *save) {
     using namespace b200sat;
-    constexpr bool C = B200SAT_KERNEL_TU_COUNT != 0, Sp = B200SAT_KERNEL_TU_SIMP != 0;
+    constexpr bool C = B200SAT_KERNEL_TU_COUNT != 0;
+#if B200SAT_KERNEL_TU_PHASE == 0
+    constexpr bool Sp = B200SAT_KERNEL_TU_SIMP != 0;
     switch (tier_nv) {
-    case 128: *spw = sizeof(SmemVars<128, Sp>); return cdcl_warp_smem<128, C, Sp>;
-    case 256: *spw = sizeof(SmemVars<256, Sp>); return cdcl_warp_smem<256, C, Sp>;
-    case 1024: *spw = sizeof(SmemVars<1024, Sp>); return cdcl_warp_smem<1024, C, Sp>;
-    default: *spw = sizeof(SmemSmall); return cdcl_warp_glob<C, Sp>;
+    case 128: *spw = sizeof(SmemVars<128, Sp>); *save = SmemSave<128>::BYTES; return ingest_smem<128, C, Sp>;
+    case 256: *spw = sizeof(SmemVars<256, Sp>); *save = SmemSave<256>::BYTES; return ingest_smem<256, C, Sp>;
+    case 1024: *spw = sizeof(SmemVars<1024, Sp>); *save = SmemSave<1024>::BYTES; return ingest_smem<1024, C, Sp>;
+    default: *spw = sizeof(SmemSmall); *save = sizeof(SmemSmall); return ingest_glob<C, Sp>;
     }
+#else
+    constexpr bool Pf = B200SAT_KERNEL_TU_PF != 0;
+    switch (tier_nv) {
+    case 128: *spw = sizeof(SmemVars<128, false>); *save = SmemSave<128>::BYTES; return search_smem<128, C, Pf>;
+    case 256: *spw = sizeof(SmemVars<256, false>); *save = SmemSave<256>::BYTES; return search_smem<256, C, Pf>;
+    case 1024: *spw = sizeof(SmemVars<1024, false>); *save = SmemSave<1024>::BYTES; return search_smem<1024, C, Pf>;
+    default: *spw = sizeof(SmemSmall); *save = sizeof(SmemSmall); return search_glob<C, Pf>;
+    }
+#endif
 }
 #endif
 #endif

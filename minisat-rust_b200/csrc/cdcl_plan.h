@@ -32,7 +32,7 @@ static inline u32 sat_u32(u64 x) { return x > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32
 
 /* attempt 0 is the first try; every retry multiplies the growable regions by 4 */
 static inline Layout plan_layout(const BatchShape &sh, int tier_nv, int kind, u32 attempt,
-                                 u64 arena_words_override, u64 wpool_override) {
+                                 u64 arena_words_override, u64 wpool_override, u32 save_bytes = 0) {
     Layout L;
     memset(&L, 0, sizeof L);
     const u64 nv = sh.max_vars ? sh.max_vars : 1;
@@ -57,6 +57,7 @@ static inline Layout plan_layout(const BatchShape &sh, int tier_nv, int kind, u3
         L.simp_lits = sat_u32((sh.max_lits + 64) * grow);
         L.simp_cap = simp_layout(L.nv_cap, L.clauses_cap, L.simp_lits, L.tmp_cap).total;
     }
+    L.save_bytes = save_bytes;
     layout_finalize(L);
     return L;
 }

@@ -49,6 +49,8 @@ struct Layout {
     u32 tier;         /* 0: var state in shared memory, 1: in the slab      */
     u64 off_arena[2], off_wpool[2], off_learnts, off_clauses, off_ol, off_tc, off_stk, off_tmp, off_vars,
         off_simp;
+    u64 off_save;     /* parked copy of the shared-memory var state of a suspended instance */
+    u32 save_bytes;   /* = sizeof(SmemVars<NV>) of the tier (sizeof(SmemSmall) for the global tier) */
     u64 slab_bytes;
 };
 
@@ -78,6 +80,7 @@ static inline void layout_finalize(Layout &L) {
     L.off_tmp = o; o += layout_align(4ull * L.tmp_cap);
     L.off_vars = o; if (L.tier == 1) o += layout_vars_bytes(L.nv_cap);
     L.off_simp = o; o += layout_align(4ull * L.simp_cap);
+    L.off_save = o; o += layout_align(L.save_bytes);
     L.slab_bytes = layout_align(o);
 }
 
@@ -139,7 +142,21 @@ struct KParams {
     u32 ring_words;           /* payload capacity of one ring                                          */
     u32 *rings[8];
     const b200sat_settings *replica_settings; /* [portfolio] diversified settings                      */
+    /* instance-resident scheduling (round 2): every work item owns slab `w - chunk_base`; a device work ring hands
+     * runnable items to warps; an item that used up its conflict slice while others wait is parked and re-queued */
+    u32 chunk_base;           /* first work index of the chunk the slabs hold                          */
+    u32 *qctl;                /* [QC_HEAD, QC_TAIL, QC_DONE, QC_TOTAL, ...] work-ring control words     */
+    unsigned long long *ring; /* work ring: (ticket + 1) << 32 | work index                            */
+    u32 ring_mask;            /* ring capacity - 1 (power of two >= 2 * items)                         */
+    u32 slice_conflicts;      /* conflicts an instance may run before it yields to waiting ones (0 = never) */
+    long long conflict_budget, propagation_budget; /* budget.rs:5-34; < 0 = none                       */
+    const volatile int *interrupt;                 /* device-visible async interrupt flag or NULL      */
+    u32 import_cap;           /* portfolio: clauses one replica imports per restart boundary (0 = no cap) */
+    u32 ring_epoch;           /* portfolio: stamps ring entries of this run                             */
 };
+enum : u32 { QC_HEAD = 0, QC_TAIL = 1, QC_DONE = 2, QC_TOTAL = 3, QC_SUSPENDS = 4, QC_WORDS = 8 };
+/* life cycle of a resident instance (Scal::phase) */
+enum : u32 { PH_NEW = 0, PH_READY = 1, PH_SEARCH = 2, PH_DONE = 3 };
 
 enum : u32 { PF_SHARE = 1, PF_IGNORE_DONE = 2, PF_SHARE_LBD2 = 4 };
 /* ring header words */

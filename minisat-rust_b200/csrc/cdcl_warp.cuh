@@ -36,6 +36,7 @@
 #include "simt_emu.h"
 #else
 #include <cuda_runtime.h>
+#include <stddef.h>
 #define DEV __device__ __forceinline__
 #define DEVNI __device__ __noinline__
 #endif
@@ -53,6 +54,14 @@ struct Scal {
     u32 simp_db_assigns, simp_db_assigns_set, status, dec_vars, heap_n, cur_arena, cur_wpool, eliminated_vars;
     u32 remove_satisfied, extra_clause_field, elim_n;
     u32 ring_cursor[8], exported, imported, simp_cur_opool;
+    /* ---- resident-instance state (round 2): what a warp needs to park an instance and any warp to resume it */
+    u32 phase;                                   /* PH_* life cycle                                              */
+    u32 sv_nvars, sv_trail_n, sv_qhead, sv_nlevels; /* the solver's register state while parked                   */
+    u32 curr_restarts;                           /* search.rs:413 loop counter                                   */
+    u32 n_ingest, n_pre, pre_ok;                 /* clause counts for the result record                          */
+    u32 in_loop;                                 /* 1: parked inside a search_loop (confl_limit valid)           */
+    u64 confl_limit;                             /* conflict count that ends the current search_loop             */
+    double progress;                             /* progress estimate of the last Interrupted return             */
 };
 
 /* ------------------------------------------------------------------ var-state tiers */
@@ -81,12 +90,19 @@ template <int NV, bool SIMP = false> struct SmemVars {
     u32 bl[32];
     SimpSmem<NV, SIMP> simp;
 };
+/* bytes of a warp's shared-memory block that make up an instance's parked state: everything in front of the
+ * simplifier's scratch (which is dead once the ingest phase is over) */
+template <int NV> struct SmemSave {
+    typedef SmemVars<NV, false> SV_;
+    static const u32 BYTES = (u32)((offsetof(SV_, simp) + 7) & ~(size_t)7);
+};
 
 template <int NV, bool SIMP = false> struct VarsS {
     typedef u16 idx_t;
     static const u32 ABSENT = 0xFFFFu;
     static const u32 MAXLEN = 0xFFF0u;
     static const bool SIMP_SMEM = SIMP;
+    static const bool GLOBAL = false;
     SmemVars<NV, SIMP> *s;
     DEV double *act() const { return s->act; }
     DEV u32 *reason() const { return s->reason; }
@@ -115,6 +131,7 @@ struct VarsG {
     static const u32 ABSENT = 0xFFFFFFFFu;
     static const u32 MAXLEN = 0x3FFFFFF0u;
     static const bool SIMP_SMEM = false;
+    static const bool GLOBAL = true;
     DEV void *simp_smem() const { return nullptr; }
     SmemSmall *s;
     double *act_;
@@ -184,11 +201,12 @@ enum : u32 { OUT_NONE = 0, OUT_KEEPW = 1, OUT_KEEPCW = 2, OUT_MOVE = 3, OUT_UNIT
 enum : u32 { LR_RESTART = 0, LR_UNSAT = 1, LR_SAT = 2, LR_ABORT = 3 };
 
 /* ================================================================== the solver */
-template <class VT, bool COUNT> struct WarpSolver {
+template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
     typedef typename VT::idx_t idx_t;
     static const u32 VT_ABSENT = VT::ABSENT;
     static const u32 VT_MAXLEN = VT::MAXLEN;
     static const bool VT_SIMP_SMEM = VT::SIMP_SMEM;
+    static const bool VT_GLOBAL = VT::GLOBAL;
     VT V;
     const KParams &P;
     const b200sat_settings *stp;   /* P.st, or this replica's diversified settings in portfolio mode */
@@ -1240,13 +1258,13 @@ template <class VT, bool COUNT> struct WarpSolver {
      * replicas -- on this GPU and, through peer-mapped pointers over NVLink, on the other GPUs -- appended. */
     DEV static u32 ld_vol(const u32 *p) { return *(const volatile u32 *)p; }
     DEV bool cancelled() {
-        if (!P.portfolio || (P.share & PF_IGNORE_DONE)) return false;
+        if (!PF || (P.share & PF_IGNORE_DONE)) return false;
         u32 v = 0; /* one lane reads, all lanes agree: another GPU may raise the flag at any moment */
         if (lane == 0) v = ld_vol(P.rings[P.my_ring] + RING_DONE);
         return bcast(v) != 0;
     }
     DEV void announce_done() {
-        if (!P.portfolio) return;
+        if (!PF) return;
         if (lane == 0) {
             __threadfence_system();
             for (u32 r = 0; r < P.n_rings; r++) atomicCAS(P.rings[r] + RING_DONE, 0u, 1u + P.replica_base + res_index);
@@ -1321,59 +1339,6 @@ template <class VT, bool COUNT> struct WarpSolver {
         return true;
     }
 
-    /* -------------------------------------------------------------- conflict handling: search.rs:263-304,503-517 */
-    /* returns false on a ground-level conflict (UNSAT) or on abort (check failed()) */
-    DEV bool propagate_learn_backtrack() {
-        for (;;) {
-            u32 confl = propagate();
-            if (failed()) return false;
-            if (confl == CREF_UNDEF) return true;
-            if (lane == 0) sc().conflicts++;
-            if (nlevels == 1) { __syncwarp(); return false; }
-            u32 bt;
-            u32 n = analyze(confl, bt);
-            if (failed()) return false;
-            if (P.portfolio) {
-                if (P.share & PF_SHARE) export_clause(n);
-                if (cancelled()) { fail(ST_CANCELLED); return false; }
-            }
-            cancel_until(bt);
-            u32 reason = CREF_UNDEF;
-            const u32 *out = ol();
-            u32 asserting = out[0];
-            if (n > 1) {
-                if (sc().n_learnts >= P.L.learnts_cap) { fail(ST_MEM_ARENA); return false; }
-                reason = alloc_clause(n, H_LEARNT | H_EXTRA);
-                if (reason == CREF_UNDEF) return false;
-                for (u32 i = lane; i < n; i += 32) arena[reason + 1 + i] = out[i];
-                if (lane == 0) {
-                    arena[reason + 1 + n] = f2u(0.0f);
-                    learnts()[sc().n_learnts] = reason;
-                    sc().n_learnts++;
-                    sc().num_learnts++;
-                    sc().learnts_literals += n;
-                    if (COUNT) sc().traffic[7] += 1 + n + 4;
-                }
-                __syncwarp();
-                bump_cla(reason, n);
-            }
-            if (lane == 0) {
-                sc().var_inc *= sc().inv_var_decay;   /* decision_heuristic.rs:142-144 */
-                sc().cla_inc *= sc().inv_cla_decay;   /* clause_db.rs:145-147 */
-                /* LearningGuard::bump search.rs:96-110 */
-                sc().size_adjust_cnt -= 1;
-                if (sc().size_adjust_cnt == 0) {
-                    sc().size_adjust_confl *= st().size_adjust_inc;
-                    sc().size_adjust_cnt = (i32)sc().size_adjust_confl;
-                    sc().max_learnts *= st().size_inc;
-                }
-            }
-            __syncwarp();
-            assign_lit(asserting, reason);
-            if (reason != CREF_UNDEF && !attach(reason)) return false;
-        }
-    }
-
     DEV static double powi(double b, i32 e) {
         double r = 1.0;
         while (e > 0) { if (e & 1) r *= b; b *= b; e >>= 1; }
@@ -1387,53 +1352,485 @@ template <class VT, bool COUNT> struct WarpSolver {
         return powi(y, seq);
     }
 
-    /* search.rs:452-501 */
-    DEV u32 search_loop(u64 nof_conflicts) {
-        if (lane == 0) sc().starts++;
-        __syncwarp();
-        const u64 confl_limit = sc().conflicts + nof_conflicts;
-        for (;;) {
-            if (!propagate_learn_backtrack()) return failed() ? LR_ABORT : LR_UNSAT;
-            if (sc().conflicts >= confl_limit) { cancel_until(GROUND); return LR_RESTART; }
-            try_simplify();
-            if ((double)sc().n_learnts >= sc().max_learnts + (double)trail_n) {
-                reduce_db();
-                if (failed()) return LR_ABORT;
-                try_garbage_collect();
+    /* ============================================================== round-2 search path
+     * One flat, resumable loop (search.rs:409-517 flattened): the instance's whole state lives in its slab plus the
+     * shared-memory var block, so a warp can park it at a conflict-free point and any warp can pick it up again.
+     * The hot functions below are written for instruction economy (ncu: the round-1 BCP spent ~360 warp
+     * instructions per dequeued literal); semantics are those of the functions they replace. */
+
+    /* BCP, watches.rs:64-152 -- same ordered-commit scheme as propagate() (see the comment there), leaner:
+     * register copies of the queue cursors, one 32-watcher chunk is the common case, moved watchers are appended
+     * with one __match_any_sync instead of a loop over target lists, and list growth / pool compaction is the
+     * slow path. */
+    DEV u32 propagate2() {
+        u32 confl = CREF_UNDEF;
+        const u32 lt = lanemask_lt(lane);
+        u32 qh = qhead, tn = trail_n;
+        const u32 q0 = qh;
+        u32 *const ar = arena;
+        u32 t_vis = 0, t_kept = 0, t_deref = 0, t_tail = 0, t_moves = 0, t_impl = 0;
+        while (qh < tn) {
+            const u32 p = V.trail()[qh];
+            qh++;
+            const u32 not_p = p ^ 1;
+            const u32 word = V.wstart()[p];
+            const u32 n = V.wlen()[p];
+            const bool dirty = (word & W_DIRTY) != 0;
+            uint2 *ws = wpool + (word >> W_SHIFT);
+            u32 j = 0, i = 0;
+            for (; i < n; i += 32) {
+                const u32 idx = i + lane;
+                const bool valid = idx < n;
+                uint2 w = make_uint2(0, 0);
+                if (valid) w = ws[idx];
+                uint4 hd = make_uint4(0, 0, 0, 0);
+                /* a blocker that is true now stays true for the whole call: such lanes never need their clause */
+                const bool need = valid && (dirty || !is_true(w.y));
+                if (need) hd = ld4(ar + w.x);
+                const bool live = valid && !(dirty && (hd.x & H_DELETED));
+                u32 kf = 2, lbase = 0;
+                for (;;) {
+                    const bool pend = live && lane >= lbase;
+                    u32 out = OUT_NONE, first = 0, lk = 0;
+                    bool scan = false;
+                    if (pend) {
+                        out = OUT_KEEPW;
+                        if (!is_true(w.y)) {
+                            first = (hd.y == not_p) ? hd.z : hd.y;
+                            const u32 fv = lval(first);
+                            out = OUT_KEEPCW;
+                            if (fv != 1) {
+                                out = (fv == 0) ? OUT_CONFL : OUT_UNIT;
+                                if (hd.x >= (3u << H_SHIFT)) {
+                                    if (kf == 2 && !is_false(hd.w)) { lk = hd.w; out = OUT_MOVE; }
+                                    else scan = hd.x >= (4u << H_SHIFT);
+                                }
+                            }
+                        }
+                    }
+                    if (__ballot_sync(FULL_MASK, scan)) {
+                        /* clauses longer than three literals whose third literal is false: 128-bit tail scan */
+                        if (scan) {
+                            const u32 len = hd.x >> H_SHIFT;
+                            if (kf == 2) kf = 3;
+                            while (out != OUT_MOVE && kf < len) {
+                                const u32 gb = (kf + 1) & ~3u;
+                                const uint4 q = ld4(ar + w.x + gb);
+                                const u32 qs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                                for (u32 t = 0; t < 4; t++) {
+                                    const u32 k2 = gb + t - 1;
+                                    if (out != OUT_MOVE && k2 >= kf && k2 < len && !is_false(qs[t])) { lk = qs[t]; kf = k2; out = OUT_MOVE; }
+                                }
+                                if (out != OUT_MOVE) kf = gb + 3;
+                            }
+                        }
+                    }
+                    const u32 umask0 = __ballot_sync(FULL_MASK, out >= OUT_UNIT);
+                    u32 stop = 32, cfl_lane = 32;
+                    if (umask0) {
+                        const u32 cmask = __ballot_sync(FULL_MASK, out == OUT_CONFL);
+                        u32 umask = umask0;
+                        do {
+                            const u32 u = (u32)__ffs(umask) - 1;
+                            if (u >= stop) break;
+                            umask &= umask - 1;
+                            if ((cmask >> u) & 1) { cfl_lane = u; stop = u + 1; break; }
+                            const u32 xv = __shfl_sync(FULL_MASK, first, u) >> 1;
+                            const bool aff = pend && lane > u && out != OUT_KEEPW &&
+                                             ((w.y >> 1) == xv || (first >> 1) == xv || (out == OUT_MOVE && (lk >> 1) == xv));
+                            const u32 am = __ballot_sync(FULL_MASK, aff);
+                            if (am) { const u32 s2 = (u32)__ffs(am) - 1; if (s2 < stop) stop = s2; }
+                        } while (umask);
+                    }
+                    const bool commit = pend && lane < stop;
+                    const bool mv = commit && out == OUT_MOVE;
+                    const bool keep = commit && !mv;
+                    const u32 keepmask = __ballot_sync(FULL_MASK, keep);
+                    if (keep) ws[j + __popc(keepmask & lt)] = make_uint2(w.x, out == OUT_KEEPW ? w.y : first);
+                    j += __popc(keepmask);
+                    if (commit && out != OUT_KEEPW) {
+                        if (hd.y == not_p || mv) {
+                            ar[w.x + 1] = first;
+                            ar[w.x + 2] = mv ? lk : not_p;
+                        }
+                        if (mv) ar[w.x + 1 + kf] = not_p;
+                    }
+                    /* implications of the committed prefix, in lane order (assignment.rs:104-113) */
+                    if (umask0) {
+                        const bool imp = commit && out == OUT_UNIT;
+                        const u32 impmask = __ballot_sync(FULL_MASK, imp);
+                        if (imp) {
+                            const u32 v = first >> 1;
+                            V.assign()[v] = (u8)((first & 1) ^ 1);
+                            V.level()[v] = (idx_t)nlevels;
+                            V.reason()[v] = w.x;
+                            V.trail()[tn + __popc(impmask & lt)] = (idx_t)first;
+                        }
+                        tn += __popc(impmask);
+                        if (COUNT) t_impl += __popc(impmask);
+                    }
+                    const u32 movemask = __ballot_sync(FULL_MASK, mv);
+                    if (COUNT) {
+                        t_vis += __popc(__ballot_sync(FULL_MASK, commit));
+                        t_kept += __popc(keepmask);
+                        t_deref += __popc(__ballot_sync(FULL_MASK, commit && out != OUT_KEEPW));
+                        u32 tl = 0;
+                        if (commit && out >= OUT_MOVE) tl = mv ? kf - 1 : (hd.x >> H_SHIFT) - 2;
+                        t_tail += warp_sum(tl);
+                        t_moves += __popc(movemask);
+                    }
+                    if (movemask) {
+                        /* ordered parallel append: lanes with the same target list keep their lane order */
+                        const u32 tgt = lk ^ 1;
+                        const u32 peers = __match_any_sync(FULL_MASK, mv ? tgt : (0x80000000u | lane));
+                        u32 tword = 0, tlen = 0;
+                        bool over = false;
+                        if (mv) {
+                            tword = V.wstart()[tgt];
+                            tlen = V.wlen()[tgt];
+                            over = tlen + __popc(peers) > (1u << (tword & W_CAP_MASK));
+                        }
+                        if (__ballot_sync(FULL_MASK, over)) {
+                            qhead = qh; trail_n = tn;
+                            if (!push_watch_multi(movemask, mv, tgt, w.x, first)) return CREF_UNDEF;
+                            ws = wpool + (V.wstart()[p] >> W_SHIFT); /* the pool may have been compacted */
+                        } else { /* every lane has read its list length before the ballot above completed */
+                            if (mv) {
+                                wpool[(tword >> W_SHIFT) + tlen + __popc(peers & lt)] = make_uint2(w.x, first);
+                                if ((peers & lt) == 0) V.wlen()[tgt] = (idx_t)(tlen + __popc(peers));
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (cfl_lane != 32) {
+                        confl = __shfl_sync(FULL_MASK, w.x, cfl_lane);
+                        const bool rem = live && lane >= stop;
+                        const u32 m = __ballot_sync(FULL_MASK, rem);
+                        if (rem) ws[j + __popc(m & lt)] = w;
+                        j += __popc(m);
+                        break;
+                    }
+                    if (stop == 32) break;
+                    lbase = stop;
+                }
+                if (confl != CREF_UNDEF) { i += 32; break; }
             }
-            if (lane == 0) sc().decisions++;
-            u32 next = pick_branch_lit();
-            if (next == LIT_NONE) return LR_SAT;
-            new_decision_level();
-            assign_lit(next, CREF_UNDEF);
+            /* conflict: the rest of the list is copied unchanged (watches.rs:123-137), minus dead watchers */
+            for (; i < n; i += 32) {
+                const u32 idx = i + lane;
+                bool live = idx < n;
+                uint2 w = make_uint2(0, 0);
+                if (live) {
+                    w = ws[idx];
+                    if (dirty) live = (ar[w.x] & H_DELETED) == 0;
+                }
+                const u32 m = __ballot_sync(FULL_MASK, live);
+                if (live) ws[j + __popc(m & lt)] = w;
+                j += __popc(m);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (j != n) V.wlen()[p] = (idx_t)j;
+                if (dirty) V.wstart()[p] = V.wstart()[p] & ~W_DIRTY;
+            }
+            __syncwarp();
+            if (confl != CREF_UNDEF) break;
+        }
+        qhead = qh; trail_n = tn;
+        if (lane == 0) {
+            sc().propagations += qh - q0;
+            if (COUNT) {
+                u64 *t = sc().traffic;
+                t[0] += t_vis; t[1] += t_kept; t[2] += t_deref; t[3] += t_tail; t[4] += t_moves; t[5] += t_impl;
+            }
+        }
+        __syncwarp();
+        return confl;
+    }
+
+    /* -------------------------------------------------------------- park / resume (no reference analogue) */
+    DEV void save_state() {
+        __syncwarp();
+        if (lane == 0) { sc().sv_nvars = nvars; sc().sv_trail_n = trail_n; sc().sv_qhead = qhead; sc().sv_nlevels = nlevels; }
+        __syncwarp();
+        {
+            const uint2 *src = reinterpret_cast<const uint2 *>(V.s);
+            uint2 *dst = reinterpret_cast<uint2 *>(slab + P.L.off_save);
+            for (u32 k = lane; k < P.L.save_bytes / 8; k += 32) dst[k] = src[k];
+        }
+        __syncwarp();
+    }
+    DEV void load_state() {
+        {
+            uint2 *dst = reinterpret_cast<uint2 *>(V.s);
+            const uint2 *src = reinterpret_cast<const uint2 *>(slab + P.L.off_save);
+            for (u32 k = lane; k < P.L.save_bytes / 8; k += 32) dst[k] = src[k];
+        }
+        __syncwarp();
+        nvars = sc().sv_nvars; trail_n = sc().sv_trail_n; qhead = sc().sv_qhead; nlevels = sc().sv_nlevels;
+        arena = arena_half(sc().cur_arena);
+        wpool = wpool_half(sc().cur_wpool);
+        __syncwarp();
+    }
+
+    /* search/util.rs:5-14 progress_estimate(): same operation order, so the f64 result is bit-identical */
+    DEV double progress_estimate() {
+        double progress = 0.0;
+        if (lane == 0) {
+            const double vars = 1.0 / (double)nvars;
+            double factor = vars;
+            for (u32 lv = 0; lv < nlevels; lv++) {
+                const u32 beg = (u32)V.lim()[lv];
+                const u32 end = lv + 1 == nlevels ? trail_n : (u32)V.lim()[lv + 1];
+                progress += factor * (double)(end - beg);
+                factor *= vars;
+            }
+        }
+        return progress;
+    }
+
+    enum : u32 { SR_SAT = 0, SR_UNSAT = 1, SR_ABORT = 2, SR_SUSPEND = 3, SR_INTERRUPTED = 4 };
+
+    /* true while other runnable items wait in the work ring (lane 0 reads, all lanes agree) */
+    DEV bool others_waiting() {
+        u32 v = 0;
+        if (lane == 0 && P.qctl) v = ld_vol(P.qctl + QC_TAIL) > ld_vol(P.qctl + QC_HEAD) ? 1u : 0u;
+        return bcast(v) != 0;
+    }
+    DEV bool interrupted_now() {
+        u32 v = 0;
+        if (lane == 0 && P.interrupt) v = *P.interrupt != 0 ? 1u : 0u;
+        return bcast(v) != 0;
+    }
+
+    /* Searcher::search_internal + search_loop + propagate_learn_backtrack (search.rs:409-517) as one resumable loop.
+     * Entered with phase PH_READY (a new search() call: solves += 1, LearningGuard reset, restart counter 0) or
+     * PH_SEARCH (parked mid-loop by SR_SUSPEND: continues exactly where it stopped, so slicing is trace-neutral). */
+    DEV u32 run_search() {
+        const bool fresh_call = sc().phase == PH_READY;
+        __syncwarp(); /* every lane has read the phase before lane 0 changes it */
+        if (fresh_call) {
+            if (lane == 0) {
+                sc().solves++;
+                double ml = (double)sc().num_clauses * st().size_factor;       /* LearningGuard::reset search.rs:89-94 */
+                double lo = (double)st().min_learnts_lim;
+                sc().max_learnts = ml > lo ? ml : lo;
+                sc().size_adjust_confl = (double)st().size_adjust_start_confl;
+                sc().size_adjust_cnt = st().size_adjust_start_confl;
+                sc().curr_restarts = 0;
+                sc().in_loop = 0;
+                sc().phase = PH_SEARCH;
+            }
+            __syncwarp();
+        }
+        u64 slice_end = P.slice_conflicts ? sc().conflicts + P.slice_conflicts : ~0ull;
+        for (;;) {
+            if (!sc().in_loop) { /* search_loop prologue, search.rs:465-467 */
+                if (PF && (P.share & PF_SHARE) && sc().curr_restarts > 0) {
+                    if (!import_clauses()) return SR_UNSAT;
+                    if (failed()) return SR_ABORT;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    const u32 cr = sc().curr_restarts;
+                    const double base = st().luby_restart ? luby(st().restart_inc, cr) : powi(st().restart_inc, (i32)cr);
+                    sc().starts++;
+                    sc().confl_limit = sc().conflicts + (u64)(base * st().restart_first);
+                    sc().in_loop = 1;
+                }
+                __syncwarp();
+            }
+            const u64 confl_limit = sc().confl_limit;
+            for (;;) {
+                /* propagate_learn_backtrack, search.rs:503-517 + handle_conflict :263-304 */
+                for (;;) {
+                    const u32 confl = propagate2();
+                    if (failed()) return SR_ABORT;
+                    if (confl == CREF_UNDEF) break;
+                    if (lane == 0) sc().conflicts++;
+                    if (nlevels == 1) { __syncwarp(); return SR_UNSAT; }
+                    u32 bt;
+                    const u32 n = analyze(confl, bt);
+                    if (failed()) return SR_ABORT;
+                    if (PF) {
+                        if (P.share & PF_SHARE) export_clause(n);
+                        if (cancelled()) { fail(ST_CANCELLED); return SR_ABORT; }
+                    }
+                    cancel_until(bt);
+                    u32 reason = CREF_UNDEF;
+                    const u32 *out = ol();
+                    const u32 asserting = out[0];
+                    if (n > 1) {
+                        if (sc().n_learnts >= P.L.learnts_cap) { fail(ST_MEM_ARENA); return SR_ABORT; }
+                        reason = alloc_clause(n, H_LEARNT | H_EXTRA);
+                        if (reason == CREF_UNDEF) return SR_ABORT;
+                        for (u32 i = lane; i < n; i += 32) arena[reason + 1 + i] = out[i];
+                        if (lane == 0) {
+                            arena[reason + 1 + n] = f2u(0.0f);
+                            learnts()[sc().n_learnts] = reason;
+                            sc().n_learnts++;
+                            sc().num_learnts++;
+                            sc().learnts_literals += n;
+                            if (COUNT) sc().traffic[7] += 1 + n + 4;
+                        }
+                        __syncwarp();
+                        bump_cla(reason, n);
+                    }
+                    if (lane == 0) {
+                        sc().var_inc *= sc().inv_var_decay;   /* decision_heuristic.rs:142-144 */
+                        sc().cla_inc *= sc().inv_cla_decay;   /* clause_db.rs:145-147 */
+                        sc().size_adjust_cnt -= 1;            /* LearningGuard::bump search.rs:96-110 */
+                        if (sc().size_adjust_cnt == 0) {
+                            sc().size_adjust_confl *= st().size_adjust_inc;
+                            sc().size_adjust_cnt = (i32)sc().size_adjust_confl;
+                            sc().max_learnts *= st().size_inc;
+                        }
+                    }
+                    __syncwarp();
+                    assign_lit(asserting, reason);
+                    if (reason != CREF_UNDEF && !attach(reason)) return SR_ABORT;
+                }
+                const u64 nconf = sc().conflicts;
+                /* Budget::within, search.rs:473-477 (budget.rs:21-25) */
+                if (P.conflict_budget >= 0 || P.propagation_budget >= 0 || P.interrupt) {
+                    const bool out_of = (P.conflict_budget >= 0 && nconf >= (u64)P.conflict_budget) ||
+                                        (P.propagation_budget >= 0 && sc().propagations >= (u64)P.propagation_budget) ||
+                                        interrupted_now();
+                    if (out_of) {
+                        const double pe = progress_estimate();
+                        cancel_until(GROUND);
+                        if (lane == 0) { sc().progress = pe; sc().in_loop = 0; sc().phase = PH_READY; }
+                        __syncwarp();
+                        return SR_INTERRUPTED;
+                    }
+                }
+                if (nconf >= confl_limit) { /* search.rs:479-482 */
+                    cancel_until(GROUND);
+                    if (lane == 0) { sc().curr_restarts++; sc().in_loop = 0; }
+                    __syncwarp();
+                    break;
+                }
+                if (nconf >= slice_end) { /* yield to waiting instances; nothing of the trace depends on this */
+                    if (others_waiting()) return SR_SUSPEND;
+                    slice_end = nconf + P.slice_conflicts;
+                }
+                try_simplify();
+                if ((double)sc().n_learnts >= sc().max_learnts + (double)trail_n) {
+                    reduce_db();
+                    if (failed()) return SR_ABORT;
+                    try_garbage_collect();
+                }
+                if (lane == 0) sc().decisions++;
+                const u32 next = pick_branch_lit();
+                if (next == LIT_NONE) return SR_SAT;
+                new_decision_level();
+                assign_lit(next, CREF_UNDEF);
+            }
         }
     }
-    /* search.rs:409-442; returns LR_SAT / LR_UNSAT / LR_ABORT */
-    DEV u32 search() {
+
+    /* -------------------------------------------------------------- work ring (device side) */
+    /* hand work item `w` (whose state is parked in its slab) to whichever warp pops it next */
+    DEV void ring_push(u32 w) {
         if (lane == 0) {
-            sc().solves++;
-            double ml = (double)sc().num_clauses * st().size_factor;       /* LearningGuard::reset search.rs:89-94 */
-            double lo = (double)st().min_learnts_lim;
-            sc().max_learnts = ml > lo ? ml : lo;
-            sc().size_adjust_confl = (double)st().size_adjust_start_confl;
-            sc().size_adjust_cnt = st().size_adjust_start_confl;
+            __threadfence(); /* the parked state is visible before the ticket is */
+            const u32 s = atomicAdd(P.qctl + QC_TAIL, 1u);
+            *(volatile unsigned long long *)(P.ring + (s & P.ring_mask)) = ((unsigned long long)(s + 1) << 32) | w;
         }
         __syncwarp();
-        u32 curr_restarts = 0;
-        for (;;) {
-            double base = st().luby_restart ? luby(st().restart_inc, curr_restarts) : powi(st().restart_inc, (i32)curr_restarts);
-            u64 ctg = (u64)(base * st().restart_first);
-            u32 r = search_loop(ctg);
-            if (r == LR_RESTART) {
-                curr_restarts++;
-                if (P.portfolio && (P.share & PF_SHARE)) {
-                    if (!import_clauses()) return LR_UNSAT;
-                    if (failed()) return LR_ABORT;
+    }
+    DEV void count_done() {
+        if (lane == 0) { __threadfence(); atomicAdd(P.qctl + QC_DONE, 1u); }
+        __syncwarp();
+    }
+
+    /* elim_clauses.rs:43-63 over the eliminated-clause stack the simplifier left in the slab (lane 0) */
+    DEV void extend_model_from_slab(u8 *model) {
+        if (lane == 0) {
+            const SimpLayout SL = simp_layout(P.L.nv_cap, P.L.clauses_cap, P.L.simp_lits, P.L.tmp_cap);
+            const u32 *base = (const u32 *)(slab + P.L.off_simp);
+            const u32 *elits = base + SL.o_elits, *esizes = base + SL.o_esizes;
+            for (u32 i = sc().elim_n; i-- > 0;) {
+                const u32 head = i > 0 ? esizes[i - 1] : 0, tail = esizes[i];
+                bool sat = false;
+                for (u32 k = head; k < tail; k++) {
+                    const u32 l = elits[k];
+                    const u8 m = model[l >> 1];
+                    if (m != 2 && (m != 0) != ((l & 1) != 0)) { sat = true; break; }
                 }
-                continue;
+                if (!sat) { const u32 l = elits[head]; model[l >> 1] = (l & 1) ? 0 : 1; }
             }
-            return r;
         }
+        __syncwarp();
+    }
+
+    /* result record + model of a finished (or interrupted) search */
+    DEV void finish_search(u32 r, bool simp_kind) {
+        const i32 verdict = (r == SR_SAT) ? B200SAT_SAT : (r == SR_UNSAT) ? B200SAT_UNSAT : B200SAT_INTERRUPTED;
+        __syncwarp();
+        write_result(verdict, sc().n_ingest, sc().n_pre, sc().pre_ok);
+        if (simp_kind && P.models && !failed() && verdict == B200SAT_SAT && st().extend_model && sc().elim_n)
+            extend_model_from_slab(P.models + (size_t)res_index * P.model_stride);
+        if (PF && !failed() && verdict != B200SAT_INTERRUPTED) announce_done();
+        if (r == SR_INTERRUPTED) save_state(); /* SolveRes::Interrupted hands the solver back (sat.rs:24): stays resident */
+        else if (lane == 0) sc().phase = PH_DONE;
+        __syncwarp();
+    }
+
+    /* -------------------------------------------------------------- ingest phase of one instance (CoreSolver):
+     * add_clause* + preprocess (sat/minisat.rs:37-55, lib.rs:47-100); leaves the instance parked (PH_READY) when a
+     * search has to follow, and always writes the result record of the phase */
+    DEV bool ingest_core(u32 inst) {
+        u32 cb, ce;
+        bool ok = setup(inst, cb, ce);
+        u32 n_ingest = 0, n_pre = 0, pre_ok = 1;
+        i32 verdict = B200SAT_INTERRUPTED;
+        bool runnable = false;
+        if (ok) {
+            for (u32 c = cb; c < ce && ok; c++) { /* CoreSolver::add_clause minisat.rs:41-48 */
+                u32 b = P.clause_off[c], e = P.clause_off[c + 1];
+                u32 cr;
+                if (st().use_rcheck) { /* search.rs:343-345 */
+                    bool imp = is_implied(P.lits + b, e - b);
+                    if (failed()) break;
+                    if (imp) continue;
+                }
+                if (add_clause(P.lits + b, e - b, cr) == 0) ok = false;
+                if (failed()) break;
+            }
+            n_ingest = sc().num_clauses;
+            n_pre = n_ingest;
+            if (!failed()) {
+                if (P.flags & B200SAT_F_PREPROCESS) { /* CoreSolver::preprocess minisat.rs:50-55, search.rs:388-395 */
+                    if (ok) {
+                        u32 confl = propagate();
+                        if (confl == CREF_UNDEF) try_simplify(); else ok = false;
+                    }
+                    pre_ok = ok ? 1 : 0;
+                    n_pre = sc().num_clauses;
+                }
+                if (!failed()) {
+                    if (!ok) verdict = B200SAT_UNSAT;
+                    else runnable = true;
+                }
+            }
+        }
+        return park_after_ingest(verdict, n_ingest, n_pre, pre_ok, runnable);
+    }
+    /* common tail of the ingest kernels; returns true when the instance waits for the search kernel */
+    DEV bool park_after_ingest(i32 verdict, u32 n_ingest, u32 n_pre, u32 pre_ok, bool runnable) {
+        __syncwarp();
+        runnable = runnable && !failed();
+        if (lane == 0) {
+            sc().n_ingest = n_ingest; sc().n_pre = n_pre; sc().pre_ok = pre_ok;
+            sc().phase = runnable ? PH_READY : PH_DONE;
+        }
+        __syncwarp();
+        write_result(verdict, n_ingest, n_pre, pre_ok);
+        if (PF && !runnable && !failed()) announce_done();
+        if (runnable) save_state();
+        return runnable;
     }
 
     /* -------------------------------------------------------------- per-instance setup + ingest */
@@ -1463,6 +1860,8 @@ template <class VT, bool COUNT> struct WarpSolver {
             s.remove_satisfied = st().remove_satisfied; s.extra_clause_field = 0; s.elim_n = 0;
             for (int i = 0; i < 8; i++) s.ring_cursor[i] = 0;
             s.exported = 0; s.imported = 0;
+            s.phase = PH_NEW; s.curr_restarts = 0; s.in_loop = 0; s.confl_limit = 0; s.progress = 0.0;
+            s.n_ingest = s.n_pre = 0; s.pre_ok = 1;
         }
         arena = arena_half(0);
         wpool = wpool_half(0);
@@ -1651,56 +2050,7 @@ template <class VT, bool COUNT> struct WarpSolver {
         return 2;
     }
 
-    /* -------------------------------------------------------------- one instance: ingest + CoreSolver driver
-     * (sat/minisat.rs:37-88, lib.rs:47-126) */
-    DEV void solve_core(u32 inst) {
-        u32 cb, ce;
-        bool ok = setup(inst, cb, ce);
-        u32 n_ingest = 0, n_pre = 0, pre_ok = 1;
-        i32 verdict = B200SAT_INTERRUPTED;
-        if (ok) {
-            for (u32 c = cb; c < ce && ok; c++) { /* CoreSolver::add_clause minisat.rs:41-48 */
-                u32 b = P.clause_off[c], e = P.clause_off[c + 1];
-                u32 cr;
-                /* search.rs:343-345.  Only the instrumented kernel flavour carries this branch (the host routes
-                 * use_rcheck there): a second inlined copy of propagate() costs the plain kernel 4 % (A/B
-                 * measured), and --rcheck is a non-default diagnostic feature. */
-                if (COUNT && st().use_rcheck) {
-                    bool imp = is_implied(P.lits + b, e - b);
-                    if (failed()) break;
-                    if (imp) continue;
-                }
-                if (add_clause(P.lits + b, e - b, cr) == 0) ok = false;
-                if (failed()) break;
-            }
-            n_ingest = sc().num_clauses;
-            n_pre = n_ingest;
-            if (!failed()) {
-                if (P.flags & B200SAT_F_PREPROCESS) { /* CoreSolver::preprocess minisat.rs:50-55, search.rs:388-395 */
-                    if (ok) {
-                        u32 confl = propagate();
-                        if (confl == CREF_UNDEF) try_simplify(); else ok = false;
-                    }
-                    pre_ok = ok ? 1 : 0;
-                    n_pre = sc().num_clauses;
-                }
-                if (!failed()) {
-                    if (!ok) verdict = B200SAT_UNSAT;
-                    else if (P.flags & B200SAT_F_NO_SOLVE) verdict = B200SAT_INTERRUPTED;
-                    else {
-                        u32 r = search();
-                        verdict = (r == LR_SAT) ? B200SAT_SAT : (r == LR_UNSAT) ? B200SAT_UNSAT : B200SAT_INTERRUPTED;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        write_result(inst, verdict, n_ingest, n_pre, pre_ok);
-        if (P.portfolio && !failed() && verdict != B200SAT_INTERRUPTED) announce_done();
-    }
-
-    DEV void write_result(u32 inst, i32 verdict, u32 n_ingest, u32 n_pre, u32 pre_ok) {
-        (void)inst;
+    DEV void write_result(i32 verdict, u32 n_ingest, u32 n_pre, u32 pre_ok) {
         b200sat_result *r = P.results + res_index;
         const Scal &s = sc();
         bool zero = !pre_ok && (P.flags & B200SAT_F_ZERO_STATS_ON_PRE_UNSAT);

@@ -1,0 +1,7 @@
+/* ingest kernels: CoreSolver, counters off */
+#define B200SAT_KERNEL_TU_NAME b200sat_pick_ingest_c0s0
+#define B200SAT_KERNEL_TU_COUNT 0
+#define B200SAT_KERNEL_TU_SIMP 0
+#define B200SAT_KERNEL_TU_PHASE 0
+#define B200SAT_KERNEL_TU_PF 0
+#include "cdcl_kernels.cuh"

@@ -1281,13 +1281,14 @@ DEVNI SimpPhaseOut simp_phase(const KParams *Pp, VT V, u8 *slab, const b200sat_s
     }
     if (!bad) {
         if (!o.pre_ok) o.verdict = B200SAT_UNSAT;
-        else if (P.flags & B200SAT_F_NO_SOLVE) o.verdict = B200SAT_INTERRUPTED;
-        else if (simp_alive) { /* Simplificator::solve_limited simplify.rs:165-211 */
+        else if (!simp_alive) o.do_search = 1; /* simp == None: core search, minisat.rs:241-260 (parked; the host launches it unless NO_SOLVE) */
+        else if (P.flags & B200SAT_F_NO_SOLVE) o.verdict = B200SAT_INTERRUPTED; /* a live simplifier is not parked */
+        else { /* Simplificator::solve_limited simplify.rs:165-211 */
             u32 pr = 0;
             if (lane == 0) { pr = Z.seq_propagate() == CREF_UNDEF ? 1 : 0; if (pr) Z.seq_try_simplify(); }
             pr = bcast(pr);
             if (pr && Z.u_eliminate()) o.do_search = 1; else o.verdict = B200SAT_UNSAT;
-        } else o.do_search = 1; /* simp == None: core search, minisat.rs:241-260 */
+        }
     }
     if (lane == 0) {
         S.sc().eliminated_vars = Z.eliminated_vars;
@@ -1301,26 +1302,18 @@ DEVNI SimpPhaseOut simp_phase(const KParams *Pp, VT V, u8 *slab, const b200sat_s
     return o;
 }
 
-template <class VT, bool COUNT>
-DEVNI void simp_extend_model(const KParams *Pp, VT V, u8 *slab, u32 lane_, u32 res_index) { /* elim_clauses.rs:43-63 */
-    if (lane_ == 0) {
-        WarpSolver<VT, COUNT> S(*Pp, lane_);
-        S.V = V; S.slab = slab; S.res_index = res_index;
-        SeqSimp<WarpSolver<VT, COUNT>, COUNT> Z(S);
-        Z.bind_ptrs();
-        Z.esizes_n = S.sc().elim_n;
-        Z.extend_model(Pp->models + (size_t)res_index * Pp->model_stride);
-    }
-    __syncwarp();
-}
-
-/* SimpSolver driver for one instance (../minisat.rs:123-279 + lib.rs:47-126 flags) */
-template <class VT, bool COUNT> DEV void solve_simp(WarpSolver<VT, COUNT> &S, u32 inst) {
+/* SimpSolver ingest phase of one instance (../minisat.rs:123-279 + lib.rs:47-126 flags): var creation and
+ * add_clause in DIMACS order, preprocessing (eliminate), and -- when solve_limited is entered with the simplifier
+ * still alive -- the elimination pass in front of the search.  Ends like ingest_core: result record written, the
+ * instance parked for the search kernel when a search has to follow.  Model extension happens after the search
+ * (WarpSolver::finish_search, elim_clauses.rs:43-63) from the eliminated-clause stack left in the slab. */
+template <class VT, bool COUNT> DEV bool ingest_simp(WarpSolver<VT, COUNT> &S, u32 inst) {
     const KParams &P = S.P;
     u32 cb, ce;
     bool setup_ok = S.setup(inst, cb, ce);
     u32 n_ingest = 0, n_pre = 0, pre_ok = 1;
     i32 verdict = B200SAT_INTERRUPTED;
+    bool runnable = false;
     if (setup_ok && P.L.simp_cap == 0) { S.fail(ST_MEM_SIMP); setup_ok = false; }
     if (setup_ok) {
         const SimpPhaseOut o = simp_phase<VT, COUNT>(&S.P, S.V, S.slab, S.stp, S.lane, S.res_index, S.nvars, cb, ce);
@@ -1329,15 +1322,9 @@ template <class VT, bool COUNT> DEV void solve_simp(WarpSolver<VT, COUNT> &S, u3
         S.arena = S.arena_half(S.sc().cur_arena);
         S.wpool = S.wpool_half(S.sc().cur_wpool);
         __syncwarp();
-        if (!S.failed() && o.do_search) {
-            u32 r = S.search();
-            verdict = (r == LR_SAT) ? B200SAT_SAT : (r == LR_UNSAT) ? B200SAT_UNSAT : B200SAT_INTERRUPTED;
-        }
+        runnable = !S.failed() && o.do_search;
     }
-    __syncwarp();
-    S.write_result(inst, verdict, n_ingest, n_pre, pre_ok);
-    if (P.models && !S.failed() && verdict == B200SAT_SAT && S.st().extend_model)
-        simp_extend_model<VT, COUNT>(&S.P, S.V, S.slab, S.lane, S.res_index);
+    return S.park_after_ingest(verdict, n_ingest, n_pre, pre_ok, runnable);
 }
 
 } // namespace b200sat

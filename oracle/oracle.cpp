@@ -853,12 +853,35 @@ struct Searcher {
         db.gc(g);
     }
 
-    enum LoopRes { LR_RESTART, LR_UNSAT, LR_SAT };
-    LoopRes search_loop(uint64_t nof_conflicts, LearningGuard &learnt) {   /* :452-501 (no assumptions; budget always within) */
+    enum LoopRes { LR_RESTART, LR_UNSAT, LR_SAT, LR_INTERRUPTED };
+    int64_t conflict_budget = -1, propagation_budget = -1;                 /* budget.rs:5-34 (no asynchronous interrupt here) */
+    double progress = 0.0;
+    bool within_budget() const {                                           /* budget.rs:21-25 */
+        return (conflict_budget < 0 || conflicts < (uint64_t)conflict_budget) &&
+               (propagation_budget < 0 || watches.propagations < (uint64_t)propagation_budget);
+    }
+    double progress_estimate() const {                                     /* search/util.rs:5-14 */
+        double vars = 1.0 / (double)assigns.number_of_vars();
+        double prog = 0.0, factor = vars;
+        size_t nl = assigns.lim.size();
+        for (size_t level = 1; level <= nl; level++) {                     /* assignment.rs:266-292 all_levels_dir */
+            size_t head = assigns.lim[level - 1];
+            size_t tail = level < nl ? assigns.lim[level] : assigns.trail.size();
+            prog += factor * (double)(tail - head);
+            factor *= vars;
+        }
+        return prog;
+    }
+    LoopRes search_loop(uint64_t nof_conflicts, LearningGuard &learnt) {   /* :452-501 (no assumptions) */
         starts += 1;
         uint64_t confl_limit = conflicts + nof_conflicts;
         for (;;) {
             if (!propagate_learn_backtrack(learnt)) return LR_UNSAT;
+            if (!within_budget()) {                                        /* :473-477 */
+                progress = progress_estimate();
+                cancel_until(GROUND_LEVEL);
+                return LR_INTERRUPTED;
+            }
             if (conflicts >= confl_limit) { cancel_until(GROUND_LEVEL); return LR_RESTART; }
             try_simplify();
             if ((double)db.learnts.size() >= learnt.max_learnts + (double)assigns.number_of_assigns()) {
@@ -872,8 +895,8 @@ struct Searcher {
             assigns.assign_lit(next, CREF_UNDEF);
         }
     }
-    /* search_internal :409-442 ; true = SAT */
-    bool search() {
+    /* search_internal :409-442 ; ORACLE_SAT / ORACLE_UNSAT / ORACLE_INTERRUPTED */
+    int search() {
         solves += 1;
         LearningGuard learnt{st.min_learnts_lim, st.size_factor, st.size_inc, st.size_adjust_start_confl, st.size_adjust_inc};
         learnt.reset(db.stats.num_clauses);
@@ -883,7 +906,7 @@ struct Searcher {
             uint64_t conflicts_to_go = (uint64_t)(rest_base * st.restart_first);   /* :38-46 */
             LoopRes r = search_loop(conflicts_to_go, learnt);
             if (r == LR_RESTART) { curr_restarts += 1; continue; }
-            return r == LR_SAT;
+            return r == LR_SAT ? ORACLE_SAT : r == LR_UNSAT ? ORACLE_UNSAT : ORACLE_INTERRUPTED;
         }
     }
     void get_stats(uint64_t *s) const {                                    /* :590-601, sat.rs:8-18 */
@@ -1326,7 +1349,7 @@ struct Solver {
             if (search.propagate() == CREF_UNDEF) search.try_simplify(); else return ORACLE_UNSAT;
             if (!simp->eliminate(search, elimclauses)) return ORACLE_UNSAT;
         } else if (kind == ORACLE_CORE && !ok) return ORACLE_UNSAT;        /* minisat.rs:80-82 */
-        if (!search.search()) return ORACLE_UNSAT;
+        { int r = search.search(); if (r != ORACLE_SAT) return r; }    /* Interrupted hands the solver back (sat.rs:24) */
         model.assign(n_vars(), 2);                                         /* extract_model formula/util.rs:35-41 */
         for (Lit l : search.assigns.trail) model[lit_var(l)] = lit_sign(l) ? 0 : 1;
         if (kind == ORACLE_SIMP && extend_model) elimclauses.extend_model(model);
@@ -1396,6 +1419,12 @@ void oracle_default_settings(oracle_settings *s) {
 
 void oracle_set_trace(uint64_t *buf, uint32_t cap) { g_trace.buf = buf; g_trace.cap = cap; g_trace.n = 0; }
 
+static int64_t g_conflict_budget = -1, g_propagation_budget = -1;
+static int g_resume_rounds = 0;
+void oracle_set_budget(int64_t conflict_budget, int64_t propagation_budget, int resume_rounds) {
+    g_conflict_budget = conflict_budget; g_propagation_budget = propagation_budget; g_resume_rounds = resume_rounds;
+}
+
 int oracle_solve_csr(const uint32_t *clause_off, const uint32_t *lits, uint32_t n_clauses,
                      const oracle_settings *s, int kind, int flags,
                      oracle_result *out, uint8_t *model_out, uint32_t model_cap) {
@@ -1421,7 +1450,16 @@ int oracle_solve_csr(const uint32_t *clause_off, const uint32_t *lits, uint32_t 
     bool zero_stats = false;
     if (!pre_ok) { verdict = ORACLE_UNSAT; zero_stats = (flags & ORACLE_F_ZERO_STATS_ON_PRE_UNSAT) != 0; }
     else if (flags & ORACLE_F_NO_SOLVE) verdict = ORACLE_INTERRUPTED;
-    else verdict = solver.solve_limited(model);
+    else {
+        solver.search.conflict_budget = g_conflict_budget;
+        solver.search.propagation_budget = g_propagation_budget;
+        verdict = solver.solve_limited(model);
+        /* SolveRes::Interrupted(progress, solver): the caller may call solve_limited on it again (sat.rs:24) */
+        for (int r = 0; r < g_resume_rounds && verdict == ORACLE_INTERRUPTED; r++) {
+            solver.search.conflict_budget = -1; solver.search.propagation_budget = -1;
+            verdict = solver.solve_limited(model);
+        }
+    }
     auto t2 = std::chrono::steady_clock::now();
     (void)t0;
     out->verdict = verdict;

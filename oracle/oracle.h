@@ -117,6 +117,12 @@ void oracle_gen_ksat(uint64_t seed, uint32_t n, uint32_t m, uint32_t k, uint32_t
 int oracle_check_model(const uint32_t *clause_off, const uint32_t *lits, uint32_t n_clauses,
                        const uint8_t *model, uint32_t n_vars);
 
+/* Budget of the solve_limited call(s) made by oracle_solve_csr / _batch_csr from now on (process-wide; budget.rs:5-34,
+ * < 0 = none).  An instance that runs out of budget returns ORACLE_INTERRUPTED; with resume_rounds > 0 solve_limited is
+ * then called again on the returned solver, without a budget, up to that many times (sat.rs:24).  Exact for CoreSolver and
+ * for SimpSolver after preprocess() (simp == None). */
+void oracle_set_budget(int64_t conflict_budget, int64_t propagation_budget, int resume_rounds);
+
 /* dump per-conflict trace (debugging divergences): up to cap records of
  * (bt_level, learnt_len, hash). Enabled per call through oracle_set_trace. */
 void oracle_set_trace(uint64_t *buf, uint32_t cap_records);

@@ -94,6 +94,7 @@ def lib():
         L.oracle_check_model.argtypes = [u32p, u32p, C.c_uint32, C.POINTER(C.c_uint8), C.c_uint32]
         L.oracle_check_model.restype = C.c_int
         L.oracle_set_trace.argtypes = [C.POINTER(C.c_uint64), C.c_uint32]
+        L.oracle_set_budget.argtypes = [C.c_int64, C.c_int64, C.c_int]
         _lib = L
     return _lib
 
@@ -148,6 +149,11 @@ def solve_batch(inst_clause_off, clause_off, lits, kind=SIMP,
     secs = lib().oracle_solve_batch_csr(ioffp, offp, lip, n, C.byref(s), kind, flags, threads,
                                         results, mp, model_stride)
     return results, models, secs
+
+
+def set_budget(conflict_budget=-1, propagation_budget=-1, resume_rounds=0):
+    """Budget of the following solve calls (process-wide); set_budget() resets it."""
+    lib().oracle_set_budget(conflict_budget, propagation_budget, resume_rounds)
 
 
 def parse_dimacs(path, strict=False):

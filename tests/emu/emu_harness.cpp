@@ -110,44 +110,110 @@ struct Job {
     KParams P;
     void *smem;
     int tier_nv;
-    u32 inst;
+    u32 inst;       /* work index: instance id, or replica id in portfolio mode */
     bool count;
     bool replica = false;
+    int phase = 0;  /* 0: ingest kernel body, 1: one search-kernel pick-up (load, run a slice, park or finish) */
+    u32 runnable = 0, suspended = 0;
 };
 
-template <bool SIMP, class VT, bool COUNT> void run_one(WarpSolver<VT, COUNT> &S, const Job *j) {
+template <class WS> void bind_job(WS &S, const Job *j) {
+    S.slab = j->P.slabs;
     S.res_index = j->inst;
+    S.stp = j->replica ? j->P.replica_settings + j->inst : &j->P.st;
+}
+
+/* the body of ingest_loop / search_loop_ring (cdcl_kernels.cuh) for ONE work item, without the device queue */
+template <bool SIMP, class WS> void ingest_one(WS &S, Job *j) {
+    bind_job(S, j);
+    const u32 inst = j->replica ? 0u : j->inst;
+    bool r;
     if constexpr (SIMP) {
 #ifdef B200SAT_HAVE_SIMP
-        solve_simp(S, j->inst);
+        r = ingest_simp(S, inst);
+#else
+        r = false;
 #endif
-    } else {
-        if (j->replica) { S.stp = j->P.replica_settings + j->inst; S.solve_core(0); return; }
-        S.solve_core(j->inst);
+    } else r = S.ingest_core(inst);
+    if (S.lane == 0) j->runnable = (r && !(j->P.flags & B200SAT_F_NO_SOLVE)) ? 1 : 0;
+}
+template <class WS> void search_one(WS &S, Job *j) {
+    bind_job(S, j);
+    S.load_state();
+    const u32 r = S.run_search();
+    if (r == WS::SR_SUSPEND) {
+        S.save_state();
+        if (S.lane == 0) j->suspended = 1;
+        return;
+    }
+    S.finish_search(r, j->P.kind == B200SAT_SIMP);
+    if (S.lane == 0) j->suspended = 0;
+}
+
+template <int NV, bool COUNT, bool PF> void entry_s(void *user, int lane) {
+    Job *j = (Job *)user;
+    if (j->phase == 0) {
+        if (j->P.kind == B200SAT_SIMP) { /* SimpSolver ingest: elimination heap + occurrence counts in shared memory */
+            WarpSolver<VarsS<NV, true>, COUNT> S(j->P, (u32)lane);
+            S.V.s = (SmemVars<NV, true> *)j->smem;
+            ingest_one<true>(S, j);
+        } else {
+            WarpSolver<VarsS<NV>, COUNT> S(j->P, (u32)lane);
+            S.V.s = (SmemVars<NV> *)j->smem;
+            ingest_one<false>(S, j);
+        }
+        return;
+    }
+    WarpSolver<VarsS<NV>, COUNT, PF> S(j->P, (u32)lane);
+    S.V.s = (SmemVars<NV> *)j->smem;
+    search_one(S, j);
+}
+template <bool COUNT, bool PF> void entry_g(void *user, int lane) {
+    Job *j = (Job *)user;
+    if (j->phase == 0) {
+        WarpSolver<VarsG, COUNT> S(j->P, (u32)lane);
+        S.V.s = (SmemSmall *)j->smem;
+        S.V.bind(j->P.slabs + j->P.L.off_vars, j->P.L.nv_cap);
+        if (j->P.kind == B200SAT_SIMP) ingest_one<true>(S, j); else ingest_one<false>(S, j);
+        return;
+    }
+    WarpSolver<VarsG, COUNT, PF> S(j->P, (u32)lane);
+    S.V.s = (SmemSmall *)j->smem;
+    S.V.bind(j->P.slabs + j->P.L.off_vars, j->P.L.nv_cap);
+    search_one(S, j);
+}
+
+u32 save_bytes_of(int tier_nv) {
+    switch (tier_nv) {
+    case 128: return SmemSave<128>::BYTES;
+    case 256: return SmemSave<256>::BYTES;
+    case 1024: return SmemSave<1024>::BYTES;
+    default: return (u32)sizeof(SmemSmall);
+    }
+}
+template <bool PF> void (*pick_entry(int tier_nv, bool count))(void *, int) {
+    switch (tier_nv) {
+    case 128: return count ? entry_s<128, true, PF> : entry_s<128, false, PF>;
+    case 256: return count ? entry_s<256, true, PF> : entry_s<256, false, PF>;
+    case 1024: return count ? entry_s<1024, true, PF> : entry_s<1024, false, PF>;
+    default: return count ? entry_g<true, PF> : entry_g<false, PF>;
     }
 }
 
-template <int NV, bool COUNT> void entry_s(void *user, int lane) {
-    Job *j = (Job *)user;
-    if (j->P.kind == B200SAT_SIMP) { /* SimpSolver kernels: elimination heap + occurrence counts in shared memory */
-        WarpSolver<VarsS<NV, true>, COUNT> S(j->P, (u32)lane);
-        S.V.s = (SmemVars<NV, true> *)j->smem;
-        S.slab = j->P.slabs;
-        run_one<true>(S, j);
-        return;
+/* One work item through both phases.  The shared-memory block is wiped between pick-ups (a different warp resumes
+ * the item on the GPU), so everything a resumed search needs has to come out of the slab. */
+template <bool PF> void run_item(Job &j, uint64_t sched_seed, u32 *n_suspends) {
+    void (*fn)(void *, int) = pick_entry<PF>(j.tier_nv, j.count);
+    j.phase = 0; j.runnable = 0;
+    simt::run_warp(fn, &j, sched_seed);
+    u32 k = 0;
+    while (j.runnable) {
+        memset(j.smem, 0xA5, 32 * 1024 * 8);
+        j.phase = 1; j.suspended = 0;
+        simt::run_warp(fn, &j, sched_seed ? sched_seed + 77 * (++k) : 0);
+        if (!j.suspended) break;
+        if (n_suspends) (*n_suspends)++;
     }
-    WarpSolver<VarsS<NV>, COUNT> S(j->P, (u32)lane);
-    S.V.s = (SmemVars<NV> *)j->smem;
-    S.slab = j->P.slabs;
-    run_one<false>(S, j);
-}
-template <bool COUNT> void entry_g(void *user, int lane) {
-    Job *j = (Job *)user;
-    WarpSolver<VarsG, COUNT> S(j->P, (u32)lane);
-    S.V.s = (SmemSmall *)j->smem;
-    S.slab = j->P.slabs;
-    S.V.bind(S.slab + j->P.L.off_vars, j->P.L.nv_cap);
-    if (j->P.kind == B200SAT_SIMP) run_one<true>(S, j); else run_one<false>(S, j);
 }
 } // namespace
 
@@ -157,12 +223,12 @@ extern "C" {
  * clauses earlier replicas exported to the shared ring).  share: PF_SHARE | PF_IGNORE_DONE bits. */
 int emu_portfolio(const uint32_t *clause_off, const uint32_t *lits, uint32_t n_clauses, const b200sat_settings *base,
                   uint32_t n_replicas, uint32_t share, int flags, uint64_t sched_seed, b200sat_result *results,
-                  uint8_t *models, uint32_t model_stride) {
+                  uint8_t *models, uint32_t model_stride, uint32_t import_cap) {
     BatchShape sh = {0, n_clauses, clause_off[n_clauses], 0};
     for (u32 c = 0; c < n_clauses; c++) { u32 len = clause_off[c + 1] - clause_off[c]; if (len > sh.max_clause_len) sh.max_clause_len = len; }
     for (u32 k = 0; k < clause_off[n_clauses]; k++) if ((lits[k] >> 1) + 1 > sh.max_vars) sh.max_vars = (lits[k] >> 1) + 1;
     int tier_nv = pick_tier_nv(sh.max_vars, sh.max_clauses);
-    Layout L = plan_layout(sh, tier_nv, B200SAT_CORE, 0, 0, 0);
+    Layout L = plan_layout(sh, tier_nv, B200SAT_CORE, 0, 0, 0, save_bytes_of(tier_nv));
     std::vector<u64> slab((L.slab_bytes + 7) / 8 + 2);
     std::vector<u64> smem(32 * 1024);
     const u32 ring_words = 1u << 18;
@@ -178,29 +244,28 @@ int emu_portfolio(const uint32_t *clause_off, const uint32_t *lits, uint32_t n_c
     j.P.slabs = (u8 *)slab.data(); j.P.L = L; j.P.st = *base; j.P.kind = B200SAT_CORE; j.P.flags = flags; j.P.attempt = 1;
     j.P.portfolio = n_replicas; j.P.replica_base = 0; j.P.share = share; j.P.n_rings = 1; j.P.my_ring = 0;
     j.P.ring_words = ring_words; j.P.rings[0] = ring.data(); j.P.replica_settings = rs.data();
-    j.smem = smem.data(); j.tier_nv = tier_nv;
+    j.P.conflict_budget = -1; j.P.propagation_budget = -1; j.P.import_cap = import_cap;
+    j.smem = smem.data(); j.tier_nv = tier_nv; j.count = false;
     for (u32 r = 0; r < n_replicas; r++) {
-        j.inst = r; /* replica id: entry_* maps it to instance 0 */
+        j.inst = r; /* replica id: instance 0 with the replica's diversified settings */
         j.replica = true;
-        void (*fn)(void *, int) = nullptr;
-        switch (tier_nv) {
-        case 128: fn = entry_s<128, false>; break;
-        case 256: fn = entry_s<256, false>; break;
-        case 1024: fn = entry_s<1024, false>; break;
-        default: fn = entry_g<false>; break;
-        }
-        simt::run_warp(fn, &j, sched_seed ? sched_seed + r : 0);
+        run_item<true>(j, sched_seed ? sched_seed + r : 0, nullptr);
     }
     return 0;
 }
 
-/* tier_nv: 128/256/512/1024 = shared-memory tier, 0 = global tier, -1 = auto.
+/* tier_nv: 128/256/1024 = shared-memory tier, 0 = global tier, -1 = auto.
  * sched_seed: 0 = lanes run in ascending order, else adversarial ordering.
- * Returns 0, or -1 when `kind` is not compiled in. */
+ * slice_conflicts: 0 = an instance runs to the end in one pick-up; else it is parked and resumed (with wiped shared
+ * memory) every time it has used that many conflicts -- the result must not depend on it.
+ * conflict_budget / propagation_budget: budget.rs:5-34 (< 0 = none); an instance that runs out returns
+ * INTERRUPTED and, when resume_rounds > 0, is searched again (a new solve_limited call) that many times without a budget.
+ * Returns the number of park/resume cycles, or -1 when `kind` is not compiled in. */
 int emu_solve_batch(const uint32_t *inst_clause_off, const uint32_t *clause_off, const uint32_t *lits,
                     uint32_t n_inst, const b200sat_settings *st, int kind, int flags, int tier_nv,
                     uint64_t arena_words, uint64_t wpool_entries, uint64_t sched_seed,
-                    b200sat_result *results, uint8_t *models, uint32_t model_stride) {
+                    b200sat_result *results, uint8_t *models, uint32_t model_stride,
+                    uint32_t slice_conflicts, int64_t conflict_budget, int64_t propagation_budget, int resume_rounds) {
 #ifndef B200SAT_HAVE_SIMP
     if (kind == B200SAT_SIMP) return -1;
 #endif
@@ -220,8 +285,13 @@ int emu_solve_batch(const uint32_t *inst_clause_off, const uint32_t *clause_off,
     if (tier_nv < 0) tier_nv = pick_tier_nv(sh.max_vars, sh.max_clauses);
     std::vector<u32> todo(n_inst);
     for (u32 i = 0; i < n_inst; i++) todo[i] = i;
+    u32 n_suspends = 0;
+    u32 qctl[QC_WORDS];
+    memset(qctl, 0, sizeof qctl);
+    qctl[QC_TAIL] = 1; /* "somebody is always waiting": every expired slice parks the instance */
     for (u32 attempt = 0; attempt < 4 && !todo.empty(); attempt++) {
-        Layout L = plan_layout(sh, tier_nv, kind, attempt, arena_words, wpool_entries);
+        if (attempt == 3) tier_nv = 0;
+        Layout L = plan_layout(sh, tier_nv, kind, attempt, arena_words, wpool_entries, save_bytes_of(tier_nv));
         std::vector<u64> slab((L.slab_bytes + 7) / 8 + 2);
         std::vector<u64> smem(32 * 1024);
         u32 queue = 0;
@@ -232,23 +302,34 @@ int emu_solve_batch(const uint32_t *inst_clause_off, const uint32_t *clause_off,
         j.P.results = results; j.P.models = models; j.P.model_stride = model_stride;
         j.P.slabs = (u8 *)slab.data(); j.P.L = L; j.P.st = *st; j.P.kind = kind; j.P.flags = flags;
         j.P.attempt = attempt + 1;
+        j.P.qctl = qctl; j.P.slice_conflicts = slice_conflicts;
         j.smem = smem.data(); j.tier_nv = tier_nv;
-        const bool count = (flags & B200SAT_F_COUNT_TRAFFIC) != 0;
+        j.count = (flags & B200SAT_F_COUNT_TRAFFIC) != 0;
         std::vector<u32> again;
         for (u32 inst : todo) {
             j.inst = inst;
-            void (*fn)(void *, int) = nullptr;
-            switch (tier_nv) {
-            case 128: fn = count ? entry_s<128, true> : entry_s<128, false>; break;
-            case 256: fn = count ? entry_s<256, true> : entry_s<256, false>; break;
-            case 1024: fn = count ? entry_s<1024, true> : entry_s<1024, false>; break;
-            default: fn = count ? entry_g<true> : entry_g<false>; break;
+            j.P.conflict_budget = conflict_budget; j.P.propagation_budget = propagation_budget;
+            const uint64_t seed = sched_seed ? sched_seed + inst : 0;
+            run_item<false>(j, seed, &n_suspends);
+            for (int r = 0; r < resume_rounds; r++) {
+                if (results[inst].status != B200SAT_OK || results[inst].verdict != B200SAT_INTERRUPTED) break;
+                if (flags & B200SAT_F_NO_SOLVE) break;
+                j.P.conflict_budget = -1; j.P.propagation_budget = -1;
+                j.runnable = 1; /* the interrupted search left the instance parked (PH_READY) */
+                void (*fn)(void *, int) = pick_entry<false>(j.tier_nv, j.count);
+                u32 k = 0;
+                while (j.runnable) {
+                    memset(j.smem, 0x5A, 32 * 1024 * 8);
+                    j.phase = 1; j.suspended = 0;
+                    simt::run_warp(fn, &j, seed ? seed + 991 * (++k) : 0);
+                    if (!j.suspended) break;
+                    n_suspends++;
+                }
             }
-            simt::run_warp(fn, &j, sched_seed ? sched_seed + inst : 0);
-            if (results[inst].status != B200SAT_OK) again.push_back(inst);
+            if (results[inst].status < 0) again.push_back(inst);
         }
         todo.swap(again);
     }
-    return 0;
+    return (int)n_suspends;
 }
 }

@@ -54,10 +54,10 @@ def lib():
         u32p = C.POINTER(C.c_uint32)
         L.emu_solve_batch.argtypes = [u32p, u32p, u32p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                       C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Result),
-                                      C.POINTER(C.c_uint8), C.c_uint32]
+                                      C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.c_int64, C.c_int64, C.c_int]
         L.emu_solve_batch.restype = C.c_int
         L.emu_portfolio.argtypes = [u32p, u32p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64,
-                                    C.POINTER(Result), C.POINTER(C.c_uint8), C.c_uint32]
+                                    C.POINTER(Result), C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32]
         L.emu_portfolio.restype = C.c_int
         _lib = L
     return _lib
@@ -69,8 +69,10 @@ def _u32(a):
 
 
 def solve_batch(inst_clause_off, clause_off, lits, settings, kind=0, flags=1 | 4 | 8 | 16, tier_nv=-1,
-                arena_words=0, wpool_entries=0, sched_seed=0, model_stride=0):
-    """settings: any ctypes struct with the b200sat_settings layout (e.g. oracle Settings)."""
+                arena_words=0, wpool_entries=0, sched_seed=0, model_stride=0, slice_conflicts=0,
+                conflict_budget=-1, propagation_budget=-1, resume_rounds=0, want_suspends=False):
+    """settings: any ctypes struct with the b200sat_settings layout (e.g. oracle Settings).
+    slice_conflicts > 0 parks and resumes every instance each time it used that many conflicts."""
     ioff, ioffp = _u32(inst_clause_off)
     off, offp = _u32(clause_off)
     li, lip = _u32(lits if len(lits) else np.zeros(1, np.uint32))
@@ -82,18 +84,21 @@ def solve_batch(inst_clause_off, clause_off, lits, settings, kind=0, flags=1 | 4
         models = np.full((n, model_stride), 2, dtype=np.uint8)
         mp = models.ctypes.data_as(C.POINTER(C.c_uint8))
     rc = lib().emu_solve_batch(ioffp, offp, lip, n, C.addressof(settings), kind, flags, tier_nv,
-                               arena_words, wpool_entries, sched_seed, res, mp, model_stride)
-    if rc != 0:
+                               arena_words, wpool_entries, sched_seed, res, mp, model_stride, slice_conflicts,
+                               conflict_budget, propagation_budget, resume_rounds)
+    if rc < 0:
         raise RuntimeError("emulator: solver kind not compiled in")
+    if want_suspends:
+        return res, models, rc
     return res, models
 
 
-def portfolio(clause_off, lits, settings, n_replicas, share=1, flags=8, sched_seed=0, model_stride=0):
+def portfolio(clause_off, lits, settings, n_replicas, share=1, flags=8, sched_seed=0, model_stride=0, import_cap=0):
     """Replicas of one instance run one after another against a shared ring (see emu_harness.cpp)."""
     off, offp = _u32(clause_off)
     li, lip = _u32(lits)
     res = (Result * n_replicas)()
     models = np.full((n_replicas, max(model_stride, 1)), 2, dtype=np.uint8)
     lib().emu_portfolio(offp, lip, len(off) - 1, C.addressof(settings), n_replicas, share, flags, sched_seed, res,
-                        models.ctypes.data_as(C.POINTER(C.c_uint8)), model_stride)
+                        models.ctypes.data_as(C.POINTER(C.c_uint8)), model_stride, import_cap)
     return res, models

@@ -18,6 +18,7 @@
  */
 #ifndef SIMT_EMU_H
 #define SIMT_EMU_H
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -102,6 +103,7 @@ static inline uint32_t __float_as_uint(float f) { uint32_t x; memcpy(&x, &f, 4);
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> static inline T atomicCAS(T *p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
 static inline void __threadfence() {}
+static inline void __nanosleep(unsigned) {}
 static inline void __threadfence_system() {}
 template <class T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 

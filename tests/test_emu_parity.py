@@ -195,3 +195,55 @@ def test_portfolio_first_finisher_cancels_the_rest(po, emu):
     assert res[0].status == 0 and res[0].verdict == 0
     # the emulator runs replicas one after another: replica 0 finishes, the others see `done` at their first conflict
     assert all(r.status == 1 and r.verdict == 2 for r in res[1:])
+
+
+# ---------------------------------------------------------------- resident instances: conflict slices, budgets (round 2)
+@pytest.mark.parametrize("kind,tier,slice_c", [(0, -1, 3), (0, 0, 5), (1, -1, 4)])
+def test_conflict_slices_are_trace_neutral(po, emu, kind, tier, slice_c):
+    """An instance that is parked after every few conflicts and resumed from its slab by a warp with wiped shared
+    memory produces the oracle's trace: suspension is not visible in any counter, hash or model."""
+    ioff, coff, lits = synth_batch(po, SEED2 + 9000, 6, 50, 213)
+    st = po.default_settings()
+    st.restart_first = 9.0
+    st.size_factor = 0.05          # reduceDB + garbage collection between the pick-ups
+    st.size_adjust_start_confl = 10
+    compare(po, emu, ioff, coff, lits, kind, settings=st, tier_nv=tier, sched_seed=17, slice_conflicts=slice_c)
+    _, _, n_susp = emu.solve_batch(ioff, coff, lits, st, kind=kind, flags=FLAGS, tier_nv=tier, slice_conflicts=slice_c,
+                                   want_suspends=True)
+    assert n_susp > 20
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_budget_interrupts_and_the_solver_resumes(po, emu, kind):
+    """budget.rs:5-34 / search.rs:473-477: a conflict or propagation budget ends solve_limited with Interrupted at
+    the first check after it is used up (backtracked to ground, stats kept); calling solve_limited again on the
+    returned solver starts a new search (solves += 1, restart sequence from 0) on the same clause database."""
+    ioff, coff, lits = synth_batch(po, SEED2 + 9100, 8, 50, 213)
+    st = po.default_settings()
+    for cb, pb in ((4, -1), (-1, 150), (0, -1)):
+        po.set_budget(cb, pb, 0)
+        try:
+            ores, _, _ = po.solve_batch(ioff, coff, lits, kind=kind, settings=st, threads=1, model_stride=50)
+        finally:
+            po.set_budget()
+        eres, _ = emu.solve_batch(ioff, coff, lits, st, kind=kind, flags=FLAGS, model_stride=50, sched_seed=3,
+                                  conflict_budget=cb, propagation_budget=pb)
+        n_int = 0
+        for o, e in zip(ores, eres):
+            assert e.status == 0 and e.verdict == o.verdict and list(e.stats) == list(o.stats)
+            assert e.trace_hash == o.trace_hash
+            n_int += o.verdict == po.INTERRUPTED
+        assert n_int >= 3
+        # ... and resumed without a budget: same as the oracle's second solve_limited call
+        po.set_budget(cb, pb, 1)
+        try:
+            ores, om, _ = po.solve_batch(ioff, coff, lits, kind=kind, settings=st, threads=1, model_stride=50)
+        finally:
+            po.set_budget()
+        eres, em = emu.solve_batch(ioff, coff, lits, st, kind=kind, flags=FLAGS, model_stride=50, sched_seed=4,
+                                   conflict_budget=cb, propagation_budget=pb, resume_rounds=1, slice_conflicts=11)
+        for o, e, a, b in zip(ores, eres, om, em):
+            assert e.status == 0 and e.verdict == o.verdict and o.verdict != po.INTERRUPTED
+            assert list(e.stats) == list(o.stats) and e.trace_hash == o.trace_hash
+            if o.verdict == 1:
+                assert (a[:o.n_vars] == b[:o.n_vars]).all()
