@@ -239,6 +239,22 @@ typedef struct b200sat_launch_info {
 } b200sat_launch_info;
 int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out);
 
+/* K2 bcp_replay (measurement; SURVEY.md 8d "BCP-only figure", reference function watches.rs:64-152): the resident
+ * batch is solved once with the instrumented kernels while every instance's search prefix is recorded (decisions,
+ * learnt clauses + backtrack levels, restarts, up to the first database reduction or ground simplification); the
+ * replay kernel then re-executes exactly those prefixes with unit propagation as the only real work.  The counted
+ * replay must reproduce the recorded propagation count and BCP traffic counters of every instance (`mismatches`). */
+typedef struct b200sat_replay_info {
+    uint32_t instances;     /* instances with a recorded prefix                                   */
+    uint32_t mismatches;    /* replays that left the recorded trace (must be 0)                   */
+    uint64_t propagations;  /* literals dequeued by the replayed prefixes                         */
+    uint64_t bcp_bytes;     /* SURVEY.md 8d algorithmic bytes, BCP terms (1)-(5) only             */
+    float    ms_min, ms_avg;/* CUDA-event time of the plain replay kernel over `reps` launches    */
+    uint32_t warps;         /* resident warps of the replay launch                                */
+} b200sat_replay_info;
+int b200sat_engine_bcp_replay(b200sat_engine *e, const b200sat_settings *s, int reps,
+                              b200sat_replay_info *out, void *stream);
+
 /* upload + solve + download with HOST buffers (the end-to-end call). */
 int b200sat_solve_batch(b200sat_engine *e, const b200sat_batch *batch, const b200sat_settings *s,
                         int kind, int flags, b200sat_result *results, uint8_t *models,

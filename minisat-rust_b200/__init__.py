@@ -94,6 +94,11 @@ class LaunchInfo(C.Structure):
                 ("suspends", C.c_uint32), ("resident_items", C.c_uint32)]
 
 
+class ReplayInfo(C.Structure):
+    _fields_ = [("instances", C.c_uint32), ("mismatches", C.c_uint32), ("propagations", C.c_uint64),
+                ("bcp_bytes", C.c_uint64), ("ms_min", C.c_float), ("ms_avg", C.c_float), ("warps", C.c_uint32)]
+
+
 def traffic_bytes(t):
     """algorithmic bytes from the eight traffic counters."""
     visited, kept, deref, tail, moves, implied, an_words, learnt_words = [int(x) for x in t]
@@ -115,6 +120,7 @@ ABI_SYMBOLS = (
     "b200sat_engine_ring_open_peer", "b200sat_portfolio_solve", "b200sat_engine_download_replicas",
     "b200sat_engine_verify_models", "b200sat_engine_subsume_instance", "b200sat_engine_simplify_instance", "b200sat_engine_bve_instance", "b200sat_read_dimacs", "b200sat_free_buffer", "b200sat_write_result",
     "b200sat_engine_set_slice", "b200sat_engine_set_budget", "b200sat_engine_interrupt",
+    "b200sat_engine_bcp_replay",
 )
 PF_SHARE, PF_IGNORE_DONE, PF_SHARE_LBD2, PF_KEEP_RING = 1, 2, 4, 8
 
@@ -161,6 +167,7 @@ def lib():
     L.b200sat_engine_download_batch.argtypes = [vp, u32p, u32p, u32p]
     L.b200sat_engine_configure.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
     L.b200sat_engine_launch_info.argtypes = [vp, C.POINTER(LaunchInfo)]
+    L.b200sat_engine_bcp_replay.argtypes = [vp, C.POINTER(Settings), C.c_int, C.POINTER(ReplayInfo), vp]
     L.b200sat_engine_set_slice.argtypes = [vp, C.c_uint32]
     L.b200sat_engine_set_budget.argtypes = [vp, C.c_int64, C.c_int64]
     L.b200sat_engine_interrupt.argtypes = [vp, C.c_int]
@@ -326,6 +333,13 @@ class Engine:
 
     def configure(self, warps_per_block=0, blocks_per_sm=0, arena_words=0, wpool_entries=0):
         _check(lib().b200sat_engine_configure(self._e, warps_per_block, blocks_per_sm, arena_words, wpool_entries))
+
+    def bcp_replay(self, settings=None, reps=3, stream=None):
+        """K2: BCP-only replay of the recorded search prefixes of the resident batch (measurement)"""
+        s = settings if settings is not None else default_settings()
+        ri = ReplayInfo()
+        _check(lib().b200sat_engine_bcp_replay(self._e, C.byref(s), reps, C.byref(ri), stream))
+        return {k: getattr(ri, k) for k, _ in ReplayInfo._fields_}
 
     def set_slice(self, slice_conflicts):
         """conflicts an instance runs before it yields to waiting ones (0 = never); trace-neutral"""

@@ -176,8 +176,13 @@ struct b200sat_engine {
     cudaEvent_t ev2 = nullptr, ev3 = nullptr; /* around the search kernel alone */
     u32 slice_conflicts = 20000;  /* conflicts an instance may run before it yields to waiting ones */
     long long conflict_budget = -1, propagation_budget = -1;
-    int *h_interrupt = nullptr;   /* pinned, device-mapped async interrupt word (Budget::asynch_interrupt) */
-    int *d_interrupt = nullptr;
+    int *h_interrupt = nullptr;   /* pinned staging of the async interrupt word (Budget::asynch_interrupt) */
+    int *d_interrupt = nullptr;   /* the word the kernels poll (device memory, d_queue + 48)               */
+    cudaStream_t side_stream = nullptr; /* carries the interrupt word to the device while a solve is running */
+    u32 *d_trace = nullptr;       /* K2: per-instance event record of the search prefix */
+    size_t cap_trace = 0;
+    u32 trace_cap = 0;            /* words per instance; 0 = recording off */
+    int replay_mode = 0;          /* 1: launch_attempt runs ingest + bcp_replay (count kernel), 2: same, plain kernel */
     u32 resident_items = 0;       /* items whose state is parked in d_slabs (chunk 0 of the last solve) */
     Layout resident_L;            /* layout the parked states were written with */
     int resident_tier_nv = 0;
@@ -245,12 +250,15 @@ extern "C" b200sat_engine *b200sat_engine_create(int device) {
     if (cudaMalloc((void **)&e->d_queue, 256) != cudaSuccess || cudaMallocHost((void **)&e->h_pinned, 256) != cudaSuccess ||
         cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
         cudaEventCreate(&e->ev2) != cudaSuccess || cudaEventCreate(&e->ev3) != cudaSuccess ||
-        cudaHostAlloc((void **)&e->h_interrupt, 64, cudaHostAllocMapped) != cudaSuccess ||
-        cudaHostGetDevicePointer((void **)&e->d_interrupt, e->h_interrupt, 0) != cudaSuccess || (*e->h_interrupt = 0) != 0) {
+        cudaMallocHost((void **)&e->h_interrupt, 64) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMemset(e->d_queue, 0, 256) != cudaSuccess) {
         set_err(B200SAT_E_CUDA, "engine allocation failed");
         delete e;
         return nullptr;
     }
+    *e->h_interrupt = 0;
+    e->d_interrupt = (int *)(e->d_queue + 48);
     return e;
 }
 
@@ -269,7 +277,9 @@ extern "C" void b200sat_engine_destroy(b200sat_engine *e) {
     if (e->ev2) cudaEventDestroy(e->ev2);
     if (e->ev3) cudaEventDestroy(e->ev3);
     if (e->h_interrupt) cudaFreeHost(e->h_interrupt);
+    if (e->side_stream) cudaStreamDestroy(e->side_stream);
     cudaFree(e->d_ring);
+    cudaFree(e->d_trace);
     delete e;
 }
 
@@ -293,7 +303,10 @@ extern "C" int b200sat_engine_set_budget(b200sat_engine *e, int64_t conflict_bud
 }
 extern "C" int b200sat_engine_interrupt(b200sat_engine *e, int raised) {
     if (!e || !e->h_interrupt) return set_err(B200SAT_E_ARG, "null engine");
-    *(volatile int *)e->h_interrupt = raised ? 1 : 0;
+    CK(cudaSetDevice(e->device));
+    *e->h_interrupt = raised ? 1 : 0;
+    CK(cudaMemcpyAsync(e->d_interrupt, e->h_interrupt, 4, cudaMemcpyHostToDevice, e->side_stream));
+    CK(cudaStreamSynchronize(e->side_stream));
     return 0;
 }
 
@@ -422,14 +435,21 @@ static int check_settings(const b200sat_settings *s, int kind) {
 __global__ void init_qctl(u32 *qctl, u32 total) {
     if (threadIdx.x < QC_WORDS) qctl[threadIdx.x] = threadIdx.x == QC_TOTAL ? total : 0u;
 }
+/* between the ingest and the search kernel: the first min(runnable, warps) ring slots are handed out statically */
+__global__ void start_ring(u32 *qctl, u32 n_warps) {
+    const u32 t = qctl[QC_TAIL];
+    const u32 h = t < n_warps ? t : n_warps;
+    qctl[QC_HEAD] = h;
+    qctl[QC_HEAD0] = h;
+}
 
 /* launch shape of one persistent kernel: as many resident warps per SM as shared memory and registers allow */
 struct LaunchShape { int wpb = 1, bps = 1; u32 grid = 0; size_t smem = 0; };
-static int shape_kernel(b200sat_engine *e, kernel_fn fn, size_t spw, u32 n_items, LaunchShape &out) {
+static int shape_kernel(b200sat_engine *e, kernel_fn fn, size_t spw, u32 n_items, int max_wpb, LaunchShape &out) {
     int best_wpb = 1, best_bps = 1, best_warps = 0;
     const int cand[] = {1, 2};
-    for (int ci = 0; ci < 2; ci++) {
-        int wpb = e->cfg_wpb > 0 ? e->cfg_wpb : cand[ci];
+    for (int ci = 0; ci < max_wpb; ci++) {
+        int wpb = (e->cfg_wpb > 0 && e->cfg_wpb <= max_wpb) ? e->cfg_wpb : cand[ci];
         if (wpb > 2) return set_err(B200SAT_E_ARG, "warps_per_block must be 1 or 2 (launch bounds)");
         size_t smem = spw * wpb;
         if (smem > e->smem_optin) { if (e->cfg_wpb > 0) return set_err(B200SAT_E_ARG, "warps_per_block needs too much shared memory"); continue; }
@@ -439,7 +459,7 @@ static int shape_kernel(b200sat_engine *e, kernel_fn fn, size_t spw, u32 n_items
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void *)fn, wpb * 32, smem));
         if (e->cfg_bps > 0 && bps > e->cfg_bps) bps = e->cfg_bps;
         if (bps * wpb > best_warps) { best_warps = bps * wpb; best_wpb = wpb; best_bps = bps; }
-        if (e->cfg_wpb > 0) break;
+        if (e->cfg_wpb > 0 && e->cfg_wpb <= max_wpb) break;
     }
     if (best_warps == 0) return set_err(B200SAT_E_CUDA, "kernel does not fit on the device");
     u32 grid = (u32)(e->num_sms * best_bps);
@@ -474,6 +494,7 @@ static void fill_params(b200sat_engine *e, KParams &P, const Layout &L) {
     P.conflict_budget = e->conflict_budget; P.propagation_budget = e->propagation_budget;
     P.interrupt = e->d_interrupt;
     P.import_cap = e->import_cap;
+    P.trace_buf = e->trace_cap ? e->d_trace : nullptr; P.trace_cap = e->trace_cap;
 }
 
 /* enqueue one attempt on the pending stream, no host sync: per chunk of resident items the ingest kernel (every
@@ -488,6 +509,7 @@ static int launch_attempt(b200sat_engine *e) {
     size_t spw_i = 0, spw_s = 0, save = 0, save2 = 0;
     kernel_fn fn_i = pick_ingest(pd.tier_nv, count, pd.kind, spw_i, save);
     kernel_fn fn_s = pick_search(pd.tier_nv, count, pd.portfolio != 0, spw_s, save2);
+    if (e->replay_mode) fn_s = e->replay_mode == 1 ? b200sat_pick_replay_c1(pd.tier_nv, &spw_s, &save2) : b200sat_pick_replay_c0(pd.tier_nv, &spw_s, &save2);
     Layout L = plan_layout(e->shape, pd.tier_nv, pd.kind, pd.attempt, e->cfg_arena, e->cfg_wpool, (u32)save);
     /* resident items per chunk: every item owns a slab; bounded by ~60% of the free HBM */
     u64 slots = pd.n_work;
@@ -502,8 +524,8 @@ static int launch_attempt(b200sat_engine *e) {
         }
     }
     LaunchShape shi, shs;
-    if ((rc = shape_kernel(e, fn_i, spw_i, (u32)slots, shi))) return rc;
-    if ((rc = shape_kernel(e, fn_s, spw_s, (u32)slots, shs))) return rc;
+    if ((rc = shape_kernel(e, fn_i, spw_i, (u32)slots, 2, shi))) return rc;
+    if ((rc = shape_kernel(e, fn_s, spw_s, (u32)slots, 1, shs))) return rc; /* the search kernels are one warp per block */
     if (slots * L.slab_bytes > e->cap_slabs) {
         CK(cudaStreamSynchronize(stream)); /* the old slabs may still be in use by an earlier launch on this stream */
         if ((rc = ensure(e->d_slabs, e->cap_slabs, (size_t)(slots * L.slab_bytes)))) return rc;
@@ -528,8 +550,16 @@ static int launch_attempt(b200sat_engine *e) {
         init_qctl<<<1, 32, 0, stream>>>(P.qctl, n_chunk);
         fn_i<<<shi.grid, shi.wpb * 32, shi.smem, stream>>>(P);
         CK(cudaGetLastError());
-        if (!(pd.flags & B200SAT_F_NO_SOLVE)) {
+        if (e->replay_mode) {
+            CK(cudaMemsetAsync(e->d_queue, 0, 4, stream));
             if (first_chunk) CK(cudaEventRecord(e->ev2, stream));
+            fn_s<<<shs.grid, shs.wpb * 32, shs.smem, stream>>>(P);
+            CK(cudaGetLastError());
+            if (first_chunk) CK(cudaEventRecord(e->ev3, stream));
+            e->info.launches += 1;
+        } else if (!(pd.flags & B200SAT_F_NO_SOLVE)) {
+            if (first_chunk) CK(cudaEventRecord(e->ev2, stream));
+            start_ring<<<1, 1, 0, stream>>>(P.qctl, shs.grid * shs.wpb);
             fn_s<<<shs.grid, shs.wpb * 32, shs.smem, stream>>>(P);
             CK(cudaGetLastError());
             if (first_chunk) CK(cudaEventRecord(e->ev3, stream));
@@ -539,7 +569,7 @@ static int launch_attempt(b200sat_engine *e) {
         first_chunk = false;
     }
     CK(cudaEventRecord(e->ev1, stream));
-    pd.searched = !(pd.flags & B200SAT_F_NO_SOLVE);
+    pd.searched = !(pd.flags & B200SAT_F_NO_SOLVE) || e->replay_mode != 0;
     pd.next_list = e->d_work[pd.attempt & 1];
     CK(cudaMemsetAsync(e->d_queue + 1, 0, 4, stream));
     collect_failed<<<(pd.n_work + 255) / 256, 256, 0, stream>>>(e->d_results, pd.work, pd.n_work, pd.portfolio != 0, pd.next_list, e->d_queue + 1);
@@ -611,6 +641,81 @@ extern "C" int b200sat_engine_solve(b200sat_engine *e, const b200sat_settings *s
     int rc = b200sat_engine_solve_async(e, s, kind, flags, stream_);
     if (rc) return rc;
     return b200sat_engine_finish(e);
+}
+
+/* K2 (SURVEY.md section 7 / 8d "BCP-only figure"): solve the resident batch once with the instrumented kernels while
+ * recording every instance's search prefix (decisions, learnt clauses, restarts up to the first database reduction),
+ * then re-ingest and run the bcp_replay kernel, which re-executes exactly those prefixes with BCP as the only real
+ * work: once with the traffic counters (validation: every replay must reproduce the recorded propagation count and
+ * BCP counters; result: algorithmic BCP bytes) and `reps` times plain, CUDA-event timed. */
+extern "C" int b200sat_engine_bcp_replay(b200sat_engine *e, const b200sat_settings *s, int reps, b200sat_replay_info *out, void *stream_) {
+    if (!e || !out) return set_err(B200SAT_E_ARG, "null argument");
+    memset(out, 0, sizeof *out);
+    if (e->n_inst == 0) return 0;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(cudaSetDevice(e->device));
+    int rc;
+    const u32 cap = 8192;
+    if ((rc = ensure(e->d_trace, e->cap_trace, (size_t)e->n_inst * cap))) return rc;
+    CK(cudaMemsetAsync(e->d_trace, 0, (size_t)e->n_inst * cap * 4, stream));
+    const int base = B200SAT_F_PREPROCESS | B200SAT_F_ZERO_STATS_ON_PRE_UNSAT;
+    e->trace_cap = cap;
+    rc = b200sat_engine_solve(e, s, B200SAT_CORE, base | B200SAT_F_COUNT_TRAFFIC, stream_);
+    e->trace_cap = 0;
+    if (rc) return rc;
+    if (e->resident_items != e->n_inst) return set_err(B200SAT_E_MEM, "bcp_replay needs the whole batch resident at once");
+    /* the record: header of every instance */
+    std::vector<u32> hdr((size_t)e->n_inst * 32);
+    CK(cudaMemcpy2D(hdr.data(), 128, e->d_trace, (size_t)cap * 4, 128, e->n_inst, cudaMemcpyDeviceToHost));
+    u64 want_props = 0, want_t[6] = {0, 0, 0, 0, 0, 0};
+    u32 recorded = 0;
+    for (u32 i = 0; i < e->n_inst; i++) {
+        const u32 *h = hdr.data() + (size_t)i * 32;
+        if (h[TR_WORDS] == 0) continue;
+        recorded++;
+    }
+    std::vector<b200sat_result> res(e->n_inst);
+    float best = 0.f, sum = 0.f;
+    e->trace_cap = cap; /* the replay kernels read the record */
+    for (int rep = 0; rep <= reps; rep++) {
+        e->replay_mode = rep == 0 ? 1 : 2;
+        rc = b200sat_engine_solve(e, s, B200SAT_CORE, base | B200SAT_F_NO_SOLVE | (rep == 0 ? B200SAT_F_COUNT_TRAFFIC : 0), stream_);
+        e->replay_mode = 0;
+        if (rc) { e->trace_cap = 0; return rc; }
+        if (rep == 0) {
+            CK(cudaMemcpy(res.data(), e->d_results, (size_t)e->n_inst * sizeof(b200sat_result), cudaMemcpyDeviceToHost));
+            u64 got_t[6] = {0, 0, 0, 0, 0, 0};
+            for (u32 i = 0; i < e->n_inst; i++) {
+                const u32 *h = hdr.data() + (size_t)i * 32;
+                if (h[TR_WORDS] == 0) continue;
+                if (res[i].status != B200SAT_OK) { out->mismatches++; continue; }
+                const u64 wp = (u64)h[TR_PROPS_LO] | ((u64)h[TR_PROPS_HI] << 32);
+                const u64 wp0 = (u64)h[TR_PROPS0_LO] | ((u64)h[TR_PROPS0_HI] << 32);
+                bool same = res[i].stats[5] == wp;
+                for (int k = 0; k < 6; k++) {
+                    const u64 wt = (u64)h[TR_TRAFFIC + 2 * k] | ((u64)h[TR_TRAFFIC + 2 * k + 1] << 32);
+                    const u64 wt0 = (u64)h[TR_TRAFFIC0 + 2 * k] | ((u64)h[TR_TRAFFIC0 + 2 * k + 1] << 32);
+                    if (res[i].traffic[k] != wt) same = false;
+                    want_t[k] += wt; got_t[k] += res[i].traffic[k] - wt0; /* the replay's own share: ingest-time BCP excluded */
+                }
+                if (!same) out->mismatches++;
+                want_props += wp;
+                out->propagations += wp - wp0;
+            }
+            /* SURVEY.md 8d formula, BCP terms only (items 1-5): watchers visited / kept, clause derefs + tails, moves, implications */
+            out->bcp_bytes = 8 * got_t[0] + 8 * got_t[1] + 4 * got_t[2] + 4 * (2 * got_t[2] + got_t[3]) + 16 * got_t[4] + 12 * got_t[5];
+        } else {
+            const float ms = e->info.search_ms;
+            sum += ms;
+            if (best == 0.f || ms < best) best = ms;
+        }
+    }
+    e->trace_cap = 0;
+    out->instances = recorded;
+    out->ms_min = best;
+    out->ms_avg = reps > 0 ? sum / (float)reps : 0.f;
+    out->warps = e->info.warps_total;
+    return 0;
 }
 
 extern "C" int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out) {

@@ -26,6 +26,8 @@ kernel_fn b200sat_pick_ingest_c1s1(int tier_nv, size_t *smem_per_warp, size_t *s
 kernel_fn b200sat_pick_search_c0(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
 kernel_fn b200sat_pick_search_c1(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
 kernel_fn b200sat_pick_search_pf(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
+kernel_fn b200sat_pick_replay_c0(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
+kernel_fn b200sat_pick_replay_c1(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
 
 #ifdef B200SAT_KERNEL_TU_NAME
 #include <cuda_runtime.h>
@@ -35,8 +37,8 @@ kernel_fn b200sat_pick_search_pf(int tier_nv, size_t *smem_per_warp, size_t *sav
 #include "simp_warp.cuh"
 #endif
 
-#ifndef B200SAT_MINBLOCKS
-#define B200SAT_MINBLOCKS 16
+#ifndef B200SAT_SEARCH_BLOCKS
+#define B200SAT_SEARCH_BLOCKS 32 /* resident one-warp blocks per SM the search kernel is compiled for: 64 registers per thread */
 #endif
 
 namespace b200sat {
@@ -85,13 +87,53 @@ template <bool COUNT, bool SIMP> __global__ void __launch_bounds__(64, 8) ingest
     S.V.s = reinterpret_cast<SmemSmall *>(smem_raw) + warp;
     ingest_loop<SIMP>(S, P);
 }
+#elif B200SAT_KERNEL_TU_PHASE == 2
+/* ---------------------------------------------------------------- K2 bcp_replay: every parked item re-executes the
+ * recorded prefix of its search with BCP as the only real work (measurement kernel for the BCP-only roofline) */
+template <class WS> __device__ __forceinline__ void replay_loop(WS &S, const KParams &P) {
+    for (;;) {
+        u32 w = 0;
+        if (S.lane == 0) w = atomicAdd(P.queue, 1u);
+        w = __shfl_sync(FULL_MASK, w, 0);
+        if (w >= P.n_work) break;
+        w += P.chunk_base;
+        bind_item(S, P, w);
+        if constexpr (WS::VT_GLOBAL) S.V.bind(S.slab + P.L.off_vars, P.L.nv_cap);
+        b200sat_result *r = P.results + S.res_index;
+        if (r->verdict != B200SAT_INTERRUPTED || r->status != B200SAT_OK) continue; /* decided at ingest: nothing was recorded */
+        S.load_state();
+        const bool ok = S.bcp_replay(S.res_index);
+        if (S.lane == 0) {
+            r->status = ok ? B200SAT_OK : -(i32)(100 + ST_INTERNAL);
+            r->stats[5] = S.sc().propagations;
+            for (int i = 0; i < 8; i++) r->traffic[i] = S.sc().traffic[i];
+        }
+        __syncwarp();
+    }
+}
+template <int NV, bool COUNT> __global__ void __launch_bounds__(32, B200SAT_SEARCH_BLOCKS) replay_smem(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSolver<VarsS<NV, false>, COUNT, false> S(P, threadIdx.x);
+    S.V.s = reinterpret_cast<SmemVars<NV, false> *>(smem_raw);
+    replay_loop(S, P);
+}
+template <bool COUNT> __global__ void __launch_bounds__(32, 16) replay_glob(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSolver<VarsG, COUNT, false> S(P, threadIdx.x);
+    S.V.s = reinterpret_cast<SmemSmall *>(smem_raw);
+    replay_loop(S, P);
+}
 #else
 /* ---------------------------------------------------------------- search: pops the work ring until every item is done */
 template <class WS> __device__ __forceinline__ void search_loop_ring(WS &S, const KParams &P) {
+    bool first = true;
     for (;;) {
         u32 w = 0xFFFFFFFFu;
         if (S.lane == 0) {
-            for (;;) {
+            /* the first item of every warp is handed out statically (ring slot = block index, published by the
+             * ingest kernel): thousands of warps popping at once would otherwise serialise on the head word */
+            if (first && blockIdx.x < WS::ld_vol(P.qctl + QC_HEAD0)) w = (u32)*(volatile unsigned long long *)(P.ring + (blockIdx.x & P.ring_mask));
+            else for (;;) {
                 const u32 h = WS::ld_vol(P.qctl + QC_HEAD), t = WS::ld_vol(P.qctl + QC_TAIL);
                 if ((i32)(t - h) > 0) {
                     if (atomicCAS(P.qctl + QC_HEAD, h, h + 1) != h) continue;
@@ -101,11 +143,16 @@ template <class WS> __device__ __forceinline__ void search_loop_ring(WS &S, cons
                     w = (u32)e;
                     break;
                 }
-                if (WS::ld_vol(P.qctl + QC_DONE) >= WS::ld_vol(P.qctl + QC_TOTAL)) break;
-                __nanosleep(1000);
+                /* Empty ring: this warp is done.  Items enter the ring only when a running instance yields, and it
+                 * yields only while the ring is non-empty, so an empty ring stays empty -- except for a yield already
+                 * under way, and the yielding warp pops again right after its push, so no item is ever stranded.
+                 * (Waiting here instead was measured: thousands of idle warps polling the ring took most of the
+                 * issue slots of the SMs that still had work.) */
+                break;
             }
             __threadfence(); /* acquire: also drops this SM's stale L1 lines of the slab (CCTL.IVALL) */
         }
+        first = false;
         w = __shfl_sync(FULL_MASK, w, 0);
         if (w == 0xFFFFFFFFu) break;
         bind_item(S, P, w);
@@ -122,18 +169,18 @@ template <class WS> __device__ __forceinline__ void search_loop_ring(WS &S, cons
         S.count_done();
     }
 }
-template <int NV, bool COUNT, bool PF> __global__ void __launch_bounds__(64, B200SAT_MINBLOCKS) search_smem(const __grid_constant__ KParams P) {
+/* ONE warp per block: the shared-memory base and the lane id are then block constants (no per-warp offset to
+ * rematerialise in the hot loop); 32 blocks per SM = 32 resident warps at 64 registers per thread */
+template <int NV, bool COUNT, bool PF> __global__ void __launch_bounds__(32, B200SAT_SEARCH_BLOCKS) search_smem(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSolver<VarsS<NV, false>, COUNT, PF> S(P, lane);
-    S.V.s = reinterpret_cast<SmemVars<NV, false> *>(smem_raw) + warp;
+    WarpSolver<VarsS<NV, false>, COUNT, PF> S(P, threadIdx.x);
+    S.V.s = reinterpret_cast<SmemVars<NV, false> *>(smem_raw);
     search_loop_ring(S, P);
 }
-template <bool COUNT, bool PF> __global__ void __launch_bounds__(64, 8) search_glob(const __grid_constant__ KParams P) {
+template <bool COUNT, bool PF> __global__ void __launch_bounds__(32, 16) search_glob(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSolver<VarsG, COUNT, PF> S(P, lane);
-    S.V.s = reinterpret_cast<SmemSmall *>(smem_raw) + warp;
+    WarpSolver<VarsG, COUNT, PF> S(P, threadIdx.x);
+    S.V.s = reinterpret_cast<SmemSmall *>(smem_raw);
     search_loop_ring(S, P);
 }
 #endif
@@ -150,6 +197,13 @@ kernel_fn B200SAT_KERNEL_TU_NAME(int tier_nv, size_t *spw, size_t *save) {
     case 256: *spw = sizeof(SmemVars<256, Sp>); *save = SmemSave<256>::BYTES; return ingest_smem<256, C, Sp>;
     case 1024: *spw = sizeof(SmemVars<1024, Sp>); *save = SmemSave<1024>::BYTES; return ingest_smem<1024, C, Sp>;
     default: *spw = sizeof(SmemSmall); *save = sizeof(SmemSmall); return ingest_glob<C, Sp>;
+    }
+#elif B200SAT_KERNEL_TU_PHASE == 2
+    switch (tier_nv) {
+    case 128: *spw = sizeof(SmemVars<128, false>); *save = SmemSave<128>::BYTES; return replay_smem<128, C>;
+    case 256: *spw = sizeof(SmemVars<256, false>); *save = SmemSave<256>::BYTES; return replay_smem<256, C>;
+    case 1024: *spw = sizeof(SmemVars<1024, false>); *save = SmemSave<1024>::BYTES; return replay_smem<1024, C>;
+    default: *spw = sizeof(SmemSmall); *save = sizeof(SmemSmall); return replay_glob<C>;
     }
 #else
     constexpr bool Pf = B200SAT_KERNEL_TU_PF != 0;

@@ -151,12 +151,19 @@ struct KParams {
     u32 slice_conflicts;      /* conflicts an instance may run before it yields to waiting ones (0 = never) */
     long long conflict_budget, propagation_budget; /* budget.rs:5-34; < 0 = none                       */
     const volatile int *interrupt;                 /* device-visible async interrupt flag or NULL      */
+    u32 *trace_buf;           /* K2: per-item event record of the search prefix (instrumented kernel only), or NULL */
+    u32 trace_cap;            /* words per item in trace_buf                                             */
     u32 import_cap;           /* portfolio: clauses one replica imports per restart boundary (0 = no cap) */
     u32 ring_epoch;           /* portfolio: stamps ring entries of this run                             */
 };
-enum : u32 { QC_HEAD = 0, QC_TAIL = 1, QC_DONE = 2, QC_TOTAL = 3, QC_SUSPENDS = 4, QC_WORDS = 8 };
+enum : u32 { QC_HEAD = 0, QC_TAIL = 1, QC_DONE = 2, QC_TOTAL = 3, QC_SUSPENDS = 4, QC_HEAD0 = 5 /* items handed out statically: warp i starts with ring slot i */, QC_WORDS = 8 };
 /* life cycle of a resident instance (Scal::phase) */
 enum : u32 { PH_NEW = 0, PH_READY = 1, PH_SEARCH = 2, PH_DONE = 3 };
+/* K2 event record (bcp_replay): header words, then events: a decision is its literal; a conflict is
+ * TR_CONFLICT | n, bt level, the n learnt literals; a restart is TR_RESTART */
+enum : u32 { TR_WORDS = 0, TR_PROPS_LO = 1, TR_PROPS_HI = 2, TR_TRAFFIC = 4 /* 6 x u64 at the end of the record */,
+             TR_PROPS0_LO = 16, TR_PROPS0_HI = 17, TR_TRAFFIC0 = 18 /* 6 x u64 when the search started */, TR_EVENTS = 32,
+             TR_CONFLICT = 0x80000000u, TR_RESTART = 0xC0000000u };
 
 enum : u32 { PF_SHARE = 1, PF_IGNORE_DONE = 2, PF_SHARE_LBD2 = 4 };
 /* ring header words */

@@ -62,6 +62,7 @@ struct Scal {
     u32 in_loop;                                 /* 1: parked inside a search_loop (confl_limit valid)           */
     u64 confl_limit;                             /* conflict count that ends the current search_loop             */
     double progress;                             /* progress estimate of the last Interrupted return             */
+    u32 rec_n, rec_on;                           /* K2 event record: words used, still recording                 */
 };
 
 /* ------------------------------------------------------------------ var-state tiers */
@@ -1491,6 +1492,9 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
                             tlen = V.wlen()[tgt];
                             over = tlen + __popc(peers) > (1u << (tword & W_CAP_MASK));
                         }
+#ifdef B200SAT_MOVES_LOOP
+                        over = true;
+#endif
                         if (__ballot_sync(FULL_MASK, over)) {
                             qhead = qh; trail_n = tn;
                             if (!push_watch_multi(movemask, mv, tgt, w.x, first)) return CREF_UNDEF;
@@ -1549,6 +1553,106 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
         return confl;
     }
 
+    /* -------------------------------------------------------------- K2: event record of the search prefix + BCP replay
+     * (SURVEY.md section 7 K2 / 8d "BCP-only figure").  The instrumented search kernel records decisions, learnt
+     * clauses with their backtrack levels and restarts until the first database reduction / ground simplification
+     * (or until the buffer is full); bcp_replay() then re-executes exactly that prefix with propagate2() as the only
+     * real work -- the decisions and learnt clauses are read back instead of being computed -- so its run time is
+     * the BCP share of the search and its propagation count must equal the recorded one. */
+    DEV u32 *rec_buf(u32 item) const { return P.trace_buf + (size_t)item * P.trace_cap; }
+    DEV void rec_close(u32 item) { /* lane 0 */
+        if (sc().rec_on) {
+            u32 *tb = rec_buf(item);
+            sc().rec_on = 0;
+            tb[TR_WORDS] = sc().rec_n;
+            tb[TR_PROPS_LO] = (u32)sc().propagations; tb[TR_PROPS_HI] = (u32)(sc().propagations >> 32);
+            for (int i = 0; i < 6; i++) { tb[TR_TRAFFIC + 2 * i] = (u32)sc().traffic[i]; tb[TR_TRAFFIC + 2 * i + 1] = (u32)(sc().traffic[i] >> 32); }
+        }
+    }
+    DEV void rec_stop(u32 item) {
+        if (lane == 0) rec_close(item);
+        __syncwarp();
+    }
+    /* lane 0: reserve `n` event words; closes the record and returns 0 when it is full */
+    DEV u32 *rec_reserve(u32 item, u32 n) {
+        if (!sc().rec_on) return nullptr;
+        if (sc().rec_n + n > P.trace_cap) { rec_close(item); return nullptr; }
+        u32 *w = rec_buf(item) + sc().rec_n;
+        sc().rec_n += n;
+        return w;
+    }
+    DEV bool recording() const { return COUNT && P.trace_buf != nullptr; }
+    /* all lanes call these; lane 0 writes.  `n` = 0 records the final ground-level conflict. */
+    DEV void rec_conflict(u32 n, u32 bt) {
+        if (lane == 0) {
+            u32 *w = rec_reserve(res_index, 2 + n);
+            if (w) { w[0] = TR_CONFLICT | n; w[1] = bt; const u32 *out = ol(); for (u32 i = 0; i < n; i++) w[2 + i] = out[i]; }
+        }
+        __syncwarp();
+    }
+    DEV void rec_word(u32 word) {
+        if (lane == 0) {
+            u32 *w = rec_reserve(res_index, 1);
+            if (w) w[0] = word;
+        }
+        __syncwarp();
+    }
+    DEV bool will_simplify() const { /* the guard of try_simplify(), search.rs:522-530 */
+        return nlevels == 1 && !((sc().simp_db_assigns_set && sc().simp_db_assigns == trail_n) || sc().propagations < sc().simp_db_props);
+    }
+    DEV void cancel_until_light(u32 target_level) { /* assignment.rs:116-130 without the heuristic's callbacks */
+        if (nlevels > target_level) {
+            const u32 target = V.lim()[target_level];
+            for (u32 k = target + lane; k < trail_n; k += 32) V.assign()[V.trail()[k] >> 1] = LB_UNDEF;
+            trail_n = target;
+            nlevels = target_level;
+        }
+        if (qhead > trail_n) qhead = trail_n;
+        __syncwarp();
+    }
+    /* returns false when the replay left the recorded trace (a bug) */
+    DEV bool bcp_replay(u32 item) {
+        const u32 *tb = rec_buf(item);
+        const u32 n_words = tb[TR_WORDS];
+        u32 pos = TR_EVENTS;
+        bool ok = true;
+        u32 confl = propagate2();
+        while (ok && !failed()) {
+            if (pos >= n_words) break; /* end of the record (whether the last propagation conflicts was not recorded) */
+            const bool expect_confl = (tb[pos] & 0xC0000000u) == TR_CONFLICT;
+            if ((confl != CREF_UNDEF) != expect_confl) { ok = false; break; }
+            const u32 ev = tb[pos];
+            if (ev == TR_RESTART) { cancel_until_light(GROUND); pos += 1; }
+            else if (ev & 0x80000000u) {
+                const u32 n = ev & 0x3FFFFFFFu, bt = tb[pos + 1];
+                if (n == 0) break; /* the final ground-level conflict */
+                const u32 *lits = tb + pos + 2;
+                pos += 2 + n;
+                cancel_until_light(bt);
+                u32 reason = CREF_UNDEF;
+                if (n > 1) {
+                    reason = alloc_clause(n, H_LEARNT | H_EXTRA);
+                    if (reason == CREF_UNDEF) break;
+                    for (u32 i = lane; i < n; i += 32) arena[reason + 1 + i] = lits[i];
+                    if (lane == 0) arena[reason + 1 + n] = f2u(0.0f);
+                    __syncwarp();
+                }
+                assign_lit(lits[0], reason);
+                if (reason != CREF_UNDEF && !attach(reason)) break;
+            } else {
+                new_decision_level();
+                assign_lit(ev, CREF_UNDEF);
+                pos += 1;
+            }
+            confl = propagate2();
+        }
+        if (ok && !failed()) {
+            const u64 want = (u64)tb[TR_PROPS_LO] | ((u64)tb[TR_PROPS_HI] << 32);
+            ok = sc().propagations == want;
+        }
+        return ok && !failed();
+    }
+
     /* -------------------------------------------------------------- park / resume (no reference analogue) */
     DEV void save_state() {
         __syncwarp();
@@ -1600,7 +1704,7 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
     }
     DEV bool interrupted_now() {
         u32 v = 0;
-        if (lane == 0 && P.interrupt) v = *P.interrupt != 0 ? 1u : 0u;
+        if (lane == 0 && P.interrupt) v = *P.interrupt != 0 ? 1u : 0u; /* volatile device word */
         return bcast(v) != 0;
     }
 
@@ -1621,6 +1725,12 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
                 sc().curr_restarts = 0;
                 sc().in_loop = 0;
                 sc().phase = PH_SEARCH;
+                if (recording()) {
+                    sc().rec_on = 1; sc().rec_n = TR_EVENTS;
+                    u32 *tb = rec_buf(res_index);
+                    tb[TR_PROPS0_LO] = (u32)sc().propagations; tb[TR_PROPS0_HI] = (u32)(sc().propagations >> 32);
+                    for (int i = 0; i < 6; i++) { tb[TR_TRAFFIC0 + 2 * i] = (u32)sc().traffic[i]; tb[TR_TRAFFIC0 + 2 * i + 1] = (u32)(sc().traffic[i] >> 32); }
+                }
             }
             __syncwarp();
         }
@@ -1644,15 +1754,18 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
             const u64 confl_limit = sc().confl_limit;
             for (;;) {
                 /* propagate_learn_backtrack, search.rs:503-517 + handle_conflict :263-304 */
+                bool had_conflict = false;
                 for (;;) {
                     const u32 confl = propagate2();
                     if (failed()) return SR_ABORT;
                     if (confl == CREF_UNDEF) break;
+                    had_conflict = true;
                     if (lane == 0) sc().conflicts++;
-                    if (nlevels == 1) { __syncwarp(); return SR_UNSAT; }
+                    if (nlevels == 1) { __syncwarp(); if (recording()) { rec_conflict(0, 0); rec_stop(res_index); } return SR_UNSAT; }
                     u32 bt;
                     const u32 n = analyze(confl, bt);
                     if (failed()) return SR_ABORT;
+                    if (recording()) rec_conflict(n, bt);
                     if (PF) {
                         if (P.share & PF_SHARE) export_clause(n);
                         if (cancelled()) { fail(ST_CANCELLED); return SR_ABORT; }
@@ -1692,11 +1805,13 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
                     if (reason != CREF_UNDEF && !attach(reason)) return SR_ABORT;
                 }
                 const u64 nconf = sc().conflicts;
-                /* Budget::within, search.rs:473-477 (budget.rs:21-25) */
-                if (P.conflict_budget >= 0 || P.propagation_budget >= 0 || P.interrupt) {
+                /* Budget::within, search.rs:473-477 (budget.rs:21-25).  The asynchronous-interrupt word lives in
+                 * device memory and is polled after conflicts only (a host-memory poll per decision costs a PCIe
+                 * round trip: measured 28x slower on the n=100 batch). */
+                if (P.conflict_budget >= 0 || P.propagation_budget >= 0 || (had_conflict && P.interrupt)) {
                     const bool out_of = (P.conflict_budget >= 0 && nconf >= (u64)P.conflict_budget) ||
                                         (P.propagation_budget >= 0 && sc().propagations >= (u64)P.propagation_budget) ||
-                                        interrupted_now();
+                                        (had_conflict && interrupted_now());
                     if (out_of) {
                         const double pe = progress_estimate();
                         cancel_until(GROUND);
@@ -1706,6 +1821,7 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
                     }
                 }
                 if (nconf >= confl_limit) { /* search.rs:479-482 */
+                    if (recording()) rec_word(TR_RESTART);
                     cancel_until(GROUND);
                     if (lane == 0) { sc().curr_restarts++; sc().in_loop = 0; }
                     __syncwarp();
@@ -1715,15 +1831,18 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
                     if (others_waiting()) return SR_SUSPEND;
                     slice_end = nconf + P.slice_conflicts;
                 }
+                if (recording() && will_simplify()) rec_stop(res_index);
                 try_simplify();
                 if ((double)sc().n_learnts >= sc().max_learnts + (double)trail_n) {
+                    if (recording()) rec_stop(res_index);
                     reduce_db();
                     if (failed()) return SR_ABORT;
                     try_garbage_collect();
                 }
                 if (lane == 0) sc().decisions++;
                 const u32 next = pick_branch_lit();
-                if (next == LIT_NONE) return SR_SAT;
+                if (next == LIT_NONE) { if (recording()) rec_stop(res_index); return SR_SAT; }
+                if (recording()) rec_word(next);
                 new_decision_level();
                 assign_lit(next, CREF_UNDEF);
             }
@@ -1861,7 +1980,7 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
             for (int i = 0; i < 8; i++) s.ring_cursor[i] = 0;
             s.exported = 0; s.imported = 0;
             s.phase = PH_NEW; s.curr_restarts = 0; s.in_loop = 0; s.confl_limit = 0; s.progress = 0.0;
-            s.n_ingest = s.n_pre = 0; s.pre_ok = 1;
+            s.n_ingest = s.n_pre = 0; s.pre_ok = 1; s.rec_n = TR_EVENTS; s.rec_on = 0;
         }
         arena = arena_half(0);
         wpool = wpool_half(0);

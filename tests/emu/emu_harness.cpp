@@ -150,6 +150,19 @@ template <class WS> void search_one(WS &S, Job *j) {
     if (S.lane == 0) j->suspended = 0;
 }
 
+/* the body of replay_loop (cdcl_kernels.cuh) for one parked item */
+template <class WS> void replay_one(WS &S, Job *j) {
+    bind_job(S, j);
+    S.load_state();
+    const bool ok = S.bcp_replay(S.res_index);
+    if (S.lane == 0) {
+        b200sat_result *r = j->P.results + S.res_index;
+        r->status = ok ? B200SAT_OK : -(i32)(100 + ST_INTERNAL);
+        r->stats[5] = S.sc().propagations;
+        for (int i = 0; i < 8; i++) r->traffic[i] = S.sc().traffic[i];
+    }
+}
+
 template <int NV, bool COUNT, bool PF> void entry_s(void *user, int lane) {
     Job *j = (Job *)user;
     if (j->phase == 0) {
@@ -166,6 +179,7 @@ template <int NV, bool COUNT, bool PF> void entry_s(void *user, int lane) {
     }
     WarpSolver<VarsS<NV>, COUNT, PF> S(j->P, (u32)lane);
     S.V.s = (SmemVars<NV> *)j->smem;
+    if (j->phase == 2) { replay_one(S, j); return; }
     search_one(S, j);
 }
 template <bool COUNT, bool PF> void entry_g(void *user, int lane) {
@@ -180,6 +194,7 @@ template <bool COUNT, bool PF> void entry_g(void *user, int lane) {
     WarpSolver<VarsG, COUNT, PF> S(j->P, (u32)lane);
     S.V.s = (SmemSmall *)j->smem;
     S.V.bind(j->P.slabs + j->P.L.off_vars, j->P.L.nv_cap);
+    if (j->phase == 2) { replay_one(S, j); return; }
     search_one(S, j);
 }
 
@@ -331,5 +346,59 @@ int emu_solve_batch(const uint32_t *inst_clause_off, const uint32_t *clause_off,
         todo.swap(again);
     }
     return (int)n_suspends;
+}
+
+/* K2 under the emulator: record the search prefix of every instance (instrumented kernels), ingest again, replay.
+ * out[i] = {recorded words, replay ok, recorded propagations, replayed propagations, recorded BCP traffic equal}. */
+int emu_bcp_replay(const uint32_t *inst_clause_off, const uint32_t *clause_off, const uint32_t *lits, uint32_t n_inst,
+                   const b200sat_settings *st, int tier_nv, uint32_t trace_cap, uint64_t sched_seed, uint64_t *out) {
+    BatchShape sh = {0, 0, 0, 0};
+    for (u32 i = 0; i < n_inst; i++) {
+        u32 cb = inst_clause_off[i], ce = inst_clause_off[i + 1];
+        if (ce - cb > sh.max_clauses) sh.max_clauses = ce - cb;
+        u64 nl = clause_off[ce] - clause_off[cb];
+        if (nl > sh.max_lits) sh.max_lits = nl;
+        for (u32 c = cb; c < ce; c++) { u32 len = clause_off[c + 1] - clause_off[c]; if (len > sh.max_clause_len) sh.max_clause_len = len; }
+        for (u32 k = clause_off[cb]; k < clause_off[ce]; k++) if ((lits[k] >> 1) + 1 > sh.max_vars) sh.max_vars = (lits[k] >> 1) + 1;
+    }
+    if (tier_nv < 0) tier_nv = pick_tier_nv(sh.max_vars, sh.max_clauses);
+    Layout L = plan_layout(sh, tier_nv, B200SAT_CORE, 1, 0, 0, save_bytes_of(tier_nv));
+    std::vector<u64> slab((L.slab_bytes + 7) / 8 + 2), smem(32 * 1024);
+    std::vector<u32> trace((size_t)n_inst * trace_cap, 0);
+    std::vector<b200sat_result> res(n_inst);
+    u32 queue = 0;
+    Job j;
+    memset(&j.P, 0, sizeof j.P);
+    j.P.inst_clause_off = inst_clause_off; j.P.clause_off = clause_off; j.P.lits = lits;
+    j.P.n_work = n_inst; j.P.queue = &queue; j.P.results = res.data();
+    j.P.slabs = (u8 *)slab.data(); j.P.L = L; j.P.st = *st; j.P.kind = B200SAT_CORE; j.P.attempt = 2;
+    j.P.conflict_budget = -1; j.P.propagation_budget = -1;
+    j.P.trace_buf = trace.data(); j.P.trace_cap = trace_cap;
+    j.smem = smem.data(); j.tier_nv = tier_nv; j.count = true;
+    void (*fn)(void *, int) = pick_entry<false>(tier_nv, true);
+    for (u32 i = 0; i < n_inst; i++) {
+        j.inst = i;
+        j.P.flags = B200SAT_F_PREPROCESS | B200SAT_F_COUNT_TRAFFIC;
+        run_item<false>(j, sched_seed ? sched_seed + i : 0, nullptr);        /* records */
+        const u32 *tb = trace.data() + (size_t)i * trace_cap;
+        out[5 * i + 0] = tb[TR_WORDS];
+        out[5 * i + 2] = (u64)tb[TR_PROPS_LO] | ((u64)tb[TR_PROPS_HI] << 32);
+        out[5 * i + 1] = 0; out[5 * i + 3] = 0; out[5 * i + 4] = 0;
+        if (tb[TR_WORDS] == 0) continue;
+        j.P.flags = B200SAT_F_PREPROCESS | B200SAT_F_COUNT_TRAFFIC | B200SAT_F_NO_SOLVE;
+        j.phase = 0; j.runnable = 0;
+        simt::run_warp(fn, &j, sched_seed ? sched_seed + 5 * i : 0);          /* ingest again: parked, not searched */
+        j.phase = 2;
+        simt::run_warp(fn, &j, sched_seed ? sched_seed + 7 * i : 0);          /* replay */
+        out[5 * i + 1] = res[i].status == B200SAT_OK ? 1 : 0;
+        out[5 * i + 3] = res[i].stats[5];
+        bool same = true;
+        for (int k = 0; k < 6; k++) {
+            const u64 wt = (u64)tb[TR_TRAFFIC + 2 * k] | ((u64)tb[TR_TRAFFIC + 2 * k + 1] << 32);
+            if (res[i].traffic[k] != wt) same = false;
+        }
+        out[5 * i + 4] = same ? 1 : 0;
+    }
+    return 0;
 }
 }

@@ -59,6 +59,9 @@ def lib():
         L.emu_portfolio.argtypes = [u32p, u32p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64,
                                     C.POINTER(Result), C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32]
         L.emu_portfolio.restype = C.c_int
+        L.emu_bcp_replay.argtypes = [u32p, u32p, u32p, C.c_uint32, C.c_void_p, C.c_int, C.c_uint32, C.c_uint64,
+                                     C.POINTER(C.c_uint64)]
+        L.emu_bcp_replay.restype = C.c_int
         _lib = L
     return _lib
 
@@ -102,3 +105,16 @@ def portfolio(clause_off, lits, settings, n_replicas, share=1, flags=8, sched_se
     lib().emu_portfolio(offp, lip, len(off) - 1, C.addressof(settings), n_replicas, share, flags, sched_seed, res,
                         models.ctypes.data_as(C.POINTER(C.c_uint8)), model_stride, import_cap)
     return res, models
+
+
+def bcp_replay(inst_clause_off, clause_off, lits, settings, tier_nv=-1, trace_cap=8192, sched_seed=0):
+    """K2 under the emulator: rows of (recorded words, replay ok, recorded propagations, replayed propagations,
+    BCP traffic counters equal) per instance."""
+    ioff, ioffp = _u32(inst_clause_off)
+    off, offp = _u32(clause_off)
+    li, lip = _u32(lits)
+    n = len(ioff) - 1
+    out = np.zeros((n, 5), dtype=np.uint64)
+    lib().emu_bcp_replay(ioffp, offp, lip, n, C.addressof(settings), tier_nv, trace_cap, sched_seed,
+                         out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    return out

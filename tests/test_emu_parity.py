@@ -247,3 +247,19 @@ def test_budget_interrupts_and_the_solver_resumes(po, emu, kind):
             assert list(e.stats) == list(o.stats) and e.trace_hash == o.trace_hash
             if o.verdict == 1:
                 assert (a[:o.n_vars] == b[:o.n_vars]).all()
+
+
+def test_bcp_replay_reproduces_the_recorded_prefix(po, emu):
+    """K2 (SURVEY.md 8d BCP-only figure): the replay of the recorded decisions / learnt clauses / restarts of a
+    search prefix makes exactly the recorded number of propagations with exactly the recorded BCP traffic."""
+    ioff, coff, lits = synth_batch(po, SEED2 + 9200, 8, 60, 256)
+    st = po.default_settings()
+    st.restart_first = 15.0
+    for cap in (8192, 300):   # a full prefix (up to the first reduceDB / end of search) and a record that fills up
+        out = emu.bcp_replay(ioff, coff, lits, st, trace_cap=cap, sched_seed=21)
+        assert (out[:, 0] > 0).sum() >= 6
+        for words, ok, rec_p, got_p, same in out:
+            if words == 0:
+                continue
+            assert ok == 1 and rec_p == got_p and same == 1
+            assert words <= cap
