@@ -45,12 +45,33 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline", type=int, default=3, help="batches in flight (engines/streams); 1 = strictly serial steps")
+    ap.add_argument("--config3", type=int, default=-1,
+                    help="instances per GPU of the bounded config-3 (n=250) sub-record; -1 = 2368 when --gpus > 1 else off")
+    ap.add_argument("--no-bcp-replay", action="store_true")
     return ap.parse_args()
 
 
 def workload_name(a, m):
     return "uniform random 3-SAT batch: %d instances/GPU, n=%d, m=%d (ratio %.2f), %s solver" % (
         a.instances, a.nvars, m, a.ratio, "CoreSolver (--core)" if a.solver == "core" else "SimpSolver (default)")
+
+
+def shared_config(a, m):
+    """`config` of the JSON line: identical keys and values in both arms (b200 and --impl reference)."""
+    return {"workload": workload_name(a, m), "instances_per_gpu": a.instances, "n_vars": a.nvars, "n_clauses": m,
+            "seed_base": hex(SEED_BASE), "solver": a.solver,
+            "l2": "256 MiB memset between steps (L2 flush); the batch (51 MB CSR + 8.5 GB of per-instance slabs) exceeds L2"}
+
+
+def load_oracle():
+    """The oracle for the CPU legs: rebuilt on THIS host with -O3 -march=native (-flto where the image has it),
+    SURVEY.md 8d; falls back to the portable build that travels with the repo."""
+    from oracle import pyoracle as po
+    try:
+        po.use_native()
+    except Exception:
+        po.build()
+    return po
 
 
 class ClockSampler(threading.Thread):
@@ -100,6 +121,7 @@ def oracle_sample_rate(po, n, m, kind, n_sample, threads, seed0):
     ioff = np.arange(0, n_sample + 1, dtype=np.uint32) * m
     res, _, secs = po.solve_batch(ioff, coff, lits, kind=kind, threads=threads)
     props = sum(int(r.stats[5]) for r in res)
+    oracle_sample_rate.last = res
     return n_sample / secs, props / secs, secs
 
 
@@ -108,8 +130,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import pyoracle as po
-    po.build()
+    po = load_oracle()
     m = int(round(a.ratio * a.nvars))
     kind = po.CORE if a.solver == "core" else po.SIMP
     cores = cpu_cores()
@@ -131,10 +152,12 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(a, m), "sample": sample,
-                   "note": "reference arm = C++ oracle port of minisat-rust (Rust toolchain absent); CPU only"},
+        "config": shared_config(a, m),
+        "details": {"sample": sample, "oracle_build": po.build_info(),
+                    "note": "reference arm = C++ oracle port of minisat-rust (Rust toolchain absent); CPU only"},
         "propagations_per_sec": p_tot / t_tot,
-        "cpu_baseline": {"value": value, "unit": "instances/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "instances/s", "cores": cores, "kind": "port", "sample": sample,
+                         "build": po.build_info()},
         "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -199,14 +222,14 @@ def main():
             e, st = engs[k % NS], streams[k % NS]
             if k >= NS:
                 e.finish()
-                li = e.launch_info(); kms += li["last_kernel_ms"]; nl += 2 * li["launches"]
+                li = e.launch_info(); kms += li["search_ms"]; nl += li["launches"] + 3
             flush.zero_()                       # L2 flush between steps (256 MiB > 126 MB L2), on the main stream
             st.wait_stream(main_stream)
             e.solve_async(kind=kind, flags=flags, stream=st.cuda_stream)
         for k in range(min(NS, k_steps)):
             e = engs[k]
             e.finish()
-            li = e.launch_info(); kms += li["last_kernel_ms"]; nl += 2 * li["launches"]
+            li = e.launch_info(); kms += li["search_ms"]; nl += li["launches"] + 3
         for st in streams:
             main_stream.wait_stream(st)
         return kms, nl
@@ -216,7 +239,8 @@ def main():
     # one un-overlapped launch for the per-launch duration the roofline is quoted on
     torch.cuda.synchronize()
     eng.solve(kind=kind, flags=flags, stream=sptr)
-    solo_ms = eng.launch_info()["last_kernel_ms"]
+    solo_info = eng.launch_info()
+    solo_ms = solo_info["search_ms"]
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -267,6 +291,34 @@ def main():
         assert (o[2]["stats"] == res_c["stats"]).all()
         assert (o[2]["verdict"] == res_c["verdict"]).all()
 
+    # ---- K2: BCP-only replay of the recorded search prefixes (SURVEY.md 8d "BCP-only figure"), rank 0, untimed region
+    bcp = None
+    if rank == 0 and a.solver == "core" and not a.no_bcp_replay:
+        bcp = eng.bcp_replay(reps=3, stream=sptr)
+
+    # ---- bounded config-3 sub-record (BASELINE.json configs[2] shape: n=250, m=1065): every rank solves a slice of the
+    # 100k batch under a conflict budget, so it finishes in seconds; the full-size run is tools/config3_run.py
+    c3 = None
+    c3_n = a.config3 if a.config3 >= 0 else (2368 if world > 1 else 0)
+    if c3_n > 0:
+        e3 = engs[-1]
+        e3.generate_ksat(0x5EED000100000000 + rank * c3_n, c3_n, 250, 1065, 3, stream=sptr)
+        e3.set_budget(conflict_budget=20000)
+        for _ in range(2):
+            e3.solve(kind=pkg.CORE, flags=flags, stream=sptr)
+        e3.set_budget()
+        li3 = e3.launch_info()
+        r3, _ = e3.download(want_models=False)
+        c3 = [float(li3["last_kernel_ms"]), float(r3["stats"][:, 5].sum()), float(r3["stats"][:, 4].sum()),
+              float((r3["verdict"] != pkg.INTERRUPTED).sum()), float((r3["status"] != 0).sum())]
+        t3 = torch.tensor(c3, dtype=torch.float64, device="cuda")
+        if dist is not None:
+            g3 = [t3.clone() for _ in range(world)]
+            dist.all_gather(g3, t3)
+            c3 = [[float(x) for x in g.tolist()] for g in g3]
+        else:
+            c3 = [c3]
+
     # ---- max over ranks
     tt = torch.tensor([dev_ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device="cuda")
     agg = torch.tensor([props, alg_bytes, confl], dtype=torch.float64, device="cuda")
@@ -284,11 +336,14 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        traffic = None
+        traffic, traffic_src = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             if a.solver == "core" and n == 100 and B == 10000:
-                traffic = float(tj["dram_bytes_per_launch"])   # from the committed ncu --set full capture of this workload
+                # NOT measured in this run (ncu cannot run inside the bench): the committed `ncu --set full` capture of
+                # this exact workload and kernel; `traffic_static` says where it came from
+                traffic = float(tj["dram_bytes_per_launch"])
+                traffic_src = {"static": True, "capture": tj.get("capture"), "kernel": tj.get("kernel"), "commit": tj.get("commit")}
         except Exception:
             pass
         value = world * B * a.steps / (dev_ms * 1e-3)
@@ -301,34 +356,57 @@ def main():
             "metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(a, m), "instances_per_gpu": B, "n_vars": n, "n_clauses": m,
-                       "seed_base": hex(SEED_BASE), "l2": "256 MiB memset between steps (L2 flush)",
-                       "pipeline": "%d batches in flight on %d engines/streams" % (NS, NS),
-                       "satisfiable": n_sat, "launch": info},
+            "config": shared_config(a, m),
+            "details": {"pipeline": "%d batches in flight on %d engines/streams" % (NS, NS), "satisfiable": n_sat,
+                        "launch": info, "solo_launch": solo_info},
             "propagations_per_sec": props_all * a.steps / (dev_ms * 1e-3),
             "conflicts_per_sec": confl_all * a.steps / (dev_ms * 1e-3),
             "e2e": {"value": world * B * a.steps / (e2e_ms * 1e-3), "unit": "instances/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "cdcl_warp_smem", "launches_in_flight": NS,
+                         "traffic": traffic, "traffic_static": traffic_src, "kernel": "search_smem<128,0,0>", "launches_in_flight": NS,
                          "kernel_ms_per_launch_overlapped": k_ms, "kernel_ms_per_launch_solo": solo_ms,
                          "achieved_solo_launch": alg_bytes / (solo_ms * 1e-3) / 1e9,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_propagation": alg_bytes / max(props, 1.0),
                          "peak_source": peak_src},
             "clocks": sampler.summary(),
         }
+        if bcp is not None:
+            # BCP only: the replay kernel re-executes the recorded prefixes (up to the first reduceDB) with unit
+            # propagation as the only real work; bytes = SURVEY.md 8d terms (1)-(5) of exactly those prefixes
+            bsec = bcp["ms_min"] * 1e-3
+            line["roofline"]["bcp_only"] = {
+                "achieved": bcp["bcp_bytes"] / bsec / 1e9 if bsec > 0 else None, "unit": "GB/s",
+                "frac": bcp["bcp_bytes"] / bsec / 1e9 / peak if bsec > 0 else None,
+                "kernel": "replay_smem<128,0>", "kernel_ms": bcp["ms_min"], "kernel_ms_avg": bcp["ms_avg"],
+                "algorithmic_bytes": bcp["bcp_bytes"], "propagations": bcp["propagations"],
+                "propagations_per_sec": bcp["propagations"] / bsec if bsec > 0 else None,
+                "instances": bcp["instances"], "replay_mismatches": bcp["mismatches"], "dram_bytes": None,
+                "note": "dram_bytes: see profiles/ (ncu capture of replay_smem); mismatches must be 0"}
+            assert bcp["mismatches"] == 0, "bcp_replay left the recorded trace"
+        if c3 is not None:
+            ms3 = max(x[0] for x in c3)
+            line["config3"] = {
+                "workload": "uniform random 3-SAT n=250 m=1065 (BASELINE.json configs[2] shape), %d instances/GPU, "
+                            "conflict budget 20000 per instance (bounded slice; full size: tools/config3_run.py, profiles/r02_config3_*.json)" % c3_n,
+                "ms": ms3, "propagations_per_sec": sum(x[1] for x in c3) / ms3 * 1e3,
+                "conflicts_per_sec": sum(x[2] for x in c3) / ms3 * 1e3, "decided_within_budget": int(sum(x[3] for x in c3)),
+                "instances": c3_n * world, "failed": int(sum(x[4] for x in c3))}
         if not a.no_cpu_baseline:
-            from oracle import pyoracle as po
-            po.build()
+            po = load_oracle()
             cores = cpu_cores()
             okind = po.CORE if a.solver == "core" else po.SIMP
             r0, _, _ = oracle_sample_rate(po, n, m, okind, max(2 * cores, 16), cores, SEED_BASE)
             ns = a.cpu_sample or int(max(cores, min(B, r0 * 12.0)))
             r, p, secs = oracle_sample_rate(po, n, m, okind, ns, cores, SEED_BASE)
+            ores = oracle_sample_rate.last
+            same = all(list(res_c[i]["stats"]) == list(ores[i].stats) and int(res_c[i]["verdict"]) == ores[i].verdict for i in range(ns))
+            assert same, "oracle sample and device disagree on verdict / stats"
             line["cpu_baseline"] = {"value": r, "unit": "instances/s", "cores": cores, "kind": "port",
                                     "sample": "first %d instances of the same batch, %d threads, %.1f s" % (ns, cores, secs),
-                                    "propagations_per_sec": p}
+                                    "propagations_per_sec": p, "build": po.build_info(),
+                                    "verdicts_and_stats_equal_device": bool(same)}
         print(json.dumps(line), flush=True)
     for e in engs:
         e.close()

@@ -236,6 +236,10 @@ typedef struct b200sat_launch_info {
     float    search_ms;        /* CUDA-event time of the search kernel(s) alone (first chunk of each attempt) */
     uint32_t suspends;         /* times an instance was parked at the end of a conflict slice and re-queued */
     uint32_t resident_items;   /* instances whose state is resident at once (slabs allocated) */
+    float    tail_ms;          /* search kernel: time between the first warp that found the work ring empty and the
+                                  last warp's exit (device %globaltimer) -- the part of the launch that is bound by
+                                  its longest-running instances */
+    float    span_ms;          /* search kernel: first block's start to last warp's exit (device %globaltimer) */
 } b200sat_launch_info;
 int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out);
 

@@ -91,7 +91,8 @@ class LaunchInfo(C.Structure):
     _fields_ = [("grid", C.c_uint32), ("block", C.c_uint32), ("smem_bytes", C.c_uint32),
                 ("warps_total", C.c_uint32), ("tier", C.c_uint32), ("launches", C.c_uint32),
                 ("slab_bytes", C.c_uint64), ("last_kernel_ms", C.c_float), ("search_ms", C.c_float),
-                ("suspends", C.c_uint32), ("resident_items", C.c_uint32)]
+                ("suspends", C.c_uint32), ("resident_items", C.c_uint32), ("tail_ms", C.c_float),
+                ("span_ms", C.c_float)]
 
 
 class ReplayInfo(C.Structure):

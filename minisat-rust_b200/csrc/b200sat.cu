@@ -593,7 +593,7 @@ extern "C" int b200sat_engine_solve_async(b200sat_engine *e, const b200sat_setti
     if (e->pend.active) { rc = b200sat_engine_finish(e); if (rc && rc != B200SAT_E_MEM) return rc; }
     CK(cudaSetDevice(e->device));
     e->info.launches = 0;
-    e->info.last_kernel_ms = 0.f; e->info.search_ms = 0.f; e->info.suspends = 0;
+    e->info.last_kernel_ms = 0.f; e->info.search_ms = 0.f; e->info.suspends = 0; e->info.tail_ms = 0.f; e->info.span_ms = 0.f;
     b200sat_engine::Pending &pd = e->pend;
     pd.stream = (cudaStream_t)stream_;
     if (e->n_inst == 0) return 0;
@@ -621,6 +621,11 @@ extern "C" int b200sat_engine_finish(b200sat_engine *e) {
         pd.total_ms += ms;
         if (pd.searched) { CK(cudaEventElapsedTime(&ms, e->ev2, e->ev3)); pd.search_ms += ms; }
         e->info.suspends += e->h_pinned[32 + QC_SUSPENDS];
+        if (pd.searched && !e->replay_mode) { /* time from the moment the work ring ran dry to the last warp's exit */
+            const unsigned long long *tq = (const unsigned long long *)(e->h_pinned + 32 + QC_T_START);
+            const unsigned long long t0 = tq[0], td = tq[1], t1 = tq[2];
+            if (t1 > t0 && td >= t0) { e->info.tail_ms = (float)((double)(t1 - td) * 1e-6); e->info.span_ms = (float)((double)(t1 - t0) * 1e-6); }
+        }
         u32 left = e->h_pinned[0];
         if (left == 0 || pd.attempt >= 4) { pd.n_work = left; break; }
         pd.retried = true;

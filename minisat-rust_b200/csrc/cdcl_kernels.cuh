@@ -43,6 +43,12 @@ kernel_fn b200sat_pick_replay_c1(int tier_nv, size_t *smem_per_warp, size_t *sav
 
 namespace b200sat {
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 template <class WS> __device__ __forceinline__ void bind_item(WS &S, const KParams &P, u32 w) {
     S.slab = P.slabs + (size_t)(w - P.chunk_base) * P.L.slab_bytes;
     S.res_index = P.work ? P.work[w] : w;
@@ -127,6 +133,9 @@ template <bool COUNT> __global__ void __launch_bounds__(32, 16) replay_glob(cons
 /* ---------------------------------------------------------------- search: pops the work ring until every item is done */
 template <class WS> __device__ __forceinline__ void search_loop_ring(WS &S, const KParams &P) {
     bool first = true;
+#ifndef B200SAT_EMU
+    if (S.lane == 0 && blockIdx.x == 0) *(volatile unsigned long long *)(P.qctl + QC_T_START) = global_timer_ns();
+#endif
     for (;;) {
         u32 w = 0xFFFFFFFFu;
         if (S.lane == 0) {
@@ -154,7 +163,16 @@ template <class WS> __device__ __forceinline__ void search_loop_ring(WS &S, cons
         }
         first = false;
         w = __shfl_sync(FULL_MASK, w, 0);
-        if (w == 0xFFFFFFFFu) break;
+        if (w == 0xFFFFFFFFu) {
+#ifndef B200SAT_EMU
+            if (S.lane == 0) { /* tail accounting: when the ring first ran dry, when the last warp left */
+                const unsigned long long t = global_timer_ns();
+                atomicCAS((unsigned long long *)(P.qctl + QC_T_DRAIN), 0ull, t);
+                atomicMax((unsigned long long *)(P.qctl + QC_T_END), t);
+            }
+#endif
+            break;
+        }
         bind_item(S, P, w);
         if constexpr (WS::VT_GLOBAL) S.V.bind(S.slab + P.L.off_vars, P.L.nv_cap);
         S.load_state();

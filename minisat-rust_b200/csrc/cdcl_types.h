@@ -156,7 +156,9 @@ struct KParams {
     u32 import_cap;           /* portfolio: clauses one replica imports per restart boundary (0 = no cap) */
     u32 ring_epoch;           /* portfolio: stamps ring entries of this run                             */
 };
-enum : u32 { QC_HEAD = 0, QC_TAIL = 1, QC_DONE = 2, QC_TOTAL = 3, QC_SUSPENDS = 4, QC_HEAD0 = 5 /* items handed out statically: warp i starts with ring slot i */, QC_WORDS = 8 };
+enum : u32 { QC_HEAD = 0, QC_TAIL = 1, QC_DONE = 2, QC_TOTAL = 3, QC_SUSPENDS = 4, QC_HEAD0 = 5 /* items handed out statically: warp i starts with ring slot i */,
+             QC_T_START = 8, QC_T_DRAIN = 10, QC_T_END = 12 /* u64 %globaltimer ns: search kernel start, first warp that found the
+                                                              ring empty, last warp exit */, QC_WORDS = 16 };
 /* life cycle of a resident instance (Scal::phase) */
 enum : u32 { PH_NEW = 0, PH_READY = 1, PH_SEARCH = 2, PH_DONE = 3 };
 /* K2 event record (bcp_replay): header words, then events: a decision is its literal; a conflict is

@@ -1380,35 +1380,28 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
             uint2 *ws = wpool + (word >> W_SHIFT);
             u32 j = 0, i = 0;
             for (; i < n; i += 32) {
+                /* Evaluation is written branch-free (safe addresses + selects): on sm_100a every lane-divergent `if`
+                 * costs a BSSY / BRA / BSYNC triple plus register moves -- 43 % of the executed instructions of the
+                 * first version of this function were such control overhead (profiles/r02_ncu_search_c.md). */
                 const u32 idx = i + lane;
                 const bool valid = idx < n;
-                uint2 w = make_uint2(0, 0);
-                if (valid) w = ws[idx];
-                uint4 hd = make_uint4(0, 0, 0, 0);
+                const uint2 w = ws[valid ? idx : i];
                 /* a blocker that is true now stays true for the whole call: such lanes never need their clause */
                 const bool need = valid && (dirty || !is_true(w.y));
-                if (need) hd = ld4(ar + w.x);
+                const uint4 hd = ld4(ar + (need ? w.x : 0u));
                 const bool live = valid && !(dirty && (hd.x & H_DELETED));
+                const bool len3 = need && hd.x >= (3u << H_SHIFT);
+                const u32 first = need ? ((hd.y == not_p) ? hd.z : hd.y) : 0u;
+                const u32 third = len3 ? hd.w : 0u;
                 u32 kf = 2, lbase = 0;
                 for (;;) {
                     const bool pend = live && lane >= lbase;
-                    u32 out = OUT_NONE, first = 0, lk = 0;
-                    bool scan = false;
-                    if (pend) {
-                        out = OUT_KEEPW;
-                        if (!is_true(w.y)) {
-                            first = (hd.y == not_p) ? hd.z : hd.y;
-                            const u32 fv = lval(first);
-                            out = OUT_KEEPCW;
-                            if (fv != 1) {
-                                out = (fv == 0) ? OUT_CONFL : OUT_UNIT;
-                                if (hd.x >= (3u << H_SHIFT)) {
-                                    if (kf == 2 && !is_false(hd.w)) { lk = hd.w; out = OUT_MOVE; }
-                                    else scan = hd.x >= (4u << H_SHIFT);
-                                }
-                            }
-                        }
-                    }
+                    const u32 bv = lval(w.y), fv = lval(first), tv = lval(third);
+                    const bool can_move = len3 && kf == 2 && tv != 0;
+                    u32 out = bv == 1 ? OUT_KEEPW : fv == 1 ? OUT_KEEPCW : can_move ? OUT_MOVE : fv == 0 ? OUT_CONFL : OUT_UNIT;
+                    if (!pend) out = OUT_NONE;
+                    u32 lk = third;
+                    const bool scan = out >= OUT_UNIT && hd.x >= (4u << H_SHIFT);
                     if (__ballot_sync(FULL_MASK, scan)) {
                         /* clauses longer than three literals whose third literal is false: 128-bit tail scan */
                         if (scan) {

@@ -69,14 +69,55 @@ def build(force=False):
 
 
 _lib = None
+_NATIVE_PATH = os.path.join(_HERE, "_native", "liboracle_native.so")
+_use_native = False
+_native_flags = ""
+
+
+def build_native():
+    """CPU-baseline build for THIS machine: -O3 -march=native -flto (mirrors the reference's opt-level=3, lto=true,
+    Cargo.toml:28-31).  Kept apart from the portable liboracle.so that travels with the repo."""
+    src = os.path.join(_HERE, "oracle.cpp")
+    if os.path.exists(_NATIVE_PATH) and os.path.getmtime(_NATIVE_PATH) >= os.path.getmtime(src):
+        return _NATIVE_PATH
+    os.makedirs(os.path.dirname(_NATIVE_PATH), exist_ok=True)
+    global _native_flags
+    for lto in (["-flto"], []):   # the oracle is ONE translation unit, so -flto changes nothing; some images lack lto-wrapper
+        cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O3", "-march=native"] + lto + [
+            "-ffp-contract=off", "-fPIC", "-shared", "-o", _NATIVE_PATH, src, "-lz", "-lpthread"]
+        if subprocess.run(cmd, capture_output=True).returncode == 0:
+            _native_flags = "-O3 -march=native" + (" -flto" if lto else " (single translation unit; -flto unavailable in this image)")
+            open(_NATIVE_PATH + ".flags", "w").write(_native_flags)
+            return _NATIVE_PATH
+    raise RuntimeError("native oracle build failed")
+
+
+def use_native():
+    """Switch this process to the -march=native -flto build (compiled here on first use).  Must be called before
+    the first oracle call; raises when the compiler is missing or fails (callers fall back to the portable build)."""
+    global _use_native, _lib
+    if _lib is not None and not _use_native:
+        raise RuntimeError("oracle library already loaded")
+    build_native()
+    _use_native = True
+
+
+def build_info():
+    if _use_native:
+        try:
+            fl = open(_NATIVE_PATH + ".flags").read()
+        except Exception:
+            fl = "-O3 -march=native"
+        return "g++ %s -ffp-contract=off, built on this host" % fl
+    return "g++ -O3 -march=x86-64-v2 -ffp-contract=off (portable build)"
 
 
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
+        if not _use_native and not os.path.exists(_LIB_PATH):
             build()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(_NATIVE_PATH if _use_native else _LIB_PATH)
         u32p = C.POINTER(C.c_uint32)
         L.oracle_default_settings.argtypes = [C.POINTER(Settings)]
         L.oracle_solve_csr.argtypes = [u32p, u32p, C.c_uint32, C.POINTER(Settings), C.c_int, C.c_int,

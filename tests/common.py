@@ -82,3 +82,15 @@ def check_models(ioff, coff, lits, verdicts, models):
     np.logical_or.at(sat_clause, clause_of_lit, lit_true)
     bad = (~sat_clause) & (verdicts[inst_of_clause] == 1)
     return int(bad.sum())
+
+
+# tests/golden/hand_traces.md: stats derived BY HAND from the Rust source (not from oracle.cpp) for five tiny formulas.
+# name -> (clauses, solver kind (0 core / 1 simp), settings overrides, verdict, 8 stats, model (0/1 per var) or None,
+#          eliminated_vars, n_clauses after preprocessing)
+HAND_TRACES = {
+    "H1_unit_chain": ([[1], [-1, 2], [-2, 3]], 0, {}, 1, [1, 1, 1, 0, 0, 3, 0, 0], [1, 1, 1], 0, 0),
+    "H2_two_conflicts_unsat": ([[1, 2], [1, -2], [-1, 2], [-1, -2]], 0, {}, 0, [1, 1, 1, 0, 2, 2, 1, 0], None, 0, 4),
+    "H3_binary_learnt": ([[1, 3, 2], [1, 3, -2]], 0, {}, 1, [1, 1, 4, 0, 1, 4, 2, 0], [0, 1, 1], 0, 2),
+    "H4_luby_restart": ([[1, 3, 2], [1, 3, -2]], 0, {"restart_first": 1.0}, 1, [1, 2, 5, 0, 1, 6, 2, 0], [0, 1, 1], 0, 2),
+    "H5_simp_elimination": ([[1, 2]], 1, {}, 1, [1, 1, 1, 0, 0, 0, 0, 0], [1, 0], 2, 0),
+}

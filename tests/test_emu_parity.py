@@ -263,3 +263,20 @@ def test_bcp_replay_reproduces_the_recorded_prefix(po, emu):
                 continue
             assert ok == 1 and rec_p == got_p and same == 1
             assert words <= cap
+
+
+def test_hand_traces_device_source(po, emu):
+    """tests/golden/hand_traces.md against the device source (emulated): a pin that does not pass through oracle.cpp."""
+    from common import HAND_TRACES
+    for name, (clauses, kind, over, verdict, stats, model, elim, ncl) in HAND_TRACES.items():
+        st = po.default_settings()
+        for k, v in over.items():
+            setattr(st, k, v)
+        ioff, coff, lits = batch_of([csr_of(clauses)])
+        nv = max(abs(x) for c in clauses for x in c)
+        res, models = emu.solve_batch(ioff, coff, lits, st, kind=kind, flags=FLAGS, model_stride=nv, sched_seed=31)
+        assert res[0].status == 0 and res[0].verdict == verdict, name
+        assert list(res[0].stats) == stats, (name, list(res[0].stats))
+        assert res[0].eliminated_vars == elim and res[0].n_clauses_pre == ncl, name
+        if model is not None:
+            assert [int(x) for x in models[0][:nv]] == model, name

@@ -122,3 +122,19 @@ def test_cxx_dimacs_reader_quirks(pkg, tmp_path):
     a = rd(t)
     b = pkg.dimacs.read_csr_text(t)
     assert list(a[0]) == list(b[0]) and list(a[1]) == list(b[1])
+
+
+def test_hand_traces(po):
+    """tests/golden/hand_traces.md: the counters derived by hand from the Rust source pin the oracle itself."""
+    from common import HAND_TRACES, csr_of
+    for name, (clauses, kind, over, verdict, stats, model, elim, ncl) in HAND_TRACES.items():
+        st = po.default_settings()
+        for k, v in over.items():
+            setattr(st, k, v)
+        off, lits = csr_of(clauses)
+        r, m = po.solve_csr(off, lits, kind=kind, settings=st)
+        assert r.verdict == verdict, name
+        assert list(r.stats) == stats, (name, list(r.stats))
+        assert r.eliminated_vars == elim and r.n_clauses_pre == ncl, name
+        if model is not None:
+            assert [int(x) for x in m] == model, name
