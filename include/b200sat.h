@@ -60,8 +60,10 @@ typedef struct b200sat_settings {
 
 /* src/sat/minisat/budget.rs:5-34.  The reference never sets a budget (no
  * public setter exists); the struct shape is kept.  conflict/propagation
- * budgets < 0 mean "off".  `interrupt` may point at a host int the caller sets
- * non-zero to cancel (checked between launches). */
+ * budgets < 0 mean "off".  `interrupt` may point at a host int another thread
+ * sets non-zero to cancel (Budget::asynch_interrupt): it is forwarded to the
+ * device while the kernel runs; every running instance stops at its next
+ * conflict and returns B200SAT_INTERRUPTED. */
 typedef struct b200sat_budget {
     int64_t       conflict_budget;
     int64_t       propagation_budget;
@@ -116,14 +118,21 @@ uint32_t b200sat_new_var(b200sat_solver *h, int upol, int dvar);
 /* Solver::add_clause (sat.rs:32).  Returns 0 only when the clause is empty
  * (after duplicate removal) or the handle is already known UNSAT; UNSAT found
  * by unit propagation is reported by preprocess / solve_limited, because
- * propagation runs on the device at solve time. */
+ * propagation runs on the device at solve time.  Adding a
+ * clause after preprocess() drops the resident device state: the next call
+ * ingests the whole clause list again. */
 int      b200sat_add_clause(b200sat_solver *h, const uint32_t *lits, size_t n);
 /* Solver::preprocess (sat.rs:33; minisat.rs:50-55,161-191): 1 ok, 0 UNSAT, <0 error */
 int      b200sat_preprocess(b200sat_solver *h, const b200sat_budget *b);
 /* Solver::solve_limited (sat.rs:34).  Returns B200SAT_UNSAT/SAT/INTERRUPTED or
  * <0.  model (may be NULL) receives n_vars bytes: 1 true, 0 false, 2 absent
- * (model in var-index order, minisat.rs:68,235-239).  Only empty assumption
- * lists are supported (the reference's callers always pass &[]). */
+ * (model in var-index order, minisat.rs:68,235-239).  After preprocess() the
+ * search continues from the state resident on the device (nothing is ingested
+ * twice).  Budgets are honoured exactly where the reference checks them
+ * (search.rs:473-477); B200SAT_INTERRUPTED leaves the handle usable -- the
+ * next solve_limited() resumes it (SolveRes::Interrupted, sat.rs:24) -- while
+ * SAT / UNSAT consume it.  `b->interrupt` is forwarded to the device while the
+ * kernel runs.  Assumptions: search.rs:216-232 (a false one ends UNSAT). */
 int      b200sat_solve_limited(b200sat_solver *h, const b200sat_budget *b,
                                const uint32_t *assumps, size_t n_assumps,
                                uint8_t *model, size_t model_cap);
@@ -227,6 +236,21 @@ int b200sat_engine_configure(b200sat_engine *e, int warps_per_block, int blocks_
  *   interrupt: Budget::asynch_interrupt -- may be raised from another host thread while a solve call is running;
  *           every running instance returns B200SAT_INTERRUPTED at its next check. */
 int b200sat_engine_set_slice(b200sat_engine *e, uint32_t slice_conflicts);
+/* Solver::new_var(upol, dvar) (sat.rs:31) for the resident batch: flags[inst_var_off[i] + v] = B200SAT_VAR_* bits of
+ * var v of instance i; inst_var_off[i+1] - inst_var_off[i] = number of vars created (may exceed the largest var a
+ * clause mentions).  NULL = every var (None, true).  Call after upload, before solve; an upload resets it. */
+enum { B200SAT_VAR_UPOL_SET = 1, B200SAT_VAR_UPOL_VAL = 2 /* user polarity = sign: 1 picks the negative literal */,
+       B200SAT_VAR_NOT_DECISION = 4 };
+int b200sat_engine_set_var_flags(b200sat_engine *e, const uint8_t *flags, const uint32_t *inst_var_off);
+/* assumptions of the following solve calls (Solver::solve_limited's &[Lit], sat.rs:34; search.rs:216-232), applied to
+ * every instance of the batch; n = 0 clears them.  A false assumption ends the search UNSAT, as in the reference
+ * (search.rs:431-435 drops analyze_final's result). */
+int b200sat_engine_set_assumptions(b200sat_engine *e, const uint32_t *lits, uint32_t n);
+/* Search again on the instances the last solve left parked on the device (B200SAT_INTERRUPTED by budget / interrupt,
+ * or ingested with B200SAT_F_NO_SOLVE): nothing is ingested again.  A new search() call in the reference's sense
+ * (sat.rs:24: solves += 1, restart sequence from 0).  The batch must be resident in one chunk. */
+int b200sat_engine_resume(b200sat_engine *e, void *stream);
+int b200sat_engine_resume_async(b200sat_engine *e, void *stream);
 int b200sat_engine_set_budget(b200sat_engine *e, int64_t conflict_budget, int64_t propagation_budget);
 int b200sat_engine_interrupt(b200sat_engine *e, int raised);
 typedef struct b200sat_launch_info {

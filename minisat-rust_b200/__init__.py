@@ -121,7 +121,8 @@ ABI_SYMBOLS = (
     "b200sat_engine_ring_open_peer", "b200sat_portfolio_solve", "b200sat_engine_download_replicas",
     "b200sat_engine_verify_models", "b200sat_engine_subsume_instance", "b200sat_engine_simplify_instance", "b200sat_engine_bve_instance", "b200sat_read_dimacs", "b200sat_free_buffer", "b200sat_write_result",
     "b200sat_engine_set_slice", "b200sat_engine_set_budget", "b200sat_engine_interrupt",
-    "b200sat_engine_bcp_replay",
+    "b200sat_engine_bcp_replay", "b200sat_engine_set_var_flags", "b200sat_engine_set_assumptions",
+    "b200sat_engine_resume", "b200sat_engine_resume_async",
 )
 PF_SHARE, PF_IGNORE_DONE, PF_SHARE_LBD2, PF_KEEP_RING = 1, 2, 4, 8
 
@@ -169,6 +170,10 @@ def lib():
     L.b200sat_engine_configure.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
     L.b200sat_engine_launch_info.argtypes = [vp, C.POINTER(LaunchInfo)]
     L.b200sat_engine_bcp_replay.argtypes = [vp, C.POINTER(Settings), C.c_int, C.POINTER(ReplayInfo), vp]
+    L.b200sat_engine_set_var_flags.argtypes = [vp, u8p, u32p]
+    L.b200sat_engine_set_assumptions.argtypes = [vp, u32p, C.c_uint32]
+    L.b200sat_engine_resume.argtypes = [vp, vp]
+    L.b200sat_engine_resume_async.argtypes = [vp, vp]
     L.b200sat_engine_set_slice.argtypes = [vp, C.c_uint32]
     L.b200sat_engine_set_budget.argtypes = [vp, C.c_int64, C.c_int64]
     L.b200sat_engine_interrupt.argtypes = [vp, C.c_int]
@@ -281,14 +286,26 @@ class Solver:
         a, p = _u32(list(clause) if len(clause) else [0])
         return bool(lib().b200sat_add_clause(self._h, p, len(clause)))
 
+    @staticmethod
+    def _budget(budget):
+        """budget: None, a Budget struct, or (conflict_budget, propagation_budget)"""
+        if budget is None:
+            return None
+        if isinstance(budget, Budget):
+            return C.byref(budget)
+        b = Budget(int(budget[0]), int(budget[1]), None)
+        return C.byref(b)
+
     def preprocess(self, budget=None):
-        return bool(_check(lib().b200sat_preprocess(self._h, None)))
+        return bool(_check(lib().b200sat_preprocess(self._h, self._budget(budget))))
 
     def solve_limited(self, budget=None, assumptions=()):
+        """-> SolveRes.  An INTERRUPTED result leaves the solver usable (SolveRes::Interrupted(progress, solver),
+        sat.rs:24): call solve_limited again to continue; SAT / UNSAT consume it."""
         n = self.n_vars()
         model = np.full(max(n, 1), 2, dtype=np.uint8)
         a, ap = _u32(list(assumptions) if len(assumptions) else [0])
-        rc = _check(lib().b200sat_solve_limited(self._h, None, ap, len(assumptions),
+        rc = _check(lib().b200sat_solve_limited(self._h, self._budget(budget), ap, len(assumptions),
                                                 model.ctypes.data_as(C.POINTER(C.c_uint8)), n))
         st = self.stats()
         if rc == SAT:
@@ -341,6 +358,23 @@ class Engine:
         ri = ReplayInfo()
         _check(lib().b200sat_engine_bcp_replay(self._e, C.byref(s), reps, C.byref(ri), stream))
         return {k: getattr(ri, k) for k, _ in ReplayInfo._fields_}
+
+    def set_var_flags(self, flags, inst_var_off):
+        """Solver::new_var(upol, dvar) records (B200SAT_VAR_* bits) of the resident batch; None clears them"""
+        if flags is None:
+            _check(lib().b200sat_engine_set_var_flags(self._e, None, None))
+            return
+        f = np.ascontiguousarray(flags, dtype=np.uint8)
+        o, op = _u32(inst_var_off)
+        _check(lib().b200sat_engine_set_var_flags(self._e, f.ctypes.data_as(C.POINTER(C.c_uint8)), op))
+
+    def set_assumptions(self, lits):
+        a, ap = _u32(lits if lits is not None and len(lits) else np.zeros(1, np.uint32))
+        _check(lib().b200sat_engine_set_assumptions(self._e, ap, 0 if lits is None else len(lits)))
+
+    def resume(self, stream=None):
+        """search again on the instances the last solve left parked (INTERRUPTED / NO_SOLVE)"""
+        _check(lib().b200sat_engine_resume(self._e, stream))
 
     def set_slice(self, slice_conflicts):
         """conflicts an instance runs before it yields to waiting ones (0 = never); trace-neutral"""

@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -179,12 +180,23 @@ struct b200sat_engine {
     int *h_interrupt = nullptr;   /* pinned staging of the async interrupt word (Budget::asynch_interrupt) */
     int *d_interrupt = nullptr;   /* the word the kernels poll (device memory, d_queue + 48)               */
     cudaStream_t side_stream = nullptr; /* carries the interrupt word to the device while a solve is running */
+    u8 *d_parked = nullptr;       /* [item] resumable state resident in its slab */
+    size_t cap_parked = 0;
+    u8 *d_var_flags = nullptr;    /* Solver::new_var(upol, dvar) records of the resident batch (optional) */
+    size_t cap_var_flags = 0;
+    u32 *d_var_off = nullptr;
+    size_t cap_var_off = 0;
+    bool have_var_flags = false;
+    u32 *d_assumps = nullptr;     /* assumptions of the following solve calls */
+    size_t cap_assumps = 0;
+    u32 n_assumps = 0;
     u32 *d_trace = nullptr;       /* K2: per-instance event record of the search prefix */
     size_t cap_trace = 0;
     u32 trace_cap = 0;            /* words per instance; 0 = recording off */
     int replay_mode = 0;          /* 1: launch_attempt runs ingest + bcp_replay (count kernel), 2: same, plain kernel */
     u32 resident_items = 0;       /* items whose state is parked in d_slabs (chunk 0 of the last solve) */
     Layout resident_L;            /* layout the parked states were written with */
+    u32 resident_attempt = 0;
     int resident_tier_nv = 0;
     u32 *d_work[2] = {nullptr, nullptr};
     size_t cap_work = 0, cap_work1 = 0;
@@ -201,7 +213,7 @@ struct b200sat_engine {
     u32 n_replicas = 0;
     /* in-flight asynchronous solve */
     struct Pending {
-        bool active = false, retried = false, searched = false;
+        bool active = false, retried = false, searched = false, resumed = false;
         float search_ms = 0.f;
         b200sat_settings st;
         int kind = 0, flags = 0, tier_nv = 0;
@@ -279,7 +291,7 @@ extern "C" void b200sat_engine_destroy(b200sat_engine *e) {
     if (e->h_interrupt) cudaFreeHost(e->h_interrupt);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     cudaFree(e->d_ring);
-    cudaFree(e->d_trace);
+    cudaFree(e->d_trace); cudaFree(e->d_parked); cudaFree(e->d_var_flags); cudaFree(e->d_var_off); cudaFree(e->d_assumps);
     delete e;
 }
 
@@ -287,6 +299,44 @@ extern "C" int b200sat_engine_configure(b200sat_engine *e, int warps_per_block, 
                                         uint64_t wpool_entries) {
     if (!e) return set_err(B200SAT_E_ARG, "null engine");
     e->cfg_wpb = warps_per_block; e->cfg_bps = blocks_per_sm; e->cfg_arena = arena_words; e->cfg_wpool = wpool_entries;
+    return 0;
+}
+
+static int alloc_outputs(b200sat_engine *e);
+/* Solver::new_var(upol, dvar) records for the resident batch (sat.rs:31; decision_heuristic.rs:70-102,181-192) */
+extern "C" int b200sat_engine_set_var_flags(b200sat_engine *e, const uint8_t *flags, const uint32_t *inst_var_off) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    CK(cudaSetDevice(e->device));
+    if (!flags || !inst_var_off) { e->have_var_flags = false; return 0; }
+    if (e->n_inst == 0) return 0;
+    const u32 total = inst_var_off[e->n_inst];
+    u32 maxv = 0;
+    for (u32 i = 0; i < e->n_inst; i++) {
+        if (inst_var_off[i + 1] < inst_var_off[i]) return set_err(B200SAT_E_ARG, "inst_var_off is not monotone");
+        maxv = std::max(maxv, inst_var_off[i + 1] - inst_var_off[i]);
+    }
+    int rc;
+    if ((rc = ensure(e->d_var_flags, e->cap_var_flags, (size_t)total + 1))) return rc;
+    if ((rc = ensure(e->d_var_off, e->cap_var_off, (size_t)e->n_inst + 1))) return rc;
+    CK(cudaMemcpy(e->d_var_flags, flags, total, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_var_off, inst_var_off, ((size_t)e->n_inst + 1) * 4, cudaMemcpyHostToDevice));
+    if (maxv > e->shape.max_vars) { /* vars created but never used in a clause still exist (n_vars, elimination, model) */
+        e->shape.max_vars = maxv;
+        if ((rc = alloc_outputs(e))) return rc;
+    }
+    e->have_var_flags = true;
+    return 0;
+}
+/* assumptions of the following solve calls (Solver::solve_limited, sat.rs:34), applied to every instance */
+extern "C" int b200sat_engine_set_assumptions(b200sat_engine *e, const uint32_t *lits, uint32_t n) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    CK(cudaSetDevice(e->device));
+    e->n_assumps = 0;
+    if (!lits || n == 0) return 0;
+    int rc;
+    if ((rc = ensure(e->d_assumps, e->cap_assumps, (size_t)n))) return rc;
+    CK(cudaMemcpy(e->d_assumps, lits, (size_t)n * 4, cudaMemcpyHostToDevice));
+    e->n_assumps = n;
     return 0;
 }
 
@@ -340,6 +390,7 @@ static int device_shape(b200sat_engine *e, cudaStream_t stream) {
 
 extern "C" int b200sat_engine_upload(b200sat_engine *e, const b200sat_batch *b, void *stream_) {
     if (!e || !b) return set_err(B200SAT_E_ARG, "null argument");
+    e->have_var_flags = false; e->resident_items = 0;
     cudaStream_t stream = (cudaStream_t)stream_;
     CK(cudaSetDevice(e->device));
     const u32 n = b->n_inst;
@@ -393,6 +444,7 @@ extern "C" int b200sat_engine_generate_ksat(b200sat_engine *e, uint64_t seed_bas
                                             uint32_t n_clauses, uint32_t k, void *stream_) {
     if (!e) return set_err(B200SAT_E_ARG, "null engine");
     if (k == 0 || k > n_vars) return set_err(B200SAT_E_ARG, "k must be in 1..n_vars");
+    e->have_var_flags = false; e->resident_items = 0;
     if ((u64)n_inst * n_clauses * k > 0xFFFFFFF0ull) return set_err(B200SAT_E_ARG, "batch exceeds 2^32 literals");
     cudaStream_t stream = (cudaStream_t)stream_;
     CK(cudaSetDevice(e->device));
@@ -441,6 +493,16 @@ __global__ void start_ring(u32 *qctl, u32 n_warps) {
     const u32 h = t < n_warps ? t : n_warps;
     qctl[QC_HEAD] = h;
     qctl[QC_HEAD0] = h;
+}
+
+/* resume: every parked item goes back on the work ring, everything else counts as done */
+__global__ void requeue_parked(const u8 *parked, u32 n_items, u32 *qctl, unsigned long long *ring, u32 ring_mask) {
+    const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_items) return;
+    if (parked[w]) {
+        const u32 s = atomicAdd(qctl + QC_TAIL, 1u);
+        ring[s & ring_mask] = ((unsigned long long)(s + 1) << 32) | w;
+    } else atomicAdd(qctl + QC_DONE, 1u);
 }
 
 /* launch shape of one persistent kernel: as many resident warps per SM as shared memory and registers allow */
@@ -495,6 +557,9 @@ static void fill_params(b200sat_engine *e, KParams &P, const Layout &L) {
     P.interrupt = e->d_interrupt;
     P.import_cap = e->import_cap;
     P.trace_buf = e->trace_cap ? e->d_trace : nullptr; P.trace_cap = e->trace_cap;
+    P.parked = e->d_parked;
+    if (e->have_var_flags && !pd.portfolio) { P.var_flags = e->d_var_flags; P.inst_var_off = e->d_var_off; }
+    P.assumps = e->d_assumps; P.n_assumps = e->n_assumps;
 }
 
 /* enqueue one attempt on the pending stream, no host sync: per chunk of resident items the ingest kernel (every
@@ -536,6 +601,8 @@ static int launch_attempt(b200sat_engine *e) {
         CK(cudaStreamSynchronize(stream));
         if ((rc = ensure(e->d_ring, e->cap_ring, (size_t)ring_cap))) return rc;
     }
+    if ((rc = ensure(e->d_parked, e->cap_parked, (size_t)std::max<u64>(pd.n_work, 1)))) return rc;
+    CK(cudaMemsetAsync(e->d_parked, 0, (size_t)std::max<u64>(pd.n_work, 1), stream));
     KParams P;
     fill_params(e, P, L);
     P.ring_mask = ring_cap - 1;
@@ -580,7 +647,7 @@ static int launch_attempt(b200sat_engine *e) {
     e->info.warps_total = shs.grid * shs.wpb; e->info.tier = L.tier; e->info.slab_bytes = L.slab_bytes;
     e->info.resident_items = (u32)slots;
     e->resident_items = (pd.n_work <= slots && pd.work == nullptr) ? pd.n_work : 0;
-    e->resident_L = L; e->resident_tier_nv = pd.tier_nv;
+    e->resident_L = L; e->resident_tier_nv = pd.tier_nv; e->resident_attempt = pd.attempt;
     return 0;
 }
 
@@ -598,7 +665,7 @@ extern "C" int b200sat_engine_solve_async(b200sat_engine *e, const b200sat_setti
     pd.stream = (cudaStream_t)stream_;
     if (e->n_inst == 0) return 0;
     pd.st = *s; pd.kind = kind; pd.flags = flags;
-    pd.attempt = 0; pd.n_work = e->n_inst; pd.work = nullptr; pd.total_ms = 0.f; pd.search_ms = 0.f; pd.retried = false;
+    pd.attempt = 0; pd.n_work = e->n_inst; pd.work = nullptr; pd.total_ms = 0.f; pd.search_ms = 0.f; pd.retried = false; pd.resumed = false;
     /* model rows of instances that end without a model read "undefined" */
     if (e->d_models) CK(cudaMemsetAsync(e->d_models, 2, (size_t)e->n_inst * e->model_stride, pd.stream));
     pd.portfolio = 0; pd.replica_base = 0; pd.share = 0;
@@ -607,6 +674,63 @@ extern "C" int b200sat_engine_solve_async(b200sat_engine *e, const b200sat_setti
     if (rc) return rc;
     pd.active = true;
     return 0;
+}
+
+/* Search again on the instances the last solve left parked: the ones that returned B200SAT_INTERRUPTED (budget or
+ * interrupt: SolveRes::Interrupted hands the solver back, sat.rs:24) or were only ingested (B200SAT_F_NO_SOLVE:
+ * preprocess() without solve_limited()).  Nothing is ingested again; settings, kind and flags are those of that solve,
+ * budget / slice / assumptions are the engine's current ones.  Requires the whole batch to be resident (one chunk). */
+extern "C" int b200sat_engine_resume_async(b200sat_engine *e, void *stream_) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    int rc;
+    if (e->pend.active) { rc = b200sat_engine_finish(e); if (rc && rc != B200SAT_E_MEM) return rc; }
+    if (e->n_inst == 0) return 0;
+    if (e->resident_items != e->n_inst) return set_err(B200SAT_E_ARG, "nothing resident to resume (solve or preprocess first; the batch must fit in one chunk)");
+    CK(cudaSetDevice(e->device));
+    b200sat_engine::Pending &pd = e->pend;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    pd.stream = stream;
+    pd.flags &= ~B200SAT_F_NO_SOLVE;
+    pd.work = nullptr; pd.n_work = e->n_inst; pd.total_ms = 0.f; pd.search_ms = 0.f; pd.retried = false;
+    pd.attempt = e->resident_attempt;
+    e->info.launches = 0; e->info.last_kernel_ms = 0.f; e->info.search_ms = 0.f; e->info.suspends = 0; e->info.tail_ms = 0.f; e->info.span_ms = 0.f;
+    const bool count = (pd.flags & B200SAT_F_COUNT_TRAFFIC) != 0;
+    size_t spw_s = 0, save2 = 0;
+    kernel_fn fn_s = pick_search(e->resident_tier_nv, count, false, spw_s, save2);
+    LaunchShape shs;
+    if ((rc = shape_kernel(e, fn_s, spw_s, e->n_inst, 1, shs))) return rc;
+    KParams P;
+    fill_params(e, P, e->resident_L);
+    u32 ring_cap = 64;
+    while (ring_cap < 2 * (u64)e->n_inst) ring_cap <<= 1;
+    P.ring_mask = ring_cap - 1;
+    P.chunk_base = 0; P.n_work = e->n_inst;
+    CK(cudaEventRecord(e->ev0, stream));
+    CK(cudaMemsetAsync(e->d_ring, 0, (size_t)ring_cap * 8, stream));
+    init_qctl<<<1, 32, 0, stream>>>(P.qctl, e->n_inst);
+    requeue_parked<<<(e->n_inst + 255) / 256, 256, 0, stream>>>(e->d_parked, e->n_inst, P.qctl, e->d_ring, P.ring_mask);
+    CK(cudaEventRecord(e->ev2, stream));
+    start_ring<<<1, 1, 0, stream>>>(P.qctl, shs.grid * shs.wpb);
+    fn_s<<<shs.grid, shs.wpb * 32, shs.smem, stream>>>(P);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->ev3, stream));
+    CK(cudaEventRecord(e->ev1, stream));
+    e->info.launches = 1;
+    pd.searched = true;
+    pd.next_list = e->d_work[pd.attempt & 1];
+    CK(cudaMemsetAsync(e->d_queue + 1, 0, 4, stream));
+    collect_failed<<<(pd.n_work + 255) / 256, 256, 0, stream>>>(e->d_results, nullptr, pd.n_work, false, pd.next_list, e->d_queue + 1);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_pinned, e->d_queue + 1, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(e->h_pinned + 32, e->d_queue + 32, QC_WORDS * 4, cudaMemcpyDeviceToHost, stream));
+    pd.active = true;
+    pd.resumed = true;
+    return 0;
+}
+extern "C" int b200sat_engine_resume(b200sat_engine *e, void *stream_) {
+    int rc = b200sat_engine_resume_async(e, stream_);
+    if (rc) return rc;
+    return b200sat_engine_finish(e);
 }
 
 extern "C" int b200sat_engine_finish(b200sat_engine *e) {
@@ -628,6 +752,7 @@ extern "C" int b200sat_engine_finish(b200sat_engine *e) {
         }
         u32 left = e->h_pinned[0];
         if (left == 0 || pd.attempt >= 4) { pd.n_work = left; break; }
+        if (pd.resumed) pd.resumed = false; /* instances that outgrew their slab while resumed start over in a larger one */
         pd.retried = true;
         pd.n_work = left;
         pd.work = pd.next_list;
@@ -1099,7 +1224,7 @@ extern "C" int b200sat_engine_download_replicas(b200sat_engine *e, b200sat_resul
 struct b200sat_solver {
     b200sat_settings st;
     int kind;
-    bool ok = true, spent = false, preprocessed = false;
+    bool ok = true, spent = false, preprocessed = false, resident = false;
     u32 n_vars = 0;
     std::vector<u8> upol;      /* 0 none, 2 false, 3 true */
     std::vector<u8> dvar;
@@ -1144,6 +1269,7 @@ extern "C" int b200sat_add_clause(b200sat_solver *h, const uint32_t *lits, size_
     for (size_t i = 1; i < ps.size(); i++) if (ps[i] == (ps[i - 1] ^ 1)) taut = true;
     h->lits.insert(h->lits.end(), lits, lits + n);
     h->clause_off.push_back((u32)h->lits.size());
+    h->resident = false; /* the next solve ingests the whole clause list again */
     if (!taut) {
         if (ps.empty()) { h->ok = false; return 0; }
         if (ps.size() > 1) h->n_clauses_known++;
@@ -1151,53 +1277,105 @@ extern "C" int b200sat_add_clause(b200sat_solver *h, const uint32_t *lits, size_
     return 1;
 }
 
-static int solver_run(b200sat_solver *h, int flags, b200sat_result *res, uint8_t *model, size_t model_cap) {
+/* wait for the pending launch of the handle's engine, forwarding the caller's interrupt word (Budget::asynch_interrupt)
+ * to the device while the kernel runs */
+static int solver_wait(b200sat_solver *h, const b200sat_budget *b) {
+    b200sat_engine *e = h->eng;
+    if (b && b->interrupt) {
+        bool raised = false;
+        while (cudaEventQuery(e->ev1) == cudaErrorNotReady) {
+            if (!raised && *b->interrupt) { b200sat_engine_interrupt(e, 1); raised = true; }
+            struct timespec ts = {0, 200000};
+            nanosleep(&ts, nullptr);
+        }
+        cudaGetLastError();
+        int rc = b200sat_engine_finish(e);
+        if (raised) b200sat_engine_interrupt(e, 0);
+        return rc;
+    }
+    return b200sat_engine_finish(e);
+}
+
+/* ingest (+ preprocess) on the device; with `search` the search kernel follows in the same call */
+static int solver_ingest(b200sat_solver *h, int flags, const b200sat_budget *b, b200sat_result *res) {
     if (!h->eng) {
         h->eng = b200sat_engine_create(0);
         if (!h->eng) return B200SAT_E_NO_DEVICE;
     }
-    for (u32 v = 0; v < h->n_vars; v++)
-        if (h->upol[v] != 0 || !h->dvar[v]) return set_err(B200SAT_E_ARG, "user polarity / non-decision vars are not supported by the device ingest yet");
     u32 ioff[2] = {0, (u32)(h->clause_off.size() - 1)};
-    b200sat_batch b;
-    b.n_inst = 1; b.inst_clause_off = ioff; b.clause_off = h->clause_off.data();
+    b200sat_batch bt;
+    bt.n_inst = 1; bt.inst_clause_off = ioff; bt.clause_off = h->clause_off.data();
     u32 dummy = 0;
-    b.lits = h->lits.empty() ? &dummy : h->lits.data();
-    std::vector<u8> m(h->n_vars ? h->n_vars : 1, 2);
-    int rc = b200sat_solve_batch(h->eng, &b, &h->st, h->kind, flags, res, m.data(), (u32)m.size());
+    bt.lits = h->lits.empty() ? &dummy : h->lits.data();
+    int rc = b200sat_engine_upload(h->eng, &bt, nullptr);
     if (rc) return rc;
-    if (model) memcpy(model, m.data(), std::min(model_cap, (size_t)h->n_vars));
-    return 0;
+    /* Solver::new_var(upol, dvar): one record per created var, also for vars no clause mentions */
+    std::vector<u8> vf(h->n_vars ? h->n_vars : 1, 0);
+    for (u32 v = 0; v < h->n_vars; v++)
+        vf[v] = (u8)((h->upol[v] ? (VARF_UPOL_SET | (h->upol[v] == 3 ? VARF_UPOL_VAL : 0)) : 0) | (h->dvar[v] ? 0 : VARF_NOT_DECISION));
+    u32 voff[2] = {0, h->n_vars};
+    if ((rc = b200sat_engine_set_var_flags(h->eng, vf.data(), voff))) return rc;
+    if ((rc = b200sat_engine_set_budget(h->eng, b ? b->conflict_budget : -1, b ? b->propagation_budget : -1))) return rc;
+    if ((rc = b200sat_engine_solve_async(h->eng, &h->st, h->kind, flags, nullptr))) return rc;
+    if ((rc = solver_wait(h, b))) return rc;
+    return b200sat_engine_download(h->eng, res, nullptr, 0, nullptr);
 }
 
-extern "C" int b200sat_preprocess(b200sat_solver *h, const b200sat_budget *) {
+extern "C" int b200sat_preprocess(b200sat_solver *h, const b200sat_budget *b) {
     if (!h) return set_err(B200SAT_E_ARG, "null handle");
     if (h->spent) return set_err(B200SAT_E_SPENT, "handle already consumed");
     if (!h->ok) return 0;
+    if (b && b->interrupt && *b->interrupt) return set_err(B200SAT_E_ARG, "interrupt is already raised");
     b200sat_result r;
-    int rc = solver_run(h, B200SAT_F_PREPROCESS | B200SAT_F_NO_SOLVE, &r, nullptr, 0);
+    int rc = solver_ingest(h, B200SAT_F_PREPROCESS | B200SAT_F_NO_SOLVE, b, &r);
     if (rc) return rc;
+    if (r.status != B200SAT_OK) return set_err(B200SAT_E_MEM, "instance outgrew the largest slab");
     h->preprocessed = true;
+    h->resident = true;      /* solve_limited() continues from this state: nothing is ingested twice */
     h->n_clauses_known = r.n_clauses_pre;
     memcpy(&h->stats, r.stats, sizeof h->stats);
     if (!r.pre_ok) h->ok = false;
     return h->ok ? 1 : 0;
 }
 
-extern "C" int b200sat_solve_limited(b200sat_solver *h, const b200sat_budget *b, const uint32_t *, size_t n_assumps, uint8_t *model,
+extern "C" int b200sat_solve_limited(b200sat_solver *h, const b200sat_budget *b, const uint32_t *assumps, size_t n_assumps, uint8_t *model,
                                      size_t model_cap) {
     if (!h) return set_err(B200SAT_E_ARG, "null handle");
     if (h->spent) return set_err(B200SAT_E_SPENT, "handle already consumed");
-    if (n_assumps) return set_err(B200SAT_E_ARG, "assumptions are not supported (the reference's callers pass &[])");
+    if (n_assumps && !assumps) return set_err(B200SAT_E_ARG, "null assumptions");
+    for (size_t i = 0; i < n_assumps; i++)
+        if ((assumps[i] >> 1) >= h->n_vars) return set_err(B200SAT_E_ARG, "assumption on an unknown variable");
     if (b && b->interrupt && *b->interrupt) return B200SAT_INTERRUPTED;
-    h->spent = true;
-    if (!h->ok && h->kind == B200SAT_CORE && h->clause_off.size() == 1) return B200SAT_UNSAT;
+    if (!h->ok && h->preprocessed) { h->spent = true; return B200SAT_UNSAT; } /* minisat.rs:80-82: stats stay as they are */
     b200sat_result r;
-    /* the device replays ingest (+ preprocess when it was requested) and then searches: one deterministic pass */
-    int rc = solver_run(h, h->preprocessed ? B200SAT_F_PREPROCESS : 0, &r, model, model_cap);
+    int rc;
+    if (!h->eng) {
+        h->eng = b200sat_engine_create(0);
+        if (!h->eng) return B200SAT_E_NO_DEVICE;
+    }
+    if ((rc = b200sat_engine_set_assumptions(h->eng, assumps, (uint32_t)n_assumps))) return rc;
+    if (h->resident) { /* state parked by preprocess() or by an Interrupted solve_limited(): search only */
+        if ((rc = b200sat_engine_set_budget(h->eng, b ? b->conflict_budget : -1, b ? b->propagation_budget : -1))) return rc;
+        if ((rc = b200sat_engine_resume_async(h->eng, nullptr))) return rc;
+        if ((rc = solver_wait(h, b))) return rc;
+        rc = b200sat_engine_download(h->eng, &r, nullptr, 0, nullptr);
+    } else rc = solver_ingest(h, h->preprocessed ? B200SAT_F_PREPROCESS : 0, b, &r);
+    b200sat_engine_set_assumptions(h->eng, nullptr, 0);
     if (rc) return rc;
+    if (r.status != B200SAT_OK) return set_err(B200SAT_E_MEM, "instance outgrew the largest slab");
     memcpy(&h->stats, r.stats, sizeof h->stats);
     h->n_clauses_known = r.n_clauses_pre;
+    if (r.verdict == B200SAT_INTERRUPTED) { /* SolveRes::Interrupted(progress, solver): the handle stays usable */
+        h->resident = true;
+        return B200SAT_INTERRUPTED;
+    }
+    h->spent = true;
+    if (r.verdict == B200SAT_SAT && model) {
+        std::vector<u8> m(h->eng->model_stride ? h->eng->model_stride : 1, 2);
+        if ((rc = b200sat_engine_download(h->eng, nullptr, m.data(), (u32)m.size(), nullptr))) return rc;
+        size_t n = std::min(model_cap, (size_t)h->n_vars);
+        for (size_t v = 0; v < n; v++) model[v] = v < m.size() ? m[v] : 2;
+    }
     return r.verdict;
 }
 

@@ -51,6 +51,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 
 template <class WS> __device__ __forceinline__ void bind_item(WS &S, const KParams &P, u32 w) {
     S.slab = P.slabs + (size_t)(w - P.chunk_base) * P.L.slab_bytes;
+    S.item_index = w;
     S.res_index = P.work ? P.work[w] : w;
     S.stp = &P.st;
     if (P.portfolio) { /* item w = replica w of instance 0 with its own diversified settings */

@@ -151,6 +151,13 @@ struct KParams {
     u32 slice_conflicts;      /* conflicts an instance may run before it yields to waiting ones (0 = never) */
     long long conflict_budget, propagation_budget; /* budget.rs:5-34; < 0 = none                       */
     const volatile int *interrupt;                 /* device-visible async interrupt flag or NULL      */
+    /* Solver::new_var(upol, dvar) (sat.rs:31) for the resident batch, or NULL = (None, true) for every var:
+     * var_flags[inst_var_off[i] + v]: VARF_* bits; inst_var_off[i + 1] - inst_var_off[i] = number of vars created */
+    const u8 *var_flags;
+    const u32 *inst_var_off;
+    const u32 *assumps;       /* assumptions of solve_limited (sat.rs:34), shared by every instance of the batch */
+    u32 n_assumps;
+    u8 *parked;               /* [item] 1: the item's state is resident and resumable (PH_READY), 0: not */
     u32 *trace_buf;           /* K2: per-item event record of the search prefix (instrumented kernel only), or NULL */
     u32 trace_cap;            /* words per item in trace_buf                                             */
     u32 import_cap;           /* portfolio: clauses one replica imports per restart boundary (0 = no cap) */
@@ -168,6 +175,7 @@ enum : u32 { TR_WORDS = 0, TR_PROPS_LO = 1, TR_PROPS_HI = 2, TR_TRAFFIC = 4 /* 6
              TR_CONFLICT = 0x80000000u, TR_RESTART = 0xC0000000u };
 
 enum : u32 { PF_SHARE = 1, PF_IGNORE_DONE = 2, PF_SHARE_LBD2 = 4 };
+enum : u32 { VARF_UPOL_SET = 1, VARF_UPOL_VAL = 2, VARF_NOT_DECISION = 4 };
 /* ring header words */
 enum : u32 { RING_HEAD = 0, RING_DONE = 1, RING_EXPORTS = 2, RING_PAYLOAD = 16 };
 static const u32 ST_CANCELLED = 20;

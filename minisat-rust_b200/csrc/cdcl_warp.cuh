@@ -212,6 +212,7 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
     const KParams &P;
     const b200sat_settings *stp;   /* P.st, or this replica's diversified settings in portfolio mode */
     u32 res_index;                 /* slot in results/models (= instance id, or replica id)          */
+    u32 item_index = 0;            /* work index of the item (slab / parked slot)                     */
     u32 lane;
     u8 *slab;
     u32 *arena;   /* active arena half */
@@ -1832,8 +1833,25 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
                     if (failed()) return SR_ABORT;
                     try_garbage_collect();
                 }
-                if (lane == 0) sc().decisions++;
-                const u32 next = pick_branch_lit();
+                u32 next = LIT_NONE;
+                /* SearchCtx::decide, search.rs:216-232: user assumptions first, one (possibly dummy) level each */
+                while (nlevels - 1 < P.n_assumps) {
+                    const u32 a = P.assumps[nlevels - 1];
+                    const u32 av = lval(a);
+                    __syncwarp(); /* every lane has read the value before cancel_until() below starts to unassign */
+                    if (av == 1) new_decision_level();
+                    else if (av == 0) {
+                        /* analyze_final (conflict.rs:255-279) computes the set of responsible assumptions, which the
+                         * reference then drops ("TODO: implement properly", search.rs:431-435): UNSAT at ground level */
+                        cancel_until(GROUND);
+                        return SR_UNSAT;
+                    } else { next = a; break; }
+                }
+                if (next == LIT_NONE) {
+                    if (lane == 0) sc().decisions++; /* :234-236, counted for real decisions only */
+                    __syncwarp();
+                    next = pick_branch_lit();
+                }
                 if (next == LIT_NONE) { if (recording()) rec_stop(res_index); return SR_SAT; }
                 if (recording()) rec_word(next);
                 new_decision_level();
@@ -1887,6 +1905,7 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
         if (PF && !failed() && verdict != B200SAT_INTERRUPTED) announce_done();
         if (r == SR_INTERRUPTED) save_state(); /* SolveRes::Interrupted hands the solver back (sat.rs:24): stays resident */
         else if (lane == 0) sc().phase = PH_DONE;
+        if (lane == 0 && P.parked) P.parked[item_index] = r == SR_INTERRUPTED ? 1 : 0;
         __syncwarp();
     }
 
@@ -1942,6 +1961,7 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
         write_result(verdict, n_ingest, n_pre, pre_ok);
         if (PF && !runnable && !failed()) announce_done();
         if (runnable) save_state();
+        if (lane == 0 && P.parked) P.parked[item_index] = runnable ? 1 : 0;
         return runnable;
     }
 
@@ -1954,6 +1974,13 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
         for (u32 k = lb + lane; k < le; k += 32) { u32 v = P.lits[k] >> 1; mx = v > mx ? v : mx; }
         mx = warp_max(mx);
         nvars = (le > lb) ? mx + 1 : 0;
+        const u8 *vfl = nullptr; /* Solver::new_var(upol, dvar) records of this instance (sat.rs:31), if any */
+        if (P.var_flags) {
+            const u32 vb = P.inst_var_off[inst], nv_given = P.inst_var_off[inst + 1] - vb;
+            vfl = P.var_flags + vb;
+            if (nv_given > nvars) nvars = nv_given; /* vars that were created but occur in no clause */
+            else if (nv_given < nvars) vfl = nullptr; /* the host checks this; never read out of range */
+        }
         trail_n = 0; qhead = 0; nlevels = 1;
         if (lane == 0) {
             Scal &s = sc();
@@ -1986,20 +2013,29 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
             V.heap()[v] = (idx_t)v;
             V.hidx()[v] = (idx_t)v;
             V.assign()[v] = LB_UNDEF;
-            V.vflags()[v] = (u8)(VF_POL | VF_DEC);
+            u32 f = VF_POL | VF_DEC; /* decision_heuristic.rs:70-88: polarity true, user_pol None, decision var */
+            if (vfl) {
+                const u32 g = vfl[v];
+                if (g & VARF_UPOL_SET) f |= VF_UPOL_SET | ((g & VARF_UPOL_VAL) ? VF_UPOL_VAL : 0u);
+                if (g & VARF_NOT_DECISION) f &= ~(u32)VF_DEC;
+            }
+            V.vflags()[v] = (u8)f;
             V.wstart()[2 * v] = 0; V.wstart()[2 * v + 1] = 0;
             V.wlen()[2 * v] = 0; V.wlen()[2 * v + 1] = 0;
         }
         if (lane == 0) V.lim()[0] = 0;
         __syncwarp();
-        if (st().rnd_init_act) { /* decision_heuristic.rs:70-88: activity drawn at var creation, heap insert in creation order */
+        if (st().rnd_init_act || vfl) { /* decision_heuristic.rs:70-102: activity drawn at var creation; only decision
+                                           vars enter the heap, in creation order (set_decision_var) */
             if (lane == 0) {
                 sc().heap_n = 0;
+                u32 nd = 0;
                 for (u32 v = 0; v < nvars; v++) {
-                    V.act()[v] = drand() * 0.00001;
+                    if (st().rnd_init_act) V.act()[v] = drand() * 0.00001;
                     V.hidx()[v] = (idx_t)VT::ABSENT;
-                    heap_insert(v);
+                    if (V.vflags()[v] & VF_DEC) { heap_insert(v); nd++; }
                 }
+                sc().dec_vars = nd;
             }
             __syncwarp();
         }

@@ -1252,6 +1252,8 @@ DEVNI SimpPhaseOut simp_phase(const KParams *Pp, VT V, u8 *slab, const b200sat_s
     if (lane == 0) {
         S.sc().extra_clause_field = 1;   /* Simplificator::on simplify.rs:546-549 */
         S.sc().remove_satisfied = 0;
+        /* a caller of the trait creates every var before it adds clauses (sat.rs:31-32) */
+        if (P.var_flags) while (Z.n_created < S.nvars) Z.init_var(Z.n_created);
         /* ingest: dimacs.rs:146-167 order -- vars are created lazily, interleaved with the clauses */
         for (u32 c = cb; c < ce && !Z.failed(); c++) {
             u32 b = P.clause_off[c], e = P.clause_off[c + 1];
@@ -1284,6 +1286,9 @@ DEVNI SimpPhaseOut simp_phase(const KParams *Pp, VT V, u8 *slab, const b200sat_s
         else if (!simp_alive) o.do_search = 1; /* simp == None: core search, minisat.rs:241-260 (parked; the host launches it unless NO_SOLVE) */
         else if (P.flags & B200SAT_F_NO_SOLVE) o.verdict = B200SAT_INTERRUPTED; /* a live simplifier is not parked */
         else { /* Simplificator::solve_limited simplify.rs:165-211 */
+            /* assumptions are frozen for the elimination in front of the search (simplify.rs:173-186) */
+            if (lane == 0) for (u32 k = 0; k < P.n_assumps; k++) S.V.vflags()[P.assumps[k] >> 1] |= (u8)VF_FROZEN;
+            __syncwarp();
             u32 pr = 0;
             if (lane == 0) { pr = Z.seq_propagate() == CREF_UNDEF ? 1 : 0; if (pr) Z.seq_try_simplify(); }
             pr = bcast(pr);

@@ -855,6 +855,7 @@ struct Searcher {
 
     enum LoopRes { LR_RESTART, LR_UNSAT, LR_SAT, LR_INTERRUPTED };
     int64_t conflict_budget = -1, propagation_budget = -1;                 /* budget.rs:5-34 (no asynchronous interrupt here) */
+    std::vector<Lit> assumptions;                                          /* solve_limited's &[Lit] */
     double progress = 0.0;
     bool within_budget() const {                                           /* budget.rs:21-25 */
         return (conflict_budget < 0 || conflicts < (uint64_t)conflict_budget) &&
@@ -888,9 +889,23 @@ struct Searcher {
                 db.reduce(ca, assigns, [&](CRef c) { watches.unwatch_clause_lazy(ca, c); });
                 try_garbage_collect();
             }
-            decisions += 1;                                                /* SearchCtx::decide :234-236 */
-            Lit next;
-            if (!heur.pick_branch_lit(assigns, next)) return LR_SAT;
+            Lit next = 0;
+            bool have = false;
+            /* SearchCtx::decide :216-232: user assumptions first, one (possibly dummy) decision level each */
+            while (assigns.lim.size() - 1 < assumptions.size()) {
+                Lit p = assumptions[assigns.lim.size() - 1];
+                if (assigns.is_true(p)) assigns.new_decision_level();
+                else if (assigns.is_false(p)) {
+                    /* analyze_final (conflict.rs:255-279) has no side effect on the counters; its result is dropped by
+                     * search_internal ("TODO: implement properly", :431-435) */
+                    cancel_until(GROUND_LEVEL);
+                    return LR_UNSAT;
+                } else { next = p; have = true; break; }
+            }
+            if (!have) {
+                decisions += 1;                                            /* :234-236 */
+                if (!heur.pick_branch_lit(assigns, next)) return LR_SAT;
+            }
             assigns.new_decision_level();                                  /* backtrack.rs:58-62 */
             assigns.assign_lit(next, CREF_UNDEF);
         }
@@ -1419,6 +1434,10 @@ void oracle_default_settings(oracle_settings *s) {
 
 void oracle_set_trace(uint64_t *buf, uint32_t cap) { g_trace.buf = buf; g_trace.cap = cap; g_trace.n = 0; }
 
+static std::vector<uint8_t> g_var_flags;   /* bit0 upol set, bit1 upol value, bit2 not a decision var */
+static std::vector<Lit> g_assumptions;
+void oracle_set_var_flags(const uint8_t *flags, uint32_t n) { g_var_flags.assign(flags, flags + (flags ? n : 0)); }
+void oracle_set_assumptions(const uint32_t *lits, uint32_t n) { g_assumptions.assign(lits, lits + (lits ? n : 0)); }
 static int64_t g_conflict_budget = -1, g_propagation_budget = -1;
 static int g_resume_rounds = 0;
 void oracle_set_budget(int64_t conflict_budget, int64_t propagation_budget, int resume_rounds) {
@@ -1432,6 +1451,11 @@ int oracle_solve_csr(const uint32_t *clause_off, const uint32_t *lits, uint32_t 
     memset(out, 0, sizeof *out);
     Solver solver(*s, kind);
     std::vector<Lit> tmp;
+    /* the trait's own call order (sat.rs:31-32): every var created with its (upol, dvar) before the clauses are added */
+    for (size_t v = 0; v < g_var_flags.size(); v++) {
+        uint8_t f = g_var_flags[v];
+        solver.new_var((f & 1) ? ((f & 2) ? 1 : 0) : -1, !(f & 4));
+    }
     for (uint32_t c = 0; c < n_clauses; c++) {                             /* Subst::add_clause dimacs.rs:146-167 */
         uint32_t b = clause_off[c], e = clause_off[c + 1];
         for (uint32_t k = b; k < e; k++)
@@ -1453,6 +1477,8 @@ int oracle_solve_csr(const uint32_t *clause_off, const uint32_t *lits, uint32_t 
     else {
         solver.search.conflict_budget = g_conflict_budget;
         solver.search.propagation_budget = g_propagation_budget;
+        solver.search.assumptions = g_assumptions;
+        if (solver.simp) for (Lit a : g_assumptions) solver.simp->frozen[lit_var(a)] = 1;   /* simplify.rs:173-186 */
         verdict = solver.solve_limited(model);
         /* SolveRes::Interrupted(progress, solver): the caller may call solve_limited on it again (sat.rs:24) */
         for (int r = 0; r < g_resume_rounds && verdict == ORACLE_INTERRUPTED; r++) {

@@ -123,6 +123,13 @@ int oracle_check_model(const uint32_t *clause_off, const uint32_t *lits, uint32_
  * for SimpSolver after preprocess() (simp == None). */
 void oracle_set_budget(int64_t conflict_budget, int64_t propagation_budget, int resume_rounds);
 
+/* Solver::new_var(upol, dvar) records of the NEXT solve calls (process-wide): var v is created with flags[v]
+ * (bit0 upol set, bit1 upol value = sign, bit2 not a decision var) before any clause is added, as a caller of the
+ * trait does (sat.rs:31-32); n = 0 restores the DIMACS behaviour (lazy creation, (None, true)). */
+void oracle_set_var_flags(const uint8_t *flags, uint32_t n);
+/* assumptions (&[Lit]) of the NEXT solve_limited calls; n = 0 clears them (search.rs:216-232,431-435) */
+void oracle_set_assumptions(const uint32_t *lits, uint32_t n);
+
 /* dump per-conflict trace (debugging divergences): up to cap records of
  * (bt_level, learnt_len, hash). Enabled per call through oracle_set_trace. */
 void oracle_set_trace(uint64_t *buf, uint32_t cap_records);

@@ -136,6 +136,8 @@ def lib():
         L.oracle_check_model.restype = C.c_int
         L.oracle_set_trace.argtypes = [C.POINTER(C.c_uint64), C.c_uint32]
         L.oracle_set_budget.argtypes = [C.c_int64, C.c_int64, C.c_int]
+        L.oracle_set_var_flags.argtypes = [C.POINTER(C.c_uint8), C.c_uint32]
+        L.oracle_set_assumptions.argtypes = [C.POINTER(C.c_uint32), C.c_uint32]
         _lib = L
     return _lib
 
@@ -195,6 +197,23 @@ def solve_batch(inst_clause_off, clause_off, lits, kind=SIMP,
 def set_budget(conflict_budget=-1, propagation_budget=-1, resume_rounds=0):
     """Budget of the following solve calls (process-wide); set_budget() resets it."""
     lib().oracle_set_budget(conflict_budget, propagation_budget, resume_rounds)
+
+
+def set_var_flags(flags=None):
+    """new_var(upol, dvar) records of the following solves (bit0 upol set, bit1 upol value, bit2 not decision)"""
+    if flags is None or len(flags) == 0:
+        lib().oracle_set_var_flags(None, 0)
+        return
+    f = np.ascontiguousarray(flags, dtype=np.uint8)
+    lib().oracle_set_var_flags(f.ctypes.data_as(C.POINTER(C.c_uint8)), len(f))
+
+
+def set_assumptions(lits=None):
+    if lits is None or len(lits) == 0:
+        lib().oracle_set_assumptions(None, 0)
+        return
+    a = np.ascontiguousarray(lits, dtype=np.uint32)
+    lib().oracle_set_assumptions(a.ctypes.data_as(C.POINTER(C.c_uint32)), len(a))
 
 
 def parse_dimacs(path, strict=False):

@@ -269,6 +269,14 @@ int emu_portfolio(const uint32_t *clause_off, const uint32_t *lits, uint32_t n_c
     return 0;
 }
 
+/* optional inputs of the following emu_solve_batch calls: new_var(upol, dvar) records and assumptions */
+static const uint8_t *g_var_flags = nullptr;
+static const uint32_t *g_inst_var_off = nullptr, *g_assumps = nullptr;
+static uint32_t g_n_assumps = 0;
+void emu_set_extras(const uint8_t *var_flags, const uint32_t *inst_var_off, const uint32_t *assumps, uint32_t n_assumps) {
+    g_var_flags = var_flags; g_inst_var_off = inst_var_off; g_assumps = assumps; g_n_assumps = n_assumps;
+}
+
 /* tier_nv: 128/256/1024 = shared-memory tier, 0 = global tier, -1 = auto.
  * sched_seed: 0 = lanes run in ascending order, else adversarial ordering.
  * slice_conflicts: 0 = an instance runs to the end in one pick-up; else it is parked and resumed (with wiped shared
@@ -296,6 +304,7 @@ int emu_solve_batch(const uint32_t *inst_clause_off, const uint32_t *clause_off,
             if (len > sh.max_clause_len) sh.max_clause_len = len;
         }
         for (u32 k = clause_off[cb]; k < clause_off[ce]; k++) if ((lits[k] >> 1) + 1 > sh.max_vars) sh.max_vars = (lits[k] >> 1) + 1;
+        if (g_var_flags && g_inst_var_off[i + 1] - g_inst_var_off[i] > sh.max_vars) sh.max_vars = g_inst_var_off[i + 1] - g_inst_var_off[i];
     }
     if (tier_nv < 0) tier_nv = pick_tier_nv(sh.max_vars, sh.max_clauses);
     std::vector<u32> todo(n_inst);
@@ -318,6 +327,7 @@ int emu_solve_batch(const uint32_t *inst_clause_off, const uint32_t *clause_off,
         j.P.slabs = (u8 *)slab.data(); j.P.L = L; j.P.st = *st; j.P.kind = kind; j.P.flags = flags;
         j.P.attempt = attempt + 1;
         j.P.qctl = qctl; j.P.slice_conflicts = slice_conflicts;
+        j.P.var_flags = g_var_flags; j.P.inst_var_off = g_inst_var_off; j.P.assumps = g_assumps; j.P.n_assumps = g_n_assumps;
         j.smem = smem.data(); j.tier_nv = tier_nv;
         j.count = (flags & B200SAT_F_COUNT_TRAFFIC) != 0;
         std::vector<u32> again;

@@ -59,6 +59,7 @@ def lib():
         L.emu_portfolio.argtypes = [u32p, u32p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64,
                                     C.POINTER(Result), C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32]
         L.emu_portfolio.restype = C.c_int
+        L.emu_set_extras.argtypes = [C.POINTER(C.c_uint8), u32p, u32p, C.c_uint32]
         L.emu_bcp_replay.argtypes = [u32p, u32p, u32p, C.c_uint32, C.c_void_p, C.c_int, C.c_uint32, C.c_uint64,
                                      C.POINTER(C.c_uint64)]
         L.emu_bcp_replay.restype = C.c_int
@@ -73,7 +74,8 @@ def _u32(a):
 
 def solve_batch(inst_clause_off, clause_off, lits, settings, kind=0, flags=1 | 4 | 8 | 16, tier_nv=-1,
                 arena_words=0, wpool_entries=0, sched_seed=0, model_stride=0, slice_conflicts=0,
-                conflict_budget=-1, propagation_budget=-1, resume_rounds=0, want_suspends=False):
+                conflict_budget=-1, propagation_budget=-1, resume_rounds=0, want_suspends=False,
+                var_flags=None, inst_var_off=None, assumptions=None):
     """settings: any ctypes struct with the b200sat_settings layout (e.g. oracle Settings).
     slice_conflicts > 0 parks and resumes every instance each time it used that many conflicts."""
     ioff, ioffp = _u32(inst_clause_off)
@@ -86,9 +88,19 @@ def solve_batch(inst_clause_off, clause_off, lits, settings, kind=0, flags=1 | 4
     if model_stride:
         models = np.full((n, model_stride), 2, dtype=np.uint8)
         mp = models.ctypes.data_as(C.POINTER(C.c_uint8))
+    vf = vo = asm = None
+    if var_flags is not None or assumptions is not None:
+        vfp = vop = asp = None
+        if var_flags is not None:
+            vf = np.ascontiguousarray(var_flags, dtype=np.uint8); vfp = vf.ctypes.data_as(C.POINTER(C.c_uint8))
+            vo, vop = _u32(inst_var_off)
+        if assumptions is not None and len(assumptions):
+            asm, asp = _u32(assumptions)
+        lib().emu_set_extras(vfp, vop, asp, 0 if asm is None else len(asm))
     rc = lib().emu_solve_batch(ioffp, offp, lip, n, C.addressof(settings), kind, flags, tier_nv,
                                arena_words, wpool_entries, sched_seed, res, mp, model_stride, slice_conflicts,
                                conflict_budget, propagation_budget, resume_rounds)
+    lib().emu_set_extras(None, None, None, 0)
     if rc < 0:
         raise RuntimeError("emulator: solver kind not compiled in")
     if want_suspends:

@@ -280,3 +280,34 @@ def test_hand_traces_device_source(po, emu):
         assert res[0].eliminated_vars == elim and res[0].n_clauses_pre == ncl, name
         if model is not None:
             assert [int(x) for x in models[0][:nv]] == model, name
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_new_var_flags_and_assumptions(po, emu, kind):
+    """Solver::new_var(upol, dvar) (decision_heuristic.rs:70-102,181-192) and solve_limited's assumptions
+    (search.rs:216-232,431-435) on the device, against the oracle: user polarities, non-decision vars, vars that occur
+    in no clause, true / undefined / false assumptions."""
+    rng = np.random.RandomState(5 + kind)
+    for trial in range(6):
+        n, m = 40, 150 + 5 * trial
+        lits = po.gen_ksat(SEED2 + 9300 + trial, n, m)
+        coff = np.arange(0, m + 1, dtype=np.uint32) * 3
+        ioff = np.array([0, m], np.uint32)
+        nv = n + 3                                   # three vars no clause mentions
+        vf = np.zeros(nv, np.uint8)
+        for v in range(nv):
+            r = rng.rand()
+            if r < 0.3: vf[v] |= 1 | (2 if rng.rand() < 0.5 else 0)      # user polarity
+            if rng.rand() < 0.15: vf[v] |= 4                            # not a decision var
+        assumps = [int((v << 1) | rng.randint(2)) for v in rng.choice(n, 3, replace=False)] if trial % 2 else []
+        po.set_var_flags(vf); po.set_assumptions(assumps)
+        try:
+            o, om = po.solve_csr(coff, lits, kind=kind)
+        finally:
+            po.set_var_flags(); po.set_assumptions()
+        e, em = emu.solve_batch(ioff, coff, lits, po.default_settings(), kind=kind, flags=FLAGS, model_stride=nv, sched_seed=9,
+                                var_flags=vf, inst_var_off=np.array([0, nv], np.uint32), assumptions=assumps)
+        assert e[0].status == 0 and e[0].verdict == o.verdict, trial
+        assert list(e[0].stats) == list(o.stats), (trial, list(e[0].stats), list(o.stats))
+        assert e[0].trace_hash == o.trace_hash and e[0].n_vars == o.n_vars == nv, trial
+        assert e[0].eliminated_vars == o.eliminated_vars

@@ -610,3 +610,72 @@ def test_bcp_replay_reproduces_recorded_prefixes(pkg):
         assert r["propagations"] > 1000000 and r["bcp_bytes"] > 100 * r["propagations"] and r["ms_min"] > 0
     finally:
         e.close()
+
+
+def _oracle_trait_run(po, kind, n_vars, vflags, clauses_off, clauses_lits, assumps=(), budget=None, resume=0):
+    """the oracle driven the way a caller of the trait drives a solver: new_var* (with flags), add_clause*, preprocess,
+    solve_limited (budget / assumptions), optionally solve_limited again on the Interrupted solver"""
+    po.set_var_flags(vflags)
+    po.set_assumptions(list(assumps))
+    if budget is not None:
+        po.set_budget(budget[0], budget[1], resume)
+    try:
+        return po.solve_csr(clauses_off, clauses_lits, kind=kind)
+    finally:
+        po.set_var_flags(); po.set_assumptions(); po.set_budget()
+
+
+@pytest.mark.parametrize("kind_name", ["core", "simp"])
+def test_trait_semantics_through_the_handle(pkg, po, kind_name):
+    """sat.rs:28-36 through the C ABI handle: new_var(upol, dvar) (decision_heuristic.rs:70-102,181-192), budgets that
+    return INTERRUPTED and leave the handle usable (sat.rs:24, budget.rs:5-34), solve_limited that continues from the
+    state preprocess() left on the device, assumptions (search.rs:216-232) -- all with the oracle's counters."""
+    Solver = pkg.CoreSolver if kind_name == "core" else pkg.SimpSolver
+    okind = po.CORE if kind_name == "core" else po.SIMP
+    rng = np.random.RandomState(11)
+    n, m = 60, 256
+    for trial in range(4):
+        lits = po.gen_ksat(SEED2 + 88000 + trial, n, m)
+        off = np.arange(0, m + 1, dtype=np.uint32) * 3
+        nv = n + 2
+        vf = np.zeros(nv, np.uint8)
+        for v in range(nv):
+            if rng.rand() < 0.25: vf[v] |= 1 | (2 if rng.rand() < 0.5 else 0)
+            if rng.rand() < 0.1: vf[v] |= 4
+        assumps = [int((v << 1) | rng.randint(2)) for v in rng.choice(n, 2, replace=False)] if trial >= 2 else []
+
+        def make():
+            s = Solver()
+            for v in range(nv):
+                s.new_var(None if not (vf[v] & 1) else bool(vf[v] & 2), not (vf[v] & 4))
+            for c in range(m):
+                assert s.add_clause([int(x) for x in lits[off[c]:off[c + 1]]])
+            return s
+
+        # (1) plain: preprocess, then solve_limited continues from the resident state
+        o, om = _oracle_trait_run(po, okind, nv, vf, off, lits, assumps)
+        s = make()
+        assert s.n_vars() == nv
+        assert s.preprocess() == bool(o.pre_ok)
+        assert s.n_clauses() == o.n_clauses_pre
+        r = s.solve_limited(assumptions=assumps)
+        assert r.kind == o.verdict, trial
+        assert [r.stats[k] for k in pkg.STAT_NAMES] == list(o.stats), (trial, r.stats, list(o.stats))
+        if o.verdict == 1:
+            model = np.full(nv, 2, np.uint8)
+            for l in r.model:
+                model[pkg.lit_var(l)] = 0 if pkg.lit_sign(l) else 1
+            assert (model[:len(om)] == om).all(), trial
+        # (2) a conflict budget interrupts; the handle stays usable and the second call finishes the job
+        o1, _ = _oracle_trait_run(po, okind, nv, vf, off, lits, assumps, budget=(3, -1), resume=0)
+        o2, _ = _oracle_trait_run(po, okind, nv, vf, off, lits, assumps, budget=(3, -1), resume=1)
+        s = make()
+        assert s.preprocess()
+        r1 = s.solve_limited(budget=(3, -1), assumptions=assumps)
+        assert r1.kind == o1.verdict and [r1.stats[k] for k in pkg.STAT_NAMES] == list(o1.stats), trial
+        if o1.verdict == pkg.INTERRUPTED:
+            r2 = s.solve_limited(assumptions=assumps)
+            assert r2.kind == o2.verdict and [r2.stats[k] for k in pkg.STAT_NAMES] == list(o2.stats), trial
+            assert r2.stats["solves"] == 2
+        with pytest.raises(pkg.EngineError):
+            s.solve_limited()      # SAT / UNSAT consumed the handle
