@@ -264,6 +264,7 @@ typedef struct b200sat_launch_info {
                                   last warp's exit (device %globaltimer) -- the part of the launch that is bound by
                                   its longest-running instances */
     float    span_ms;          /* search kernel: first block's start to last warp's exit (device %globaltimer) */
+    uint32_t max_warps;        /* warps of the search kernel that can be resident on this GPU at once (SMs x blocks/SM) */
 } b200sat_launch_info;
 int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out);
 
@@ -306,6 +307,9 @@ int  b200sat_engine_ring_ipc_handle(b200sat_engine *e, uint8_t handle[64]); /* c
 int  b200sat_engine_ring_open_peer(b200sat_engine *e, uint32_t slot, const uint8_t handle[64]);
 /* Launch n_replicas replicas (global ids replica_base ...) of instance 0 of the resident batch (CoreSolver).
  * Results (one b200sat_result + model per REPLICA) are fetched with b200sat_engine_download_replicas. */
+/* clauses one replica imports per restart boundary (0 = no cap; default 64).  Every replica also skips clauses whose
+ * order-independent hash it has imported before (8192-bit filter per replica). */
+int  b200sat_engine_set_import_cap(b200sat_engine *e, uint32_t cap);
 int  b200sat_portfolio_solve(b200sat_engine *e, const b200sat_settings *base, uint32_t n_replicas,
                              uint32_t replica_base, uint32_t share_flags, int flags, void *stream);
 int  b200sat_engine_download_replicas(b200sat_engine *e, b200sat_result *results, uint8_t *models,

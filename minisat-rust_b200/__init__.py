@@ -92,7 +92,7 @@ class LaunchInfo(C.Structure):
                 ("warps_total", C.c_uint32), ("tier", C.c_uint32), ("launches", C.c_uint32),
                 ("slab_bytes", C.c_uint64), ("last_kernel_ms", C.c_float), ("search_ms", C.c_float),
                 ("suspends", C.c_uint32), ("resident_items", C.c_uint32), ("tail_ms", C.c_float),
-                ("span_ms", C.c_float)]
+                ("span_ms", C.c_float), ("max_warps", C.c_uint32)]
 
 
 class ReplayInfo(C.Structure):
@@ -122,7 +122,7 @@ ABI_SYMBOLS = (
     "b200sat_engine_verify_models", "b200sat_engine_subsume_instance", "b200sat_engine_simplify_instance", "b200sat_engine_bve_instance", "b200sat_read_dimacs", "b200sat_free_buffer", "b200sat_write_result",
     "b200sat_engine_set_slice", "b200sat_engine_set_budget", "b200sat_engine_interrupt",
     "b200sat_engine_bcp_replay", "b200sat_engine_set_var_flags", "b200sat_engine_set_assumptions",
-    "b200sat_engine_resume", "b200sat_engine_resume_async",
+    "b200sat_engine_resume", "b200sat_engine_resume_async", "b200sat_engine_set_import_cap",
 )
 PF_SHARE, PF_IGNORE_DONE, PF_SHARE_LBD2, PF_KEEP_RING = 1, 2, 4, 8
 
@@ -174,6 +174,7 @@ def lib():
     L.b200sat_engine_set_assumptions.argtypes = [vp, u32p, C.c_uint32]
     L.b200sat_engine_resume.argtypes = [vp, vp]
     L.b200sat_engine_resume_async.argtypes = [vp, vp]
+    L.b200sat_engine_set_import_cap.argtypes = [vp, C.c_uint32]
     L.b200sat_engine_set_slice.argtypes = [vp, C.c_uint32]
     L.b200sat_engine_set_budget.argtypes = [vp, C.c_int64, C.c_int64]
     L.b200sat_engine_interrupt.argtypes = [vp, C.c_int]
@@ -375,6 +376,9 @@ class Engine:
     def resume(self, stream=None):
         """search again on the instances the last solve left parked (INTERRUPTED / NO_SOLVE)"""
         _check(lib().b200sat_engine_resume(self._e, stream))
+
+    def set_import_cap(self, cap):
+        _check(lib().b200sat_engine_set_import_cap(self._e, cap))
 
     def set_slice(self, slice_conflicts):
         """conflicts an instance runs before it yields to waiting ones (0 = never); trace-neutral"""

@@ -340,6 +340,12 @@ extern "C" int b200sat_engine_set_assumptions(b200sat_engine *e, const uint32_t 
     return 0;
 }
 
+/* portfolio: clauses one replica imports per restart boundary (0 = no cap); default 64 */
+extern "C" int b200sat_engine_set_import_cap(b200sat_engine *e, uint32_t cap) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    e->import_cap = cap;
+    return 0;
+}
 extern "C" int b200sat_engine_set_slice(b200sat_engine *e, uint32_t slice_conflicts) {
     if (!e) return set_err(B200SAT_E_ARG, "null engine");
     e->slice_conflicts = slice_conflicts;
@@ -646,6 +652,7 @@ static int launch_attempt(b200sat_engine *e) {
     e->info.grid = shs.grid; e->info.block = shs.wpb * 32; e->info.smem_bytes = (u32)shs.smem;
     e->info.warps_total = shs.grid * shs.wpb; e->info.tier = L.tier; e->info.slab_bytes = L.slab_bytes;
     e->info.resident_items = (u32)slots;
+    e->info.max_warps = (u32)(e->num_sms * shs.bps * shs.wpb);
     e->resident_items = (pd.n_work <= slots && pd.work == nullptr) ? pd.n_work : 0;
     e->resident_L = L; e->resident_tier_nv = pd.tier_nv; e->resident_attempt = pd.attempt;
     return 0;

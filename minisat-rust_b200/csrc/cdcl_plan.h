@@ -23,7 +23,9 @@ static const int kNumSmemTiers = 3;
 
 /* smallest shared-memory tier that holds `nvars`, or 0 for the global tier */
 static inline int pick_tier_nv(u32 nvars, u32 max_clauses) {
-    if (max_clauses > 60000) return 0; /* u16 watch-list lengths */
+    /* u16 watch-list lengths: a single list of more than 65,520 watchers fails with ST_MEM_LIST and the instance is
+     * retried on the global tier; with up to ~200k clauses spread over the literals that practically never happens */
+    if (max_clauses > 200000) return 0;
     for (int i = 0; i < kNumSmemTiers; i++) if (nvars <= (u32)kSmemTiers[i]) return kSmemTiers[i];
     return 0;
 }

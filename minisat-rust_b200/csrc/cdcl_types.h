@@ -50,6 +50,7 @@ struct Layout {
     u64 off_arena[2], off_wpool[2], off_learnts, off_clauses, off_ol, off_tc, off_stk, off_tmp, off_vars,
         off_simp;
     u64 off_save;     /* parked copy of the shared-memory var state of a suspended instance */
+    u64 off_pf;       /* portfolio: 8192-bit filter of the clause hashes this replica already imported */
     u32 save_bytes;   /* = sizeof(SmemVars<NV>) of the tier (sizeof(SmemSmall) for the global tier) */
     u64 slab_bytes;
 };
@@ -81,6 +82,7 @@ static inline void layout_finalize(Layout &L) {
     L.off_vars = o; if (L.tier == 1) o += layout_vars_bytes(L.nv_cap);
     L.off_simp = o; o += layout_align(4ull * L.simp_cap);
     L.off_save = o; o += layout_align(L.save_bytes);
+    L.off_pf = o; o += layout_align(1024);
     L.slab_bytes = layout_align(o);
 }
 

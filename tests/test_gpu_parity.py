@@ -620,7 +620,7 @@ def _oracle_trait_run(po, kind, n_vars, vflags, clauses_off, clauses_lits, assum
     if budget is not None:
         po.set_budget(budget[0], budget[1], resume)
     try:
-        return po.solve_csr(clauses_off, clauses_lits, kind=kind)
+        return po.solve_csr(clauses_off, clauses_lits, kind=kind, flags=po.F_PREPROCESS)
     finally:
         po.set_var_flags(); po.set_assumptions(); po.set_budget()
 
@@ -679,3 +679,51 @@ def test_trait_semantics_through_the_handle(pkg, po, kind_name):
             assert r2.stats["solves"] == 2
         with pytest.raises(pkg.EngineError):
             s.solve_limited()      # SAT / UNSAT consumed the handle
+
+
+@pytest.mark.parametrize("kind_name", ["core", "simp"])
+@pytest.mark.parametrize("corpus", ["corpus_full_cnf.npz", "corpus_full_hard.npz"])
+def test_config1_every_bundled_file(pkg, po, eng, kind_name, corpus):
+    """BASELINE.json configs[0] on EVERYTHING the reference bundles (tests/minisat.rs:12-37 walks every 4th file of
+    the same directories): all 3,023 tests/cnf files and every tests/cnf-hard file inside the fixture's time box, at
+    default settings, one solve each: verdict == SATLIB name class, verdict / 8 stats / trace hash == oracle fixture
+    (tests/golden/make_full_corpus.py), every SAT model checked against its CNF."""
+    import os, time
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", corpus)
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    g = np.load(path)
+    n = len(g["names"])
+    ioff_all, coff_all = g["inst_clause_off"].astype(np.int64), g["clause_off"].astype(np.int64)
+    lits_all = g["lits"].astype(np.uint32)
+    kind = pkg.CORE if kind_name == "core" else pkg.SIMP
+    nv = g["n_vars"]
+    groups = [[i for i in range(n) if lo < nv[i] <= hi] for lo, hi in ((0, 128), (128, 256), (256, 1024), (1024, 1 << 30))]
+    t_all, solved = 0.0, 0
+    for group in groups:
+        if not group:
+            continue
+        insts = []
+        for i in group:
+            cb, ce = ioff_all[i], ioff_all[i + 1]
+            off = coff_all[cb:ce + 1]
+            insts.append(((off - off[0]).astype(np.uint32), lits_all[off[0]:off[-1]]))
+        ioff, coff, lits = batch_of(insts)
+        stride = int(max(nv[i] for i in group))
+        t0 = time.time()
+        res, models = eng.solve_batch(ioff, coff, lits, kind=kind, flags=flags(pkg), model_stride=stride)
+        t_all += time.time() - t0
+        for k, i in enumerate(group):
+            name = str(g["names"][i])
+            assert res[k]["status"] == 0, name
+            assert res[k]["verdict"] == int(g[kind_name + "_verdict"][i]), name
+            if int(g["name_verdict"][i]) >= 0:
+                assert res[k]["verdict"] == int(g["name_verdict"][i]), name
+            assert list(res[k]["stats"]) == [int(x) for x in g[kind_name + "_stats"][i]], name
+            assert int(res[k]["trace_hash"]) == int(g[kind_name + "_hash"][i]), name
+            if kind_name == "simp":
+                assert res[k]["eliminated_vars"] == int(g["simp_elim"][i]) and res[k]["n_clauses_pre"] == int(g["simp_nclauses_pre"][i]), name
+        assert check_models(ioff, coff, lits, res["verdict"], models) == 0
+        solved += len(group)
+    print("\nconfig 1 [%s, %s]: %d instances in %.2f s through the C ABI with host buffers = %.0f instances/s; excluded: %s"
+          % (corpus, kind_name, solved, t_all, solved / t_all, list(g["excluded"])))
