@@ -94,7 +94,10 @@ enum {
     B200SAT_F_NO_SOLVE   = 2,     /* stop after preprocess (--no-solve, lib.rs:83-86)         */
     B200SAT_F_ZERO_STATS_ON_PRE_UNSAT = 4, /* lib.rs:75-78: "Solved by simplification" reports Stats::default() */
     B200SAT_F_TRACE_HASH = 8,     /* fold (bt level, learnt lits) of every conflict into result.trace_hash */
-    B200SAT_F_COUNT_TRAFFIC = 16  /* fill result.traffic (SURVEY.md 8d counters)              */
+    B200SAT_F_COUNT_TRAFFIC = 16, /* fill result.traffic (SURVEY.md 8d counters)              */
+    B200SAT_F_SIMP_OFF_EMPTY = 32 /* with kind CORE: the solver is a SimpSolver whose preprocess() ran on the EMPTY
+                                     formula first (--no-pre, lib.rs:36-41): the simplifier is off, but SimplifyGuard
+                                     already holds (Some(0), 0) (search.rs:114-135), which changes when try_simplify fires */
 };
 
 void        b200sat_default_settings(b200sat_settings *s);   /* the Default impls, SURVEY App. B */
@@ -307,6 +310,8 @@ int  b200sat_engine_ring_ipc_handle(b200sat_engine *e, uint8_t handle[64]); /* c
 int  b200sat_engine_ring_open_peer(b200sat_engine *e, uint32_t slot, const uint8_t handle[64]);
 /* Launch n_replicas replicas (global ids replica_base ...) of instance 0 of the resident batch (CoreSolver).
  * Results (one b200sat_result + model per REPLICA) are fetched with b200sat_engine_download_replicas. */
+/* map the ring of another engine of the SAME process (another GPU) into slot `slot` through CUDA peer access */
+int  b200sat_engine_ring_open_local_peer(b200sat_engine *e, uint32_t slot, b200sat_engine *owner);
 /* clauses one replica imports per restart boundary (0 = no cap; default 64).  Every replica also skips clauses whose
  * order-independent hash it has imported before (8192-bit filter per replica). */
 int  b200sat_engine_set_import_cap(b200sat_engine *e, uint32_t cap);

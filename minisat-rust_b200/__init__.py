@@ -24,6 +24,7 @@ LIB_PATH = os.environ.get("B200SAT_LIB") or os.path.join(_HERE, "libb200sat.so")
 CORE, SIMP = 0, 1
 UNSAT, SAT, INTERRUPTED = 0, 1, 2
 F_PREPROCESS, F_NO_SOLVE, F_ZERO_STATS_ON_PRE_UNSAT, F_TRACE_HASH, F_COUNT_TRAFFIC = 1, 2, 4, 8, 16
+F_SIMP_OFF_EMPTY = 32
 E_NO_DEVICE, E_CUDA, E_ARG, E_SPENT, E_MEM = -1, -2, -3, -4, -5
 STAT_NAMES = ("solves", "restarts", "decisions", "rnd_decisions", "conflicts", "propagations",
               "tot_literals", "del_literals")
@@ -123,6 +124,7 @@ ABI_SYMBOLS = (
     "b200sat_engine_set_slice", "b200sat_engine_set_budget", "b200sat_engine_interrupt",
     "b200sat_engine_bcp_replay", "b200sat_engine_set_var_flags", "b200sat_engine_set_assumptions",
     "b200sat_engine_resume", "b200sat_engine_resume_async", "b200sat_engine_set_import_cap",
+    "b200sat_engine_ring_open_local_peer",
 )
 PF_SHARE, PF_IGNORE_DONE, PF_SHARE_LBD2, PF_KEEP_RING = 1, 2, 4, 8
 
@@ -175,6 +177,7 @@ def lib():
     L.b200sat_engine_resume.argtypes = [vp, vp]
     L.b200sat_engine_resume_async.argtypes = [vp, vp]
     L.b200sat_engine_set_import_cap.argtypes = [vp, C.c_uint32]
+    L.b200sat_engine_ring_open_local_peer.argtypes = [vp, C.c_uint32, vp]
     L.b200sat_engine_set_slice.argtypes = [vp, C.c_uint32]
     L.b200sat_engine_set_budget.argtypes = [vp, C.c_int64, C.c_int64]
     L.b200sat_engine_interrupt.argtypes = [vp, C.c_int]
@@ -376,6 +379,10 @@ class Engine:
     def resume(self, stream=None):
         """search again on the instances the last solve left parked (INTERRUPTED / NO_SOLVE)"""
         _check(lib().b200sat_engine_resume(self._e, stream))
+
+    def ring_open_local_peer(self, slot, owner):
+        """map the ring of `owner` (an Engine of this process on another GPU) through CUDA peer access"""
+        _check(lib().b200sat_engine_ring_open_local_peer(self._e, slot, owner._e))
 
     def set_import_cap(self, cap):
         _check(lib().b200sat_engine_set_import_cap(self._e, cap))

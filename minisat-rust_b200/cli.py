@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-from . import (CORE, SIMP, SAT, UNSAT, INTERRUPTED, F_PREPROCESS, F_NO_SOLVE, Engine, EngineError,
+from . import (CORE, SIMP, SAT, UNSAT, INTERRUPTED, F_PREPROCESS, F_NO_SOLVE, F_SIMP_OFF_EMPTY, Engine, EngineError,
                default_settings, dimacs, lib, mk_lit, SolveRes, Stats, STAT_NAMES)
 
 
@@ -126,11 +126,12 @@ def run(argv=None, out=sys.stdout, errout=sys.stderr):
     # --no-pre on a SimpSolver = preprocess() on the empty formula first, which switches the simplifier off
     # (lib.rs:38-40): from then on the instance is handled exactly like by the core solver
     run_kind = kind if (kind == CORE or pre) else CORE
-    res_ing, _ = eng.solve_batch(ioff, off, lits, settings=st, kind=run_kind, flags=F_NO_SOLVE, model_stride=max(n_vars, 1))
+    no_pre_flag = F_SIMP_OFF_EMPTY if (kind == SIMP and not pre) else 0
+    res_ing, _ = eng.solve_batch(ioff, off, lits, settings=st, kind=run_kind, flags=F_NO_SOLVE | no_pre_flag, model_stride=max(n_vars, 1))
     info("|  Number of variables:  %12d                                         |" % int(res_ing[0]["n_vars"]))
     info("|  Number of clauses:    %12d                                         |" % int(res_ing[0]["n_clauses_ingest"]))
     info("|  Parse time:           %12.2f s                                       |" % (t_parse - t0))
-    flags = F_PREPROCESS | (0 if solve else F_NO_SOLVE)
+    flags = F_PREPROCESS | (0 if solve else F_NO_SOLVE) | no_pre_flag
     res, models = eng.solve_batch(ioff, off, lits, settings=st, kind=run_kind, flags=flags, model_stride=max(n_vars, 1))
     r = res[0]
     if int(r["status"]) != 0:

@@ -207,6 +207,7 @@ struct b200sat_engine {
     /* portfolio: clause-exchange rings (slot my_ring is ours, the others are peer mappings) */
     u32 *rings[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ring_is_peer[8] = {false, false, false, false, false, false, false, false};
+    bool ring_is_local_peer[8] = {false, false, false, false, false, false, false, false};
     u32 n_rings = 0, my_ring = 0, ring_words = 0;
     b200sat_settings *d_replica_settings = nullptr;
     size_t cap_replica_settings = 0;
@@ -281,7 +282,7 @@ extern "C" void b200sat_engine_destroy(b200sat_engine *e) {
     cudaFree(e->d_slabs); cudaFree(e->d_queue); cudaFree(e->d_work[0]); cudaFree(e->d_work[1]);
     cudaFree(e->d_replica_settings); cudaFree(e->d_verified); cudaFree(e->d_pp);
     for (u32 r = 0; r < 8; r++)
-        if (e->rings[r]) { if (e->ring_is_peer[r]) cudaIpcCloseMemHandle(e->rings[r]); else cudaFree(e->rings[r]); }
+        if (e->rings[r]) { if (e->ring_is_local_peer[r]) {} else if (e->ring_is_peer[r]) cudaIpcCloseMemHandle(e->rings[r]); else cudaFree(e->rings[r]); }
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -1158,6 +1159,26 @@ extern "C" int b200sat_engine_ring_open_peer(b200sat_engine *e, uint32_t slot, c
     CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     e->rings[slot] = (u32 *)p;
     e->ring_is_peer[slot] = true;
+    return 0;
+}
+
+/* single-process multi-GPU use (tests, embedding hosts): the ring of another engine of THIS process is mapped through
+ * CUDA peer access instead of an IPC handle (cudaIpcOpenMemHandle refuses handles of the calling process) */
+extern "C" int b200sat_engine_ring_open_local_peer(b200sat_engine *e, uint32_t slot, b200sat_engine *owner) {
+    if (!e || !owner || slot >= e->n_rings || slot == e->my_ring || !owner->rings[owner->my_ring]) return set_err(B200SAT_E_ARG, "bad peer slot");
+    if (owner->ring_words != e->ring_words) return set_err(B200SAT_E_ARG, "rings must have the same size");
+    CK(cudaSetDevice(e->device));
+    if (owner->device != e->device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, e->device, owner->device));
+        if (!can) return set_err(B200SAT_E_CUDA, "no peer access between the two devices");
+        cudaError_t pe = cudaDeviceEnablePeerAccess(owner->device, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return set_err(B200SAT_E_CUDA, cudaGetErrorString(pe));
+        cudaGetLastError();
+    }
+    e->rings[slot] = owner->rings[owner->my_ring];
+    e->ring_is_peer[slot] = true;
+    e->ring_is_local_peer[slot] = true;
     return 0;
 }
 

@@ -117,6 +117,15 @@ B200SAT_HD static inline SimpLayout simp_layout(u32 nv, u32 max_clauses, u64 max
     s.o_opool[0] = o; o += s.opool_cap;
     s.o_opool[1] = o; o += s.opool_cap;
     s.total = o;
+    /* the offsets are u32 words: a layout that does not fit is reported as total = 0 (simp_cap 0 -> ST_MEM_SIMP /
+     * B200SAT_E_MEM) instead of silently wrapping and aliasing regions */
+    {
+        const u64 n64 = nv, M64 = max_clauses, L64 = max_lits, C64 = max_clause_len;
+        const u64 tot = 7 * n64 + (3 * n64 + 3) / 4 + 1 + (8 * M64 + 4096) + (6 * L64 + 8 * n64 + 1024) + (3 * M64 + 2 * n64 + 64) +
+                        3 * (3 * M64 + 256) + (4 * L64 + 64 * (C64 + 32) + 4096) + (3 * M64 + 256) + (4 * C64 + 256) +
+                        2 * (6 * L64 + 16 * n64 + 4096);
+        if (tot > 0xFFFFFFF0ull || max_lits > 0xFFFFFFF0ull) s.total = 0;
+    }
     return s;
 }
 

@@ -2017,7 +2017,8 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
             s.inv_var_decay = 1.0 / st().var_decay;
             s.inv_cla_decay = 1.0 / st().clause_decay;
             s.arena_top = 0; s.wpool_top = 0; s.n_learnts = 0; s.n_clauses = 0; s.num_clauses = 0; s.num_learnts = 0;
-            s.size_adjust_cnt = 0; s.simp_db_assigns = 0; s.simp_db_assigns_set = 0; s.status = ST_OK;
+            s.size_adjust_cnt = 0; s.simp_db_assigns = 0; s.status = ST_OK;
+            s.simp_db_assigns_set = (P.flags & B200SAT_F_SIMP_OFF_EMPTY) ? 1u : 0u; /* lib.rs:36-41: try_simplify already ran once, on nothing */
             s.dec_vars = nvars; s.heap_n = nvars; s.cur_arena = 0; s.cur_wpool = 0; s.eliminated_vars = 0;
             s.remove_satisfied = st().remove_satisfied; s.extra_clause_field = 0; s.elim_n = 0;
             for (int i = 0; i < 8; i++) s.ring_cursor[i] = 0;

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <unordered_set>
 #include <vector>
 #include <zlib.h>
 
@@ -80,7 +81,7 @@ extern "C" int b200sat_read_dimacs(const char *path, int strict, uint32_t **clau
     if (!slurp(path, buf, e)) return fail(err, errcap, e);
     Parser p(buf);
     std::vector<uint32_t> off{0}, ls;
-    std::vector<uint8_t> seen;
+    std::unordered_set<uint32_t> seen;
     bool parsing = false;
     unsigned long long vars = 0, clauses = 0, found = 0, distinct = 0;
     for (;;) {
@@ -110,8 +111,7 @@ extern "C" int b200sat_read_dimacs(const char *path, int strict, uint32_t **clau
                 if (lit == 0) { found++; off.push_back((uint32_t)ls.size()); break; }
                 unsigned long long v = (unsigned long long)(lit < 0 ? -lit : lit);
                 if (v > 0x7FFFFFF0ull) return fail(err, errcap, "variable id too large");
-                if (v >= seen.size()) seen.resize(v + 1, 0);
-                if (!seen[v]) { seen[v] = 1; distinct++; }
+                if (seen.insert((uint32_t)v).second) distinct++; /* HashSet in the reference (dimacs.rs): size follows the distinct ids */
                 ls.push_back((uint32_t)(((v - 1) << 1) | (lit < 0 ? 1u : 0u)));
             }
         }

@@ -1451,6 +1451,7 @@ int oracle_solve_csr(const uint32_t *clause_off, const uint32_t *lits, uint32_t 
     memset(out, 0, sizeof *out);
     Solver solver(*s, kind);
     std::vector<Lit> tmp;
+    if ((flags & ORACLE_F_NO_PRE) && kind == ORACLE_SIMP) solver.preprocess();   /* lib.rs:36-41 */
     /* the trait's own call order (sat.rs:31-32): every var created with its (upol, dvar) before the clauses are added */
     for (size_t v = 0; v < g_var_flags.size(); v++) {
         uint8_t f = g_var_flags[v];

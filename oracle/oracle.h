@@ -63,7 +63,8 @@ enum { ORACLE_CORE = 0, ORACLE_SIMP = 1 };
 enum {
     ORACLE_F_PREPROCESS = 1,  /* call Solver::preprocess before solve_limited (lib.rs:66)            */
     ORACLE_F_NO_SOLVE   = 2,  /* stop after preprocess (--no-solve, lib.rs:83-86) -> INTERRUPTED     */
-    ORACLE_F_ZERO_STATS_ON_PRE_UNSAT = 4 /* lib.rs:75-78 / tests/minisat.rs:116-117: Stats::default() */
+    ORACLE_F_ZERO_STATS_ON_PRE_UNSAT = 4, /* lib.rs:75-78 / tests/minisat.rs:116-117: Stats::default() */
+    ORACLE_F_NO_PRE = 32      /* --no-pre (lib.rs:36-41): SimpSolver::preprocess on the empty formula before parsing  */
 };
 
 typedef struct oracle_result {

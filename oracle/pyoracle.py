@@ -17,6 +17,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 CORE, SIMP = 0, 1
 UNSAT, SAT, INTERRUPTED = 0, 1, 2
 F_PREPROCESS, F_NO_SOLVE, F_ZERO_STATS_ON_PRE_UNSAT = 1, 2, 4
+F_NO_PRE = 32
 STAT_NAMES = ("solves", "restarts", "decisions", "rnd_decisions", "conflicts",
               "propagations", "tot_literals", "del_literals")
 TRAFFIC_NAMES = ("visited", "kept", "deref", "tail", "moves", "implied", "an_words", "learnt_words")

@@ -311,3 +311,19 @@ def test_new_var_flags_and_assumptions(po, emu, kind):
         assert list(e[0].stats) == list(o.stats), (trial, list(e[0].stats), list(o.stats))
         assert e[0].trace_hash == o.trace_hash and e[0].n_vars == o.n_vars == nv, trial
         assert e[0].eliminated_vars == o.eliminated_vars
+
+
+def test_no_pre_simp_solver_is_a_core_solver_with_a_seeded_simplify_guard(po, emu):
+    """--no-pre (lib.rs:36-41): SimpSolver::preprocess runs on the EMPTY formula before parsing; the simplifier is off
+    afterwards but SimplifyGuard holds (Some(0), 0), so try_simplify fires at different moments than in a fresh
+    CoreSolver.  Device: kind CORE + B200SAT_F_SIMP_OFF_EMPTY == oracle SimpSolver with ORACLE_F_NO_PRE."""
+    ioff, coff, lits = synth_batch(po, SEED2 + 9400, 16, 80, 341)
+    st = po.default_settings()
+    ores, om, _ = po.solve_batch(ioff, coff, lits, kind=po.SIMP, flags=po.F_PREPROCESS | po.F_NO_PRE, threads=2, model_stride=80)
+    eres, em = emu.solve_batch(ioff, coff, lits, st, kind=po.CORE, flags=1 | 8 | 32, model_stride=80, sched_seed=4)
+    fresh, _, _ = po.solve_batch(ioff, coff, lits, kind=po.CORE, flags=po.F_PREPROCESS, threads=2)
+    differs = 0
+    for o, e, f in zip(ores, eres, fresh):
+        assert e.status == 0 and e.verdict == o.verdict and list(e.stats) == list(o.stats) and e.trace_hash == o.trace_hash
+        differs += list(f.stats) != list(o.stats)
+    assert differs > 0   # the seeded guard really changes the trace of some instances

@@ -727,3 +727,59 @@ def test_config1_every_bundled_file(pkg, po, eng, kind_name, corpus):
         solved += len(group)
     print("\nconfig 1 [%s, %s]: %d instances in %.2f s through the C ABI with host buffers = %.0f instances/s; excluded: %s"
           % (corpus, kind_name, solved, t_all, solved / t_all, list(g["excluded"])))
+
+
+def test_portfolio_two_gpus_peer_rings_and_cancel(pkg, po):
+    """config 5 plumbing on two GPUs of one box: each GPU's replicas append to their own ring and read the other GPU's
+    ring through peer memory (NVLink P2P); a verdict on one GPU cancels the replicas of the other one."""
+    import threading, time, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", "portfolio_uuf250_0100.npz"))
+    off, lits = g["clause_off"].astype(np.uint32), g["lits"].astype(np.uint32)
+    ioff, coff, li = batch_of([(off, lits)])
+    e0, e1 = pkg.Engine(0), pkg.Engine(1)
+    try:
+        for e, slot in ((e0, 0), (e1, 1)):
+            e.upload(ioff, coff, li)
+            e.ring_create(1 << 20, 2, slot)
+        e0.ring_open_local_peer(1, e1)
+        e1.ring_open_local_peer(0, e0)
+        # (1) clause exchange across the GPUs on a hard UNSAT instance: both sides import, the verdict is UNSAT
+        out = {}
+        def run(e, base, key):
+            out[key] = e.portfolio_solve(512, replica_base=base, share=pkg.PF_SHARE | pkg.PF_KEEP_RING, model_stride=250)
+        for e in (e0, e1):
+            e.ring_reset()
+        torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+        th = [threading.Thread(target=run, args=(e0, 0, "a")), threading.Thread(target=run, args=(e1, 512, "b"))]
+        t0 = time.time()
+        [t.start() for t in th]; [t.join() for t in th]
+        dt = time.time() - t0
+        ra, rb = out["a"][0], out["b"][0]
+        done = [r for r in list(ra) + list(rb) if r["verdict"] != pkg.INTERRUPTED and r["status"] == 0]
+        assert done and all(r["verdict"] == pkg.UNSAT for r in done)
+        assert int(ra["imported"].sum()) > 0 and int(rb["imported"].sum()) > 0
+        assert int(ra["exported"].sum()) > 0 and int(rb["exported"].sum()) > 0
+        # the GPU that did not find the verdict was cancelled through its peer-mapped done word (status 1)
+        assert all(r["status"] in (0, 1) for r in list(ra) + list(rb))
+        assert dt < 120
+        # (2) first-finisher cancel alone: GPU 1 solves a trivial instance at once, GPU 0's replicas of the hard one stop
+        tiny = batch_of([csr_of([[1, 2], [-1, 2], [1, -2]])])
+        e1.upload(*tiny)
+        for e in (e0, e1):
+            e.ring_reset()
+        torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+        def run0():
+            out["c"] = e0.portfolio_solve(256, share=pkg.PF_KEEP_RING, model_stride=250)
+        t = threading.Thread(target=run0)
+        t0 = time.time()
+        t.start()
+        time.sleep(0.5)
+        rt = e1.portfolio_solve(4, replica_base=256, share=pkg.PF_KEEP_RING, model_stride=2)
+        t.join()
+        assert time.time() - t0 < 30          # alone, the hard instance takes minutes
+        assert all(r["verdict"] == pkg.SAT for r in rt[0])
+        assert int((out["c"][0]["status"] == 1).sum()) > 200   # cancelled replicas
+    finally:
+        e0.close(); e1.close()

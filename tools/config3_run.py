@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=64)
     ap.add_argument("--slice", type=int, default=20000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--max-seconds", type=float, default=0.0, help="raise the async interrupt after this long (0 = never): "
+                    "instances still running then are reported as interrupted")
     a = ap.parse_args()
     import torch
     import _b200pkg
@@ -47,10 +49,17 @@ def main():
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
+    import threading
+    killer = threading.Timer(a.max_seconds, lambda: eng.interrupt(True)) if a.max_seconds > 0 else None
+    if killer:
+        killer.start()
     t0 = time.perf_counter()
     eng.solve(kind=pkg.CORE, flags=flags)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    if killer:
+        killer.cancel()
+        eng.interrupt(False)
     info = eng.launch_info()
     res, _ = eng.download(want_models=False)
     verified, n_bad = eng.verify_models()
@@ -59,6 +68,7 @@ def main():
     mine = dict(ms=info["last_kernel_ms"], search_ms=info["search_ms"], tail_ms=info["tail_ms"], span_ms=info["span_ms"],
                 props=float(st[:, 5].sum()), confl=float(st[:, 4].sum()), sat=int((res["verdict"] == pkg.SAT).sum()),
                 unsat=int((res["verdict"] == pkg.UNSAT).sum()), failed=int((res["status"] != 0).sum()),
+                interrupted=int((res["verdict"] == pkg.INTERRUPTED).sum()),
                 bad_models=int(n_bad), max_confl=float(st[:, 4].max()), alg=alg, suspends=info["suspends"],
                 attempts=int(res["attempts"].max()), wall=wall, warps=info["warps_total"])
     keys = sorted(mine)
@@ -79,7 +89,8 @@ def main():
             "conflicts_per_sec": sum(p["confl"] for p in per) / ms * 1e3,
             "conflicts_mean": sum(p["confl"] for p in per) / a.instances, "conflicts_max": max(p["max_confl"] for p in per),
             "sat": int(sum(p["sat"] for p in per)), "unsat": int(sum(p["unsat"] for p in per)),
-            "failed": int(sum(p["failed"] for p in per)), "model_violations": int(sum(p["bad_models"] for p in per)),
+            "failed": int(sum(p["failed"] for p in per)), "interrupted_by_time_limit": int(sum(p["interrupted"] for p in per)),
+            "model_violations": int(sum(p["bad_models"] for p in per)),
             "all_models_verified_on_device": all(p["bad_models"] == 0 for p in per),
             "tail_fraction": max(p["tail_ms"] / max(p["span_ms"], 1e-9) for p in per),
             "tail_ms_per_gpu": [p["tail_ms"] for p in per], "ms_per_gpu": [p["ms"] for p in per],

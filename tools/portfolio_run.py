@@ -27,6 +27,9 @@ import numpy as np  # noqa: E402
 def load_instance(a):
     if a.synthetic >= 0:
         return None, "uniform 3-SAT n=250 m=1065, instance %d of the config-3 sequence" % a.synthetic
+    if a.instance == "uuf250-0100.cnf.gz":   # a hard UNSAT tests/cnf-hard instance (more than 500k conflicts for the reference configuration)
+        g = np.load(os.path.join(ROOT, "tests", "golden", "portfolio_uuf250_0100.npz"))
+        return (g["clause_off"].astype(np.uint32), g["lits"].astype(np.uint32)), "tests/cnf-hard/uuf250-0100.cnf.gz (%d clauses)" % (len(g["clause_off"]) - 1)
     g = np.load(os.path.join(ROOT, "tests", "golden", "corpus_hard.npz"))
     i = list(g["names"]).index(a.instance)
     cb, ce = int(g["inst_clause_off"][i]), int(g["inst_clause_off"][i + 1])
@@ -132,7 +135,20 @@ def main():
         elif arm == "noshare":
             run_arm("no_sharing", n_rep, 0)
         elif arm == "single":
-            run_arm("single_replica_reference_configuration", 1, pkg.PF_IGNORE_DONE, only_rank0=True)
+            # the reference configuration alone on one warp: the plain trace-mode solve (with the larger-slab retry ladder)
+            if rank == 0:
+                killer = threading.Timer(a.budget_s, lambda: eng.interrupt(True))
+                killer.start()
+                t0 = time.perf_counter()
+                eng.solve(kind=pkg.CORE, flags=pkg.F_PREPROCESS)
+                secs = time.perf_counter() - t0
+                killer.cancel(); eng.interrupt(False)
+                r1, _ = eng.download(want_models=False)
+                out["arms"]["single_replica_reference_configuration"] = {
+                    "time_to_verdict_s": secs, "verdicts": [int(r1[0]["verdict"])], "conflicts": int(r1[0]["stats"][4]),
+                    "status": int(r1[0]["status"]), "note": "verdict 2 = stopped by --budget-s"}
+            if dist is not None:
+                dist.barrier()
     if a.cpu and rank == 0:
         from oracle import pyoracle as po
         try:
