@@ -271,6 +271,12 @@ typedef struct b200sat_launch_info {
 } b200sat_launch_info;
 int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out);
 
+/* Progress rows of the reference's search table (search.rs:289-301: printed whenever the learnt-clause limit is bumped),
+ * recorded on the device for every instance solved with B200SAT_F_COUNT_TRAFFIC while rows > 0.  One row = 8 doubles:
+ * conflicts, free decision vars, original clauses, their literals, learnt limit, learnts, literals per learnt, progress %. */
+int b200sat_engine_set_progress_rows(b200sat_engine *e, uint32_t rows);
+int b200sat_engine_download_progress(b200sat_engine *e, uint32_t inst, double *out, uint32_t cap_rows, uint32_t *n_rows);
+
 /* K2 bcp_replay (measurement; SURVEY.md 8d "BCP-only figure", reference function watches.rs:64-152): the resident
  * batch is solved once with the instrumented kernels while every instance's search prefix is recorded (decisions,
  * learnt clauses + backtrack levels, restarts, up to the first database reduction or ground simplification); the

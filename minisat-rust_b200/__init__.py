@@ -124,7 +124,7 @@ ABI_SYMBOLS = (
     "b200sat_engine_set_slice", "b200sat_engine_set_budget", "b200sat_engine_interrupt",
     "b200sat_engine_bcp_replay", "b200sat_engine_set_var_flags", "b200sat_engine_set_assumptions",
     "b200sat_engine_resume", "b200sat_engine_resume_async", "b200sat_engine_set_import_cap",
-    "b200sat_engine_ring_open_local_peer",
+    "b200sat_engine_ring_open_local_peer", "b200sat_engine_set_progress_rows", "b200sat_engine_download_progress",
 )
 PF_SHARE, PF_IGNORE_DONE, PF_SHARE_LBD2, PF_KEEP_RING = 1, 2, 4, 8
 
@@ -176,6 +176,8 @@ def lib():
     L.b200sat_engine_set_assumptions.argtypes = [vp, u32p, C.c_uint32]
     L.b200sat_engine_resume.argtypes = [vp, vp]
     L.b200sat_engine_resume_async.argtypes = [vp, vp]
+    L.b200sat_engine_set_progress_rows.argtypes = [vp, C.c_uint32]
+    L.b200sat_engine_download_progress.argtypes = [vp, C.c_uint32, C.POINTER(C.c_double), C.c_uint32, u32p]
     L.b200sat_engine_set_import_cap.argtypes = [vp, C.c_uint32]
     L.b200sat_engine_ring_open_local_peer.argtypes = [vp, C.c_uint32, vp]
     L.b200sat_engine_set_slice.argtypes = [vp, C.c_uint32]
@@ -383,6 +385,16 @@ class Engine:
     def ring_open_local_peer(self, slot, owner):
         """map the ring of `owner` (an Engine of this process on another GPU) through CUDA peer access"""
         _check(lib().b200sat_engine_ring_open_local_peer(self._e, slot, owner._e))
+
+    def set_progress_rows(self, rows):
+        """record the search-table progress rows (search.rs:289-301) of solves run with F_COUNT_TRAFFIC"""
+        _check(lib().b200sat_engine_set_progress_rows(self._e, rows))
+
+    def progress_rows(self, inst=0, cap=256):
+        out = np.zeros((cap, 8), dtype=np.float64)
+        n = C.c_uint32()
+        _check(lib().b200sat_engine_download_progress(self._e, inst, out.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(n)))
+        return out[:n.value]
 
     def set_import_cap(self, cap):
         _check(lib().b200sat_engine_set_import_cap(self._e, cap))

@@ -6,8 +6,9 @@ src/sat/minisat/search.rs:398-405 search table frame).
 
 Log lines go to stderr (the reference logs through env_logger to stderr), the verdict line to
 stdout.  Out-of-range flag values are silently ignored, `--phase-saving` is a no-op and
-`--rsync` does not exist, exactly as in the reference.  Not reproduced in round 1: the
-per-learnt-limit progress rows inside the search table (the device does not log them).
+`--rsync` does not exist, exactly as in the reference.  The per-learnt-limit progress rows of
+the search table (search.rs:289-301) are recorded on the device by the instrumented kernel and
+printed after the solve (`--verb 1`); `--no-pre` seeds the SimplifyGuard as lib.rs:36-41 does.
 Solving runs on the GPU through the C ABI; there is no CPU path.
 """
 import argparse
@@ -16,7 +17,7 @@ import time
 
 import numpy as np
 
-from . import (CORE, SIMP, SAT, UNSAT, INTERRUPTED, F_PREPROCESS, F_NO_SOLVE, F_SIMP_OFF_EMPTY, Engine, EngineError,
+from . import (CORE, SIMP, SAT, UNSAT, INTERRUPTED, F_PREPROCESS, F_NO_SOLVE, F_SIMP_OFF_EMPTY, F_COUNT_TRAFFIC, Engine, EngineError,
                default_settings, dimacs, lib, mk_lit, SolveRes, Stats, STAT_NAMES)
 
 
@@ -132,6 +133,9 @@ def run(argv=None, out=sys.stdout, errout=sys.stderr):
     info("|  Number of clauses:    %12d                                         |" % int(res_ing[0]["n_clauses_ingest"]))
     info("|  Parse time:           %12.2f s                                       |" % (t_parse - t0))
     flags = F_PREPROCESS | (0 if solve else F_NO_SOLVE) | no_pre_flag
+    if verb >= 1 and solve:
+        eng.set_progress_rows(256)   # the search table's progress rows come from the instrumented kernel
+        flags |= F_COUNT_TRAFFIC
     res, models = eng.solve_batch(ioff, off, lits, settings=st, kind=run_kind, flags=flags, model_stride=max(n_vars, 1))
     r = res[0]
     if int(r["status"]) != 0:
@@ -151,6 +155,9 @@ def run(argv=None, out=sys.stdout, errout=sys.stderr):
         info("| Conflicts |          ORIGINAL         |          LEARNT          | Progress |")
         info("|           |    Vars  Clauses Literals |    Limit  Clauses Lit/Cl |          |")
         info("===============================================================================")
+        for row in eng.progress_rows(0):   # search.rs:289-301, one row per learnt-limit bump
+            info("| %9d | %7d %8d %8d | %8d %8d %6.0f | %6.3f %% |" % (int(row[0]), int(row[1]), int(row[2]), int(row[3]),
+                                                                       int(row[4]), int(row[5]), row[6], row[7]))
         info("===============================================================================")
         verdict = int(r["verdict"])
     cpu_time = time.perf_counter() - t0

@@ -190,6 +190,9 @@ struct b200sat_engine {
     u32 *d_assumps = nullptr;     /* assumptions of the following solve calls */
     size_t cap_assumps = 0;
     u32 n_assumps = 0;
+    double *d_progress = nullptr; /* CLI search-table rows of the instrumented kernel */
+    size_t cap_progress = 0;
+    u32 progress_rows = 0;
     u32 *d_trace = nullptr;       /* K2: per-instance event record of the search prefix */
     size_t cap_trace = 0;
     u32 trace_cap = 0;            /* words per instance; 0 = recording off */
@@ -292,7 +295,7 @@ extern "C" void b200sat_engine_destroy(b200sat_engine *e) {
     if (e->h_interrupt) cudaFreeHost(e->h_interrupt);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     cudaFree(e->d_ring);
-    cudaFree(e->d_trace); cudaFree(e->d_parked); cudaFree(e->d_var_flags); cudaFree(e->d_var_off); cudaFree(e->d_assumps);
+    cudaFree(e->d_trace); cudaFree(e->d_progress); cudaFree(e->d_parked); cudaFree(e->d_var_flags); cudaFree(e->d_var_off); cudaFree(e->d_assumps);
     delete e;
 }
 
@@ -341,6 +344,29 @@ extern "C" int b200sat_engine_set_assumptions(b200sat_engine *e, const uint32_t 
     return 0;
 }
 
+/* Rows of the reference's search table (search.rs:289-301: one per learnt-limit bump) are recorded for every instance
+ * of the following solves that run with B200SAT_F_COUNT_TRAFFIC (the instrumented kernels); rows = 0 switches it off. */
+extern "C" int b200sat_engine_set_progress_rows(b200sat_engine *e, uint32_t rows) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    e->progress_rows = rows;
+    return 0;
+}
+/* out: rows x 8 doubles {conflicts, vars, clauses, literals, learnt limit, learnts, literals per learnt, progress %} */
+extern "C" int b200sat_engine_download_progress(b200sat_engine *e, uint32_t inst, double *out, uint32_t cap_rows, uint32_t *n_rows) {
+    if (!e || !out || !n_rows || inst >= e->n_inst) return set_err(B200SAT_E_ARG, "bad argument");
+    *n_rows = 0;
+    if (!e->progress_rows || !e->d_progress) return 0;
+    CK(cudaSetDevice(e->device));
+    const size_t stride = 1 + 8 * (size_t)e->progress_rows;
+    std::vector<double> h(stride);
+    CK(cudaMemcpy(h.data(), e->d_progress + inst * stride, stride * sizeof(double), cudaMemcpyDeviceToHost));
+    u32 n = (u32)h[0];
+    if (n > e->progress_rows) n = e->progress_rows;
+    if (n > cap_rows) n = cap_rows;
+    memcpy(out, h.data() + 1, (size_t)n * 8 * sizeof(double));
+    *n_rows = n;
+    return 0;
+}
 /* portfolio: clauses one replica imports per restart boundary (0 = no cap); default 64 */
 extern "C" int b200sat_engine_set_import_cap(b200sat_engine *e, uint32_t cap) {
     if (!e) return set_err(B200SAT_E_ARG, "null engine");
@@ -565,6 +591,7 @@ static void fill_params(b200sat_engine *e, KParams &P, const Layout &L) {
     P.import_cap = e->import_cap;
     P.trace_buf = e->trace_cap ? e->d_trace : nullptr; P.trace_cap = e->trace_cap;
     P.parked = e->d_parked;
+    if (e->progress_rows && e->d_progress && !pd.portfolio) { P.progress_buf = e->d_progress; P.progress_cap = e->progress_rows; }
     if (e->have_var_flags && !pd.portfolio) { P.var_flags = e->d_var_flags; P.inst_var_off = e->d_var_off; }
     P.assumps = e->d_assumps; P.n_assumps = e->n_assumps;
 }
@@ -674,6 +701,11 @@ extern "C" int b200sat_engine_solve_async(b200sat_engine *e, const b200sat_setti
     if (e->n_inst == 0) return 0;
     pd.st = *s; pd.kind = kind; pd.flags = flags;
     pd.attempt = 0; pd.n_work = e->n_inst; pd.work = nullptr; pd.total_ms = 0.f; pd.search_ms = 0.f; pd.retried = false; pd.resumed = false;
+    if (e->progress_rows && (flags & B200SAT_F_COUNT_TRAFFIC)) {
+        const size_t words = (size_t)e->n_inst * (1 + 8 * (size_t)e->progress_rows);
+        if ((rc = ensure(e->d_progress, e->cap_progress, words))) return rc;
+        CK(cudaMemsetAsync(e->d_progress, 0, words * sizeof(double), pd.stream));
+    }
     /* model rows of instances that end without a model read "undefined" */
     if (e->d_models) CK(cudaMemsetAsync(e->d_models, 2, (size_t)e->n_inst * e->model_stride, pd.stream));
     pd.portfolio = 0; pd.replica_base = 0; pd.share = 0;

@@ -169,6 +169,9 @@ struct KParams {
     const u32 *assumps;       /* assumptions of solve_limited (sat.rs:34), shared by every instance of the batch */
     u32 n_assumps;
     u8 *parked;               /* [item] 1: the item's state is resident and resumable (PH_READY), 0: not */
+    double *progress_buf;     /* CLI search-table rows (search.rs:289-301), instrumented kernel only: per item
+                                 [n_rows][8 values per row ...], or NULL */
+    u32 progress_cap;         /* rows per item */
     u32 *trace_buf;           /* K2: per-item event record of the search prefix (instrumented kernel only), or NULL */
     u32 trace_cap;            /* words per item in trace_buf                                             */
     u32 import_cap;           /* portfolio: clauses one replica imports per restart boundary (0 = no cap) */

@@ -1787,6 +1787,10 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
                         if (P.share & PF_SHARE) export_clause(n);
                         if (cancelled()) { fail(ST_CANCELLED); return SR_ABORT; }
                     }
+                    /* the reference prints its progress row inside handle_conflict, i.e. BEFORE the trail is backtracked
+                     * (search.rs:263-304 vs :503-517): the estimate is taken here when this conflict bumps the limit */
+                    double row_progress = 0.0;
+                    if (COUNT && P.progress_buf && sc().size_adjust_cnt == 1) row_progress = progress_estimate() * 100.0;
                     cancel_until(bt);
                     u32 reason = CREF_UNDEF;
                     const u32 *out = ol();
@@ -1815,6 +1819,20 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
                             sc().size_adjust_confl *= st().size_adjust_inc;
                             sc().size_adjust_cnt = (i32)sc().size_adjust_confl;
                             sc().max_learnts *= st().size_inc;
+                            if (COUNT && P.progress_buf) { /* the progress row of the search table, search.rs:289-301 */
+                                double *pb = P.progress_buf + (size_t)res_index * (1 + 8 * (size_t)P.progress_cap);
+                                const u32 row = (u32)pb[0];
+                                if (row < P.progress_cap) {
+                                    const u32 ground = nlevels > 1 ? (u32)V.lim()[1] : trail_n;
+                                    double *r = pb + 1 + 8 * (size_t)row;
+                                    r[0] = (double)sc().conflicts; r[1] = (double)(sc().dec_vars - ground);
+                                    r[2] = (double)sc().num_clauses; r[3] = (double)sc().clauses_literals;
+                                    r[4] = (double)(u64)sc().max_learnts; r[5] = (double)sc().num_learnts;
+                                    r[6] = (double)sc().learnts_literals / (double)sc().num_learnts;
+                                    r[7] = row_progress;
+                                    pb[0] = (double)(row + 1);
+                                }
+                            }
                         }
                     }
                     __syncwarp();

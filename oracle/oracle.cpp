@@ -630,6 +630,8 @@ struct LearningGuard {                                                     /* :7
 };
 
 struct TraceSink { uint64_t *buf = nullptr; uint32_t cap = 0, n = 0; };
+struct ProgressRow { double v[8]; };
+static std::vector<ProgressRow> *g_progress_rows = nullptr;   /* single-threaded use only (oracle_solve_csr) */
 static thread_local TraceSink g_trace;
 
 struct Searcher {
@@ -817,7 +819,12 @@ struct Searcher {
         }
         heur.decay_activity();
         db.decay_activity();
-        learnt.bump();
+        if (learnt.bump() && g_progress_rows) {                            /* the info! row of :289-301 (trail not yet backtracked) */
+            size_t ground = assigns.lim.size() > 1 ? assigns.lim[1] : assigns.trail.size();
+            g_progress_rows->push_back({(double)conflicts, (double)(heur.dec_vars - (int64_t)ground), (double)db.stats.num_clauses,
+                                        (double)db.stats.clauses_literals, (double)(uint64_t)learnt.max_learnts, (double)db.stats.num_learnts,
+                                        (double)db.stats.learnts_literals / (double)db.stats.num_learnts, progress_estimate() * 100.0});
+        }
         return true;
     }
 
@@ -1434,6 +1441,14 @@ void oracle_default_settings(oracle_settings *s) {
 
 void oracle_set_trace(uint64_t *buf, uint32_t cap) { g_trace.buf = buf; g_trace.cap = cap; g_trace.n = 0; }
 
+static std::vector<ProgressRow> g_progress_store;
+/* record the search-table rows (search.rs:289-301) of the following oracle_solve_csr calls; read them back afterwards */
+void oracle_record_progress(int on) { g_progress_store.clear(); g_progress_rows = on ? &g_progress_store : nullptr; }
+uint32_t oracle_get_progress(double *out, uint32_t cap_rows) {
+    uint32_t n = (uint32_t)std::min<size_t>(cap_rows, g_progress_store.size());
+    for (uint32_t i = 0; i < n; i++) memcpy(out + 8 * (size_t)i, g_progress_store[i].v, sizeof(double) * 8);
+    return n;
+}
 static std::vector<uint8_t> g_var_flags;   /* bit0 upol set, bit1 upol value, bit2 not a decision var */
 static std::vector<Lit> g_assumptions;
 void oracle_set_var_flags(const uint8_t *flags, uint32_t n) { g_var_flags.assign(flags, flags + (flags ? n : 0)); }

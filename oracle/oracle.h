@@ -131,6 +131,11 @@ void oracle_set_var_flags(const uint8_t *flags, uint32_t n);
 /* assumptions (&[Lit]) of the NEXT solve_limited calls; n = 0 clears them (search.rs:216-232,431-435) */
 void oracle_set_assumptions(const uint32_t *lits, uint32_t n);
 
+/* rows of the reference's search table (search.rs:289-301), recorded by the following oracle_solve_csr calls
+ * (single-threaded use); 8 doubles per row */
+void oracle_record_progress(int on);
+uint32_t oracle_get_progress(double *out, uint32_t cap_rows);
+
 /* dump per-conflict trace (debugging divergences): up to cap records of
  * (bt_level, learnt_len, hash). Enabled per call through oracle_set_trace. */
 void oracle_set_trace(uint64_t *buf, uint32_t cap_records);

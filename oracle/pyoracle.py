@@ -137,6 +137,9 @@ def lib():
         L.oracle_check_model.restype = C.c_int
         L.oracle_set_trace.argtypes = [C.POINTER(C.c_uint64), C.c_uint32]
         L.oracle_set_budget.argtypes = [C.c_int64, C.c_int64, C.c_int]
+        L.oracle_record_progress.argtypes = [C.c_int]
+        L.oracle_get_progress.argtypes = [C.POINTER(C.c_double), C.c_uint32]
+        L.oracle_get_progress.restype = C.c_uint32
         L.oracle_set_var_flags.argtypes = [C.POINTER(C.c_uint8), C.c_uint32]
         L.oracle_set_assumptions.argtypes = [C.POINTER(C.c_uint32), C.c_uint32]
         _lib = L
@@ -193,6 +196,18 @@ def solve_batch(inst_clause_off, clause_off, lits, kind=SIMP,
     secs = lib().oracle_solve_batch_csr(ioffp, offp, lip, n, C.byref(s), kind, flags, threads,
                                         results, mp, model_stride)
     return results, models, secs
+
+
+def solve_csr_with_progress(clause_off, lits, kind=SIMP, settings=None, cap=256):
+    """solve_csr + the rows of the search table (search.rs:289-301) as an (n, 8) float64 array"""
+    lib().oracle_record_progress(1)
+    try:
+        r, m = solve_csr(clause_off, lits, kind=kind, settings=settings)
+        out = np.zeros((cap, 8), dtype=np.float64)
+        n = lib().oracle_get_progress(out.ctypes.data_as(C.POINTER(C.c_double)), cap)
+    finally:
+        lib().oracle_record_progress(0)
+    return r, m, out[:n]
 
 
 def set_budget(conflict_budget=-1, propagation_budget=-1, resume_rounds=0):

@@ -783,3 +783,20 @@ def test_portfolio_two_gpus_peer_rings_and_cancel(pkg, po):
         assert int((out["c"][0]["status"] == 1).sum()) > 200   # cancelled replicas
     finally:
         e0.close(); e1.close()
+
+
+def test_search_table_progress_rows(pkg, po, eng):
+    """The CLI's search table (search.rs:289-301): the rows the device records at every learnt-limit bump equal the
+    oracle's, value by value (conflicts, free vars, clauses, literals, limit, learnts, lits per learnt, progress %)."""
+    lits = po.gen_ksat(SEED3 + 3, 250, 1065)
+    off = np.arange(0, 1066, dtype=np.uint32) * 3
+    o, _, orows = po.solve_csr_with_progress(off, lits, kind=po.CORE)
+    assert len(orows) >= 3
+    eng.set_progress_rows(256)
+    try:
+        res, _ = eng.solve_batch(np.array([0, 1065], np.uint32), off, lits, kind=pkg.CORE, flags=flags(pkg), model_stride=250)
+        rows = eng.progress_rows(0)
+    finally:
+        eng.set_progress_rows(0)
+    assert list(res[0]["stats"]) == list(o.stats)
+    assert rows.shape == orows.shape and (rows == orows).all(), (rows[:3], orows[:3])
