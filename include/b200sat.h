@@ -268,6 +268,7 @@ typedef struct b200sat_launch_info {
                                   its longest-running instances */
     float    span_ms;          /* search kernel: first block's start to last warp's exit (device %globaltimer) */
     uint32_t max_warps;        /* warps of the search kernel that can be resident on this GPU at once (SMs x blocks/SM) */
+    uint32_t rescued;          /* free-running mode: instances decided by a helper replica (b200sat_engine_set_rescue) */
 } b200sat_launch_info;
 int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out);
 
@@ -276,6 +277,16 @@ int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out);
  * conflicts, free decision vars, original clauses, their literals, learnt limit, learnts, literals per learnt, progress %. */
 int b200sat_engine_set_progress_rows(b200sat_engine *e, uint32_t rows);
 int b200sat_engine_download_progress(b200sat_engine *e, uint32_t inst, double *out, uint32_t cap_rows, uint32_t *n_rows);
+
+/* Free-running mode with straggler rescue -- NOT the reference trace (default: off).  Once the device work ring is empty,
+ * warps with nothing left to do clone the post-ingest state of instances that are still running into their own slabs
+ * and search them as diversified helper replicas (the portfolio machinery: units / binaries exchanged through a ring
+ * per running warp, first finisher claims the instance).  The original replica exports but never imports, so an
+ * instance it decides itself still carries the reference's counters; an instance a helper decided first has
+ * `attempts & 0x100` set and the helper's counters.  Verdicts are exact either way and every SAT model satisfies the
+ * original formula (b200sat_engine_verify_models).  This is what removes the tail of a batch: in trace mode a launch
+ * lasts as long as its hardest instance on ONE warp. */
+int b200sat_engine_set_rescue(b200sat_engine *e, int on);
 
 /* K2 bcp_replay (measurement; SURVEY.md 8d "BCP-only figure", reference function watches.rs:64-152): the resident
  * batch is solved once with the instrumented kernels while every instance's search prefix is recorded (decisions,

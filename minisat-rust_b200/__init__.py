@@ -93,7 +93,7 @@ class LaunchInfo(C.Structure):
                 ("warps_total", C.c_uint32), ("tier", C.c_uint32), ("launches", C.c_uint32),
                 ("slab_bytes", C.c_uint64), ("last_kernel_ms", C.c_float), ("search_ms", C.c_float),
                 ("suspends", C.c_uint32), ("resident_items", C.c_uint32), ("tail_ms", C.c_float),
-                ("span_ms", C.c_float), ("max_warps", C.c_uint32)]
+                ("span_ms", C.c_float), ("max_warps", C.c_uint32), ("rescued", C.c_uint32)]
 
 
 class ReplayInfo(C.Structure):
@@ -125,6 +125,7 @@ ABI_SYMBOLS = (
     "b200sat_engine_bcp_replay", "b200sat_engine_set_var_flags", "b200sat_engine_set_assumptions",
     "b200sat_engine_resume", "b200sat_engine_resume_async", "b200sat_engine_set_import_cap",
     "b200sat_engine_ring_open_local_peer", "b200sat_engine_set_progress_rows", "b200sat_engine_download_progress",
+    "b200sat_engine_set_rescue",
 )
 PF_SHARE, PF_IGNORE_DONE, PF_SHARE_LBD2, PF_KEEP_RING = 1, 2, 4, 8
 
@@ -178,6 +179,7 @@ def lib():
     L.b200sat_engine_resume_async.argtypes = [vp, vp]
     L.b200sat_engine_set_progress_rows.argtypes = [vp, C.c_uint32]
     L.b200sat_engine_download_progress.argtypes = [vp, C.c_uint32, C.POINTER(C.c_double), C.c_uint32, u32p]
+    L.b200sat_engine_set_rescue.argtypes = [vp, C.c_int]
     L.b200sat_engine_set_import_cap.argtypes = [vp, C.c_uint32]
     L.b200sat_engine_ring_open_local_peer.argtypes = [vp, C.c_uint32, vp]
     L.b200sat_engine_set_slice.argtypes = [vp, C.c_uint32]
@@ -395,6 +397,10 @@ class Engine:
         n = C.c_uint32()
         _check(lib().b200sat_engine_download_progress(self._e, inst, out.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(n)))
         return out[:n.value]
+
+    def set_rescue(self, on=True):
+        """free-running mode: idle warps help instances that are still running (NOT the reference trace for those)"""
+        _check(lib().b200sat_engine_set_rescue(self._e, 1 if on else 0))
 
     def set_import_cap(self, cap):
         _check(lib().b200sat_engine_set_import_cap(self._e, cap))

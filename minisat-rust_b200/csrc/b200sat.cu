@@ -180,6 +180,11 @@ struct b200sat_engine {
     int *h_interrupt = nullptr;   /* pinned staging of the async interrupt word (Budget::asynch_interrupt) */
     int *d_interrupt = nullptr;   /* the word the kernels poll (device memory, d_queue + 48)               */
     cudaStream_t side_stream = nullptr; /* carries the interrupt word to the device while a solve is running */
+    bool rescue = false;          /* free-running mode: idle warps help instances that are still running */
+    u8 *d_pristine = nullptr;     /* copy of the slabs as the ingest kernel left them (rescue mode) */
+    size_t cap_pristine = 0;
+    u32 *d_run_table = nullptr, *d_rrings = nullptr;
+    size_t cap_run_table = 0, cap_rrings = 0;
     u8 *d_parked = nullptr;       /* [item] resumable state resident in its slab */
     size_t cap_parked = 0;
     u8 *d_var_flags = nullptr;    /* Solver::new_var(upol, dvar) records of the resident batch (optional) */
@@ -295,7 +300,7 @@ extern "C" void b200sat_engine_destroy(b200sat_engine *e) {
     if (e->h_interrupt) cudaFreeHost(e->h_interrupt);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     cudaFree(e->d_ring);
-    cudaFree(e->d_trace); cudaFree(e->d_progress); cudaFree(e->d_parked); cudaFree(e->d_var_flags); cudaFree(e->d_var_off); cudaFree(e->d_assumps);
+    cudaFree(e->d_trace); cudaFree(e->d_progress); cudaFree(e->d_pristine); cudaFree(e->d_run_table); cudaFree(e->d_rrings); cudaFree(e->d_parked); cudaFree(e->d_var_flags); cudaFree(e->d_var_off); cudaFree(e->d_assumps);
     delete e;
 }
 
@@ -365,6 +370,17 @@ extern "C" int b200sat_engine_download_progress(b200sat_engine *e, uint32_t inst
     if (n > cap_rows) n = cap_rows;
     memcpy(out, h.data() + 1, (size_t)n * 8 * sizeof(double));
     *n_rows = n;
+    return 0;
+}
+/* Free-running mode with straggler rescue (default off = trace mode): once the work ring is empty, idle warps clone the
+ * post-ingest state of instances that are still running and search them as diversified helper replicas that exchange
+ * units / binaries with each other; the first replica to finish decides the instance.  Verdicts stay exact and every
+ * SAT model is one of the original formula; the counters of an instance a helper decided (result.attempts & 0x100) are
+ * the helper's, not the reference trace's.  Needs the whole batch resident at once (2 x the slab memory); not
+ * combined with budgets, traffic counting or the portfolio call. */
+extern "C" int b200sat_engine_set_rescue(b200sat_engine *e, int on) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    e->rescue = on != 0;
     return 0;
 }
 /* portfolio: clauses one replica imports per restart boundary (0 = no cap); default 64 */
@@ -608,6 +624,8 @@ static int launch_attempt(b200sat_engine *e) {
     size_t spw_i = 0, spw_s = 0, save = 0, save2 = 0;
     kernel_fn fn_i = pick_ingest(pd.tier_nv, count, pd.kind, spw_i, save);
     kernel_fn fn_s = pick_search(pd.tier_nv, count, pd.portfolio != 0, spw_s, save2);
+    const bool rescue = e->rescue && !pd.portfolio && !e->replay_mode && !count && !(pd.flags & B200SAT_F_NO_SOLVE);
+    if (rescue) fn_s = b200sat_pick_search_rescue(pd.tier_nv, &spw_s, &save2);
     if (e->replay_mode) fn_s = e->replay_mode == 1 ? b200sat_pick_replay_c1(pd.tier_nv, &spw_s, &save2) : b200sat_pick_replay_c0(pd.tier_nv, &spw_s, &save2);
     Layout L = plan_layout(e->shape, pd.tier_nv, pd.kind, pd.attempt, e->cfg_arena, e->cfg_wpool, (u32)save);
     /* resident items per chunk: every item owns a slab; bounded by ~60% of the free HBM */
@@ -615,7 +633,7 @@ static int launch_attempt(b200sat_engine *e) {
     if (slots * L.slab_bytes > e->cap_slabs) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        size_t budget = (size_t)((double)(free_b + e->cap_slabs) * 0.6);
+        size_t budget = (size_t)((double)(free_b + e->cap_slabs) * (rescue ? 0.3 : 0.6));
         if (e->cfg_slab_budget && e->cfg_slab_budget < budget) budget = e->cfg_slab_budget;
         if (slots * L.slab_bytes > budget) {
             slots = budget / L.slab_bytes;
@@ -635,11 +653,31 @@ static int launch_attempt(b200sat_engine *e) {
         CK(cudaStreamSynchronize(stream));
         if ((rc = ensure(e->d_ring, e->cap_ring, (size_t)ring_cap))) return rc;
     }
+    const u32 rr_words = 4096;
+    if (rescue) {
+        if (pd.n_work > slots) return set_err(B200SAT_E_MEM, "straggler rescue needs the whole batch resident at once");
+        if ((rc = ensure(e->d_pristine, e->cap_pristine, (size_t)(slots * L.slab_bytes)))) return rc;
+        if ((rc = ensure(e->d_run_table, e->cap_run_table, (size_t)shs.grid + 32))) return rc;
+        if ((rc = ensure(e->d_rrings, e->cap_rrings, (size_t)shs.grid * (RING_PAYLOAD + rr_words)))) return rc;
+        CK(cudaMemsetAsync(e->d_run_table, 0, ((size_t)shs.grid + 32) * 4, stream));
+        CK(cudaMemsetAsync(e->d_rrings, 0, (size_t)shs.grid * (RING_PAYLOAD + rr_words) * 4, stream));
+        /* diversified settings of the helper replicas (entry 0 = the reference configuration) */
+        const u32 n_div = 64;
+        std::vector<b200sat_settings> hs(n_div);
+        for (u32 i = 0; i < n_div; i++) diversify_settings(&pd.st, i, &hs[i]);
+        if ((rc = ensure(e->d_replica_settings, e->cap_replica_settings, (size_t)n_div))) return rc;
+        CK(cudaMemcpyAsync(e->d_replica_settings, hs.data(), n_div * sizeof(b200sat_settings), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream)); /* hs is a local */
+    }
     if ((rc = ensure(e->d_parked, e->cap_parked, (size_t)std::max<u64>(pd.n_work, 1)))) return rc;
     CK(cudaMemsetAsync(e->d_parked, 0, (size_t)std::max<u64>(pd.n_work, 1), stream));
     KParams P;
     fill_params(e, P, L);
     P.ring_mask = ring_cap - 1;
+    if (rescue) {
+        P.rescue = 1; P.run_table = e->d_run_table; P.rrings = e->d_rrings; P.rr_words = rr_words; P.pristine = e->d_pristine;
+        P.n_div = 64; P.replica_settings = e->d_replica_settings; P.share = PF_SHARE; P.import_cap = e->import_cap;
+    }
     CK(cudaEventRecord(e->ev0, stream));
     float dummy = 0.f; (void)dummy;
     bool first_chunk = true;
@@ -659,6 +697,7 @@ static int launch_attempt(b200sat_engine *e) {
             if (first_chunk) CK(cudaEventRecord(e->ev3, stream));
             e->info.launches += 1;
         } else if (!(pd.flags & B200SAT_F_NO_SOLVE)) {
+            if (rescue) CK(cudaMemcpyAsync(e->d_pristine, e->d_slabs, (size_t)n_chunk * L.slab_bytes, cudaMemcpyDeviceToDevice, stream));
             if (first_chunk) CK(cudaEventRecord(e->ev2, stream));
             start_ring<<<1, 1, 0, stream>>>(P.qctl, shs.grid * shs.wpb);
             fn_s<<<shs.grid, shs.wpb * 32, shs.smem, stream>>>(P);
@@ -695,7 +734,7 @@ extern "C" int b200sat_engine_solve_async(b200sat_engine *e, const b200sat_setti
     if (e->pend.active) { rc = b200sat_engine_finish(e); if (rc && rc != B200SAT_E_MEM) return rc; }
     CK(cudaSetDevice(e->device));
     e->info.launches = 0;
-    e->info.last_kernel_ms = 0.f; e->info.search_ms = 0.f; e->info.suspends = 0; e->info.tail_ms = 0.f; e->info.span_ms = 0.f;
+    e->info.last_kernel_ms = 0.f; e->info.search_ms = 0.f; e->info.suspends = 0; e->info.tail_ms = 0.f; e->info.span_ms = 0.f; e->info.rescued = 0;
     b200sat_engine::Pending &pd = e->pend;
     pd.stream = (cudaStream_t)stream_;
     if (e->n_inst == 0) return 0;
@@ -785,6 +824,7 @@ extern "C" int b200sat_engine_finish(b200sat_engine *e) {
         pd.total_ms += ms;
         if (pd.searched) { CK(cudaEventElapsedTime(&ms, e->ev2, e->ev3)); pd.search_ms += ms; }
         e->info.suspends += e->h_pinned[32 + QC_SUSPENDS];
+        e->info.rescued += e->h_pinned[32 + QC_RESCUED];
         if (pd.searched && !e->replay_mode) { /* time from the moment the work ring ran dry to the last warp's exit */
             const unsigned long long *tq = (const unsigned long long *)(e->h_pinned + 32 + QC_T_START);
             const unsigned long long t0 = tq[0], td = tq[1], t1 = tq[2];

@@ -26,6 +26,7 @@ kernel_fn b200sat_pick_ingest_c1s1(int tier_nv, size_t *smem_per_warp, size_t *s
 kernel_fn b200sat_pick_search_c0(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
 kernel_fn b200sat_pick_search_c1(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
 kernel_fn b200sat_pick_search_pf(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
+kernel_fn b200sat_pick_search_rescue(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
 kernel_fn b200sat_pick_replay_c0(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
 kernel_fn b200sat_pick_replay_c1(int tier_nv, size_t *smem_per_warp, size_t *save_bytes);
 
@@ -188,6 +189,84 @@ template <class WS> __device__ __forceinline__ void search_loop_ring(WS &S, cons
         S.count_done();
     }
 }
+#if B200SAT_KERNEL_TU_RESCUE
+/* ---------------------------------------------------------------- search with straggler rescue (free-running mode):
+ * phase 1 = search_loop_ring with every popped instance registered as "main replica" of its warp; phase 2 = the warp
+ * has nothing left to pop and helps instances that are still running (KParams::rescue, WarpSolver::rescue_*). */
+template <class WS> __device__ __forceinline__ void search_loop_rescue(WS &S, const KParams &P) {
+    const u32 my_warp = blockIdx.x, n_warps = gridDim.x;
+    bool first = true, have_slab = false;
+    if (S.lane == 0 && blockIdx.x == 0) *(volatile unsigned long long *)(P.qctl + QC_T_START) = global_timer_ns();
+    for (;;) {
+        u32 w = 0xFFFFFFFFu;
+        if (S.lane == 0) {
+            if (first && blockIdx.x < WS::ld_vol(P.qctl + QC_HEAD0)) w = (u32)*(volatile unsigned long long *)(P.ring + (blockIdx.x & P.ring_mask));
+            else for (;;) {
+                const u32 h = WS::ld_vol(P.qctl + QC_HEAD), t = WS::ld_vol(P.qctl + QC_TAIL);
+                if ((i32)(t - h) > 0) {
+                    if (atomicCAS(P.qctl + QC_HEAD, h, h + 1) != h) continue;
+                    volatile unsigned long long *slot = P.ring + (h & P.ring_mask);
+                    unsigned long long e;
+                    do { e = *slot; } while ((u32)(e >> 32) != h + 1);
+                    w = (u32)e;
+                }
+                break;
+            }
+            __threadfence();
+        }
+        first = false;
+        w = __shfl_sync(FULL_MASK, w, 0);
+        if (w == 0xFFFFFFFFu) break;
+        bind_item(S, P, w);
+        if constexpr (WS::VT_GLOBAL) S.V.bind(S.slab + P.L.off_vars, P.L.nv_cap);
+        S.load_state();
+        have_slab = true;
+        S.rescue_begin_main(my_warp, w);
+        const u32 r = S.run_search();
+        if (r == WS::SR_SUSPEND) {
+            S.rescue_end_main(my_warp);
+            S.save_state();
+            if (S.lane == 0) atomicAdd(P.qctl + QC_SUSPENDS, 1u);
+            S.ring_push(w);
+            continue;
+        }
+        bool mine = !(r == WS::SR_ABORT && S.sc().status == ST_CANCELLED); /* a helper decided it first */
+        if (mine) mine = S.rescue_claim();
+        if (mine) S.finish_search(r, P.kind == B200SAT_SIMP);
+        S.rescue_end_main(my_warp);
+    }
+    if (S.lane == 0) {
+        const unsigned long long t = global_timer_ns();
+        atomicCAS((unsigned long long *)(P.qctl + QC_T_DRAIN), 0ull, t);
+    }
+    if (have_slab) {
+        for (u32 round = 0;; round++) {
+            const u32 mw = S.rescue_pick(n_warps, my_warp, round);
+            if (mw == 0xFFFFFFFFu) break;
+            if (!S.rescue_join(mw)) continue;
+            const u32 r = S.run_search();
+            if ((r == WS::SR_SAT || r == WS::SR_UNSAT) && S.rescue_claim()) {
+                S.finish_search(r, P.kind == B200SAT_SIMP);
+                if (S.lane == 0) atomicAdd(P.qctl + QC_RESCUED, 1u);
+            }
+            __syncwarp();
+        }
+    }
+    if (S.lane == 0) atomicMax((unsigned long long *)(P.qctl + QC_T_END), global_timer_ns());
+}
+template <int NV> __global__ void __launch_bounds__(32, B200SAT_SEARCH_BLOCKS) rescue_smem(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSolver<VarsS<NV, false>, false, true> S(P, threadIdx.x);
+    S.V.s = reinterpret_cast<SmemVars<NV, false> *>(smem_raw);
+    search_loop_rescue(S, P);
+}
+__global__ void __launch_bounds__(32, 16) rescue_glob(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSolver<VarsG, false, true> S(P, threadIdx.x);
+    S.V.s = reinterpret_cast<SmemSmall *>(smem_raw);
+    search_loop_rescue(S, P);
+}
+#else
 /* ONE warp per block: the shared-memory base and the lane id are then block constants (no per-warp offset to
  * rematerialise in the hot loop); 32 blocks per SM = 32 resident warps at 64 registers per thread */
 template <int NV, bool COUNT, bool PF> __global__ void __launch_bounds__(32, B200SAT_SEARCH_BLOCKS) search_smem(const __grid_constant__ KParams P) {
@@ -202,6 +281,7 @@ template <bool COUNT, bool PF> __global__ void __launch_bounds__(32, 16) search_
     S.V.s = reinterpret_cast<SmemSmall *>(smem_raw);
     search_loop_ring(S, P);
 }
+#endif
 #endif
 
 } // namespace b200sat
@@ -223,6 +303,13 @@ kernel_fn B200SAT_KERNEL_TU_NAME(int tier_nv, size_t *spw, size_t *save) {
     case 256: *spw = sizeof(SmemVars<256, false>); *save = SmemSave<256>::BYTES; return replay_smem<256, C>;
     case 1024: *spw = sizeof(SmemVars<1024, false>); *save = SmemSave<1024>::BYTES; return replay_smem<1024, C>;
     default: *spw = sizeof(SmemSmall); *save = sizeof(SmemSmall); return replay_glob<C>;
+    }
+#elif B200SAT_KERNEL_TU_RESCUE
+    switch (tier_nv) {
+    case 128: *spw = sizeof(SmemVars<128, false>); *save = SmemSave<128>::BYTES; return rescue_smem<128>;
+    case 256: *spw = sizeof(SmemVars<256, false>); *save = SmemSave<256>::BYTES; return rescue_smem<256>;
+    case 1024: *spw = sizeof(SmemVars<1024, false>); *save = SmemSave<1024>::BYTES; return rescue_smem<1024>;
+    default: *spw = sizeof(SmemSmall); *save = sizeof(SmemSmall); return rescue_glob;
     }
 #else
     constexpr bool Pf = B200SAT_KERNEL_TU_PF != 0;

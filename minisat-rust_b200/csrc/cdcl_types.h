@@ -169,6 +169,17 @@ struct KParams {
     const u32 *assumps;       /* assumptions of solve_limited (sat.rs:34), shared by every instance of the batch */
     u32 n_assumps;
     u8 *parked;               /* [item] 1: the item's state is resident and resumable (PH_READY), 0: not */
+    /* straggler rescue (free-running mode, no reference analogue): once the work ring is empty, idle warps
+     * clone the pristine post-ingest state of a still-running instance into their own slab and search it as diversified
+     * helper replicas that exchange short learnt clauses with each other through the running warp's rescue ring; the
+     * original ("main") replica exports but never imports, so it stays on the reference trace.  Whoever finishes first
+     * claims the instance. */
+    u32 rescue;               /* 0 = off (trace mode) */
+    u32 *run_table;           /* [search warp] item it runs as main replica | 0x80000000, or 0 */
+    u32 *rrings;              /* [search warp][RING_PAYLOAD + rr_words] rescue rings */
+    u32 rr_words;
+    const u8 *pristine;       /* copy of every slab as the ingest kernel left it */
+    u32 n_div;                /* diversified settings available in replica_settings[] */
     double *progress_buf;     /* CLI search-table rows (search.rs:289-301), instrumented kernel only: per item
                                  [n_rows][8 values per row ...], or NULL */
     u32 progress_cap;         /* rows per item */
@@ -177,7 +188,7 @@ struct KParams {
     u32 import_cap;           /* portfolio: clauses one replica imports per restart boundary (0 = no cap) */
     u32 ring_epoch;           /* portfolio: stamps ring entries of this run                             */
 };
-enum : u32 { QC_HEAD = 0, QC_TAIL = 1, QC_DONE = 2, QC_TOTAL = 3, QC_SUSPENDS = 4, QC_HEAD0 = 5 /* items handed out statically: warp i starts with ring slot i */,
+enum : u32 { QC_HEAD = 0, QC_TAIL = 1, QC_DONE = 2, QC_TOTAL = 3, QC_SUSPENDS = 4, QC_HEAD0 = 5 /* items handed out statically: warp i starts with ring slot i */, QC_RESCUED = 6 /* instances decided by a helper replica */,
              QC_T_START = 8, QC_T_DRAIN = 10, QC_T_END = 12 /* u64 %globaltimer ns: search kernel start, first warp that found the
                                                               ring empty, last warp exit */, QC_WORDS = 16 };
 /* life cycle of a resident instance (Scal::phase) */
@@ -191,7 +202,8 @@ enum : u32 { TR_WORDS = 0, TR_PROPS_LO = 1, TR_PROPS_HI = 2, TR_TRAFFIC = 4 /* 6
 enum : u32 { PF_SHARE = 1, PF_IGNORE_DONE = 2, PF_SHARE_LBD2 = 4 };
 enum : u32 { VARF_UPOL_SET = 1, VARF_UPOL_VAL = 2, VARF_NOT_DECISION = 4 };
 /* ring header words */
-enum : u32 { RING_HEAD = 0, RING_DONE = 1, RING_EXPORTS = 2, RING_PAYLOAD = 16 };
+enum : u32 { RING_HEAD = 0, RING_DONE = 1, RING_EXPORTS = 2, RING_ITEM = 3 /* rescue: item the ring belongs to | 0x80000000 */,
+             RING_HELPERS = 4 /* rescue: helper replicas that joined */, RING_PAYLOAD = 16 };
 static const u32 ST_CANCELLED = 20;
 
 } // namespace b200sat

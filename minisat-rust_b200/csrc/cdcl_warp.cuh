@@ -213,6 +213,10 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
     const b200sat_settings *stp;   /* P.st, or this replica's diversified settings in portfolio mode */
     u32 res_index;                 /* slot in results/models (= instance id, or replica id)          */
     u32 item_index = 0;            /* work index of the item (slab / parked slot)                     */
+    u32 *rx_ring = nullptr;        /* straggler rescue: the ring of the instance this replica works on */
+    u32 rx_tag = 0;                /* ... its item tag (RING_ITEM word)                                */
+    bool rx_main = false;          /* ... true: the original replica (exports only, stays on the trace) */
+    u32 result_flags = 0;          /* OR-ed into result.attempts (0x100: decided by a helper replica)  */
     u32 lane;
     u8 *slab;
     u32 *arena;   /* active arena half */
@@ -1262,11 +1266,14 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
     DEV bool cancelled() {
         if (!PF || (P.share & PF_IGNORE_DONE)) return false;
         u32 v = 0; /* one lane reads, all lanes agree: another GPU may raise the flag at any moment */
-        if (lane == 0) v = ld_vol(P.rings[P.my_ring] + RING_DONE);
+        if (lane == 0) {
+            if (rx_ring) v = (ld_vol(rx_ring + RING_DONE) == rx_tag || ld_vol(rx_ring + RING_ITEM) != rx_tag) ? 1u : 0u;
+            else v = ld_vol(P.rings[P.my_ring] + RING_DONE);
+        }
         return bcast(v) != 0;
     }
     DEV void announce_done() {
-        if (!PF) return;
+        if (!PF || rx_ring) return; /* rescue mode: the instance is claimed by a CAS on its ring (rescue_claim) */
         if (lane == 0) {
             __threadfence_system();
             for (u32 r = 0; r < P.n_rings; r++) atomicCAS(P.rings[r] + RING_DONE, 0u, 1u + P.replica_base + res_index);
@@ -1289,17 +1296,23 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
             lbd = __popc(__ballot_sync(FULL_MASK, lane < n && (u32)__ffs(peers) - 1 == lane));
             if (lbd > 2) return;
         }
-        u32 *ring = P.rings[P.my_ring];
+        u32 *ring = rx_ring ? rx_ring : P.rings[P.my_ring];
+        const u32 ring_words = rx_ring ? P.rr_words : P.ring_words;
+        if (rx_ring && rx_main) { /* the original replica feeds its helpers, if it has any */
+            u32 nh = 0;
+            if (lane == 0) nh = ld_vol(rx_ring + RING_HELPERS);
+            if (bcast(nh) == 0) return;
+        }
         u32 pos = 0;
         if (lane == 0) pos = atomicAdd(ring + RING_HEAD, n + 1);
         pos = bcast(pos);
-        if (pos + n + 1 > P.ring_words) return; /* ring full: stop exporting */
+        if (pos + n + 1 > ring_words) return; /* ring full: stop exporting */
         u32 *pay = ring + RING_PAYLOAD + pos;
         if (lane < n) pay[1 + lane] = lit;
         __threadfence_system();
         __syncwarp();
         if (lane == 0) {
-            *(volatile u32 *)pay = 0x80000000u | (((P.replica_base + res_index) & 0x7FFFFFu) << 8) | n;
+            *(volatile u32 *)pay = 0x80000000u | (((rx_ring ? rx_tag : P.replica_base + res_index) & 0x7FFFFFu) << 8) | n;
             sc().exported++;
         }
         __syncwarp();
@@ -1313,16 +1326,20 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
         const u32 cap = P.import_cap ? P.import_cap : 0xFFFFFFFFu;
         u32 *filter = (u32 *)(slab + P.L.off_pf);
         u32 got = 0;
-        for (u32 r = 0; r < P.n_rings && got < cap; r++) {
-            const u32 *ring = P.rings[r];
+        const u32 n_rings = rx_ring ? 1u : P.n_rings;
+        const u32 ring_words = rx_ring ? P.rr_words : P.ring_words;
+        for (u32 r = 0; r < n_rings && got < cap; r++) {
+            const u32 *ring = rx_ring ? rx_ring : P.rings[r];
             u32 cur = sc().ring_cursor[r];
             for (;;) {
-                if (got >= cap || cur + 1 > P.ring_words) break;
+                if (got >= cap || cur + 1 > ring_words) break;
                 u32 hdr = ld_vol(ring + RING_PAYLOAD + cur);
                 if (!(hdr & 0x80000000u)) break; /* not committed yet */
                 u32 n = hdr & 0xFF;
                 u32 src = (hdr >> 8) & 0x7FFFFFu;
-                if (src != me) {
+                /* portfolio: everything but my own exports; rescue: only clauses of the instance I work on (the ring is
+                 * re-used by the next instance of its warp; the duplicate filter drops my own exports) */
+                if (rx_ring ? src == (rx_tag & 0x7FFFFFu) : src != me) {
                     __threadfence();
                     u32 *t = tmp();
                     u32 lit = lane < n ? ld_vol(ring + RING_PAYLOAD + cur + 1 + lane) : 0u;
@@ -1670,6 +1687,95 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
         return ok && !failed();
     }
 
+    /* -------------------------------------------------------------- straggler rescue (see KParams::rescue) */
+    DEV u32 *rescue_ring(u32 warp) const { return P.rrings + (size_t)warp * (RING_PAYLOAD + P.rr_words); }
+    /* the original replica of `item` starts on this warp: its ring is handed over to the new instance */
+    DEV void rescue_begin_main(u32 warp, u32 item) {
+        rx_ring = rescue_ring(warp); rx_tag = 0x80000000u | item; rx_main = true; result_flags = 0;
+        if (lane == 0) { *(volatile u32 *)(rx_ring + RING_ITEM) = 0; __threadfence(); } /* helpers of the previous instance stop */
+        __syncwarp();
+        for (u32 k = lane; k < P.rr_words; k += 32) rx_ring[RING_PAYLOAD + k] = 0; /* no stale entry survives the hand-over */
+        __syncwarp();
+        if (lane == 0) {
+            *(volatile u32 *)(rx_ring + RING_HEAD) = 0; *(volatile u32 *)(rx_ring + RING_DONE) = 0;
+            *(volatile u32 *)(rx_ring + RING_HELPERS) = 0;
+            __threadfence();
+            *(volatile u32 *)(rx_ring + RING_ITEM) = rx_tag;
+            *(volatile u32 *)(P.run_table + warp) = rx_tag;
+        }
+        __syncwarp();
+    }
+    DEV void rescue_end_main(u32 warp) {
+        if (lane == 0) { *(volatile u32 *)(P.run_table + warp) = 0; __threadfence(); }
+        __syncwarp();
+    }
+    /* First finisher takes the instance: RING_DONE receives the instance's tag (a stale value left by a late helper of
+     * the ring's previous instance is simply overwritten); all lanes get the answer. */
+    DEV bool rescue_claim() {
+        u32 won = 0;
+        if (lane == 0 && ld_vol(rx_ring + RING_ITEM) == rx_tag) {
+            for (;;) {
+                const u32 old = ld_vol(rx_ring + RING_DONE);
+                if (old == rx_tag) break; /* another replica of this instance was first */
+                if (atomicCAS(rx_ring + RING_DONE, old, rx_tag) == old) { won = 1; break; }
+            }
+        }
+        return bcast(won) != 0;
+    }
+    /* An idle warp looks for a running instance to help: returns the main warp's index or ~0u.  Instances with few
+     * helpers are preferred so that the idle warps spread over the stragglers. */
+    DEV u32 rescue_pick(u32 n_warps, u32 my_warp, u32 round) {
+        for (u32 pass = 0; pass < 2; pass++) {
+            const u32 cap = pass == 0 ? 4u + round : 0x7FFFFFFFu;
+            const u32 start = (my_warp * 2654435761u + round * 40503u) % n_warps;
+            for (u32 k = 0; k < n_warps; k += 32) {
+                const u32 idx = (start + k + lane) % n_warps;
+                bool ok = false;
+                if (k + lane < n_warps && ld_vol(P.run_table + idx) != 0) {
+                    const u32 *rg = rescue_ring(idx);
+                    ok = ld_vol(rg + RING_DONE) != ld_vol(rg + RING_ITEM) && ld_vol(rg + RING_HELPERS) < cap;
+                }
+                const u32 m = __ballot_sync(FULL_MASK, ok);
+                if (m) return __shfl_sync(FULL_MASK, idx, __ffs(m) - 1);
+            }
+        }
+        return 0xFFFFFFFFu;
+    }
+    /* become helper replica of the instance main warp `mw` runs: clone its pristine post-ingest state into my slab and
+     * diversify.  false = the instance is gone already. */
+    DEV bool rescue_join(u32 mw) {
+        u32 *rg = rescue_ring(mw);
+        u32 tag = 0, hidx = 0;
+        if (lane == 0) {
+            tag = ld_vol(rg + RING_ITEM);
+            if (tag != 0 && ld_vol(rg + RING_DONE) != tag) hidx = atomicAdd(rg + RING_HELPERS, 1u) + 1;
+            else tag = 0;
+        }
+        tag = bcast(tag); hidx = bcast(hidx);
+        if (tag == 0) return false;
+        const u32 item = tag & 0x7FFFFFFFu;
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.pristine + (size_t)(item - P.chunk_base) * P.L.slab_bytes);
+        uint4 *dst = reinterpret_cast<uint4 *>(slab);
+        for (u64 k = lane; k < P.L.slab_bytes / 16; k += 32) dst[k] = src[k];
+        __syncwarp();
+        rx_ring = rg; rx_tag = tag; rx_main = false; result_flags = 0x100;
+        res_index = P.work ? P.work[item] : item;
+        item_index = item;
+        stp = P.replica_settings + (1 + (hidx + item) % (P.n_div - 1)); /* entry 0 is the reference configuration */
+        load_state();
+        if (lane == 0) { /* the diversified configuration replaces what setup() derived from the base settings */
+            sc().seed = st().random_seed + (double)(hidx % 977);
+            sc().inv_var_decay = 1.0 / st().var_decay;
+            sc().inv_cla_decay = 1.0 / st().clause_decay;
+            for (int i = 0; i < 8; i++) sc().ring_cursor[i] = 0;
+            if (st().rnd_init_act) for (u32 v = 0; v < nvars; v++) V.act()[v] = drand() * 0.00001;
+        }
+        { u32 *filter = (u32 *)(slab + P.L.off_pf); for (u32 k = lane; k < 256; k += 32) filter[k] = 0; }
+        __syncwarp();
+        if (st().rnd_init_act) rebuild_order_heap();
+        return true;
+    }
+
     /* -------------------------------------------------------------- park / resume (no reference analogue) */
     DEV void save_state() {
         __syncwarp();
@@ -1754,7 +1860,7 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
         u64 slice_end = P.slice_conflicts ? sc().conflicts + P.slice_conflicts : ~0ull;
         for (;;) {
             if (!sc().in_loop) { /* search_loop prologue, search.rs:465-467 */
-                if (PF && (P.share & PF_SHARE) && sc().curr_restarts > 0) {
+                if (PF && (P.share & PF_SHARE) && sc().curr_restarts > 0 && !rx_main) {
                     if (!import_clauses()) return SR_UNSAT;
                     if (failed()) return SR_ABORT;
                 }
@@ -1863,7 +1969,7 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
                     break;
                 }
                 if (nconf >= slice_end) { /* yield to waiting instances; nothing of the trace depends on this */
-                    if (others_waiting()) return SR_SUSPEND;
+                    if (!(PF && rx_ring && !rx_main) && others_waiting()) return SR_SUSPEND; /* helper replicas never park */
                     slice_end = nconf + P.slice_conflicts;
                 }
                 if (recording() && will_simplify()) rec_stop(res_index);
@@ -2253,7 +2359,7 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
             r->n_clauses_pre = n_pre;
             r->eliminated_vars = s.eliminated_vars;
             r->pre_ok = pre_ok;
-            r->attempts = P.attempt;
+            r->attempts = P.attempt | result_flags;
             r->stats[0] = zero ? 0 : s.solves;       /* search.rs:590-601 */
             r->stats[1] = zero ? 0 : s.starts;
             r->stats[2] = zero ? 0 : s.decisions;

@@ -4,4 +4,5 @@
 #define B200SAT_KERNEL_TU_SIMP 1
 #define B200SAT_KERNEL_TU_PHASE 0
 #define B200SAT_KERNEL_TU_PF 0
+#define B200SAT_KERNEL_TU_RESCUE 0
 #include "cdcl_kernels.cuh"

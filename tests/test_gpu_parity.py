@@ -800,3 +800,37 @@ def test_search_table_progress_rows(pkg, po, eng):
         eng.set_progress_rows(0)
     assert list(res[0]["stats"]) == list(o.stats)
     assert rows.shape == orows.shape and (rows == orows).all(), (rows[:3], orows[:3])
+
+
+def test_straggler_rescue_keeps_verdicts_and_models(pkg, po):
+    """Free-running mode (b200sat_engine_set_rescue): idle warps help instances that are still running.  Verdicts equal
+    the trace-mode run's, every SAT model satisfies its CNF, instances decided by their original replica still carry the
+    reference counters, and trace mode itself is untouched."""
+    e = pkg.Engine(0)
+    try:
+        n_inst, n, m = 6000, 150, 639
+        e.generate_ksat(SEED2 + 99000, n_inst, n, m, 3)
+        e.solve(kind=pkg.CORE, flags=pkg.F_PREPROCESS)
+        t_trace = e.launch_info()["search_ms"]
+        ref, _ = e.download(want_models=False)
+        e.set_rescue(True)
+        e.solve(kind=pkg.CORE, flags=pkg.F_PREPROCESS)
+        info = e.launch_info()
+        res, models = e.download(model_stride=n)
+        ioff, coff, lits = e.download_batch()
+        assert int((res["status"] != 0).sum()) == 0
+        assert (res["verdict"] == ref["verdict"]).all()
+        assert check_models(ioff, coff, lits, res["verdict"], models) == 0
+        ver, n_bad = e.verify_models()
+        assert n_bad == 0
+        helped = (res["attempts"] & 0x100) != 0
+        assert (res["stats"][~helped] == ref["stats"][~helped]).all()      # untouched instances: reference counters
+        assert int(helped.sum()) == info["rescued"]
+        print("\nrescue: %d of %d instances decided by helper replicas; search %.1f ms vs %.1f ms in trace mode"
+              % (int(helped.sum()), n_inst, info["search_ms"], t_trace))
+        e.set_rescue(False)
+        e.solve(kind=pkg.CORE, flags=pkg.F_PREPROCESS)
+        again, _ = e.download(want_models=False)
+        assert (again["stats"] == ref["stats"]).all() and ((again["attempts"] & 0x100) == 0).all()
+    finally:
+        e.close()
