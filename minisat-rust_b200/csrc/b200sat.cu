@@ -653,7 +653,7 @@ static int launch_attempt(b200sat_engine *e) {
         CK(cudaStreamSynchronize(stream));
         if ((rc = ensure(e->d_ring, e->cap_ring, (size_t)ring_cap))) return rc;
     }
-    const u32 rr_words = 4096;
+    const u32 rr_words = 32768; /* 128 KB per running warp: the last stragglers collect thousands of helpers */
     if (rescue) {
         if (pd.n_work > slots) return set_err(B200SAT_E_MEM, "straggler rescue needs the whole batch resident at once");
         if ((rc = ensure(e->d_pristine, e->cap_pristine, (size_t)(slots * L.slab_bytes)))) return rc;
