@@ -272,6 +272,21 @@ typedef struct b200sat_launch_info {
 } b200sat_launch_info;
 int b200sat_engine_launch_info(b200sat_engine *e, b200sat_launch_info *out);
 
+/* K4 as ONE preprocessor (round 2, csrc/preprocess_coop.cu): backward subsumption, self-subsuming strengthening and
+ * bounded variable elimination of instance `inst` of the resident batch, interleaved until nothing changes
+ * (simplify.rs:213-274 as passes) inside one persistent cooperative kernel: multi-block scans, grid-wide barriers
+ * instead of launches (3 launches per instance).  Reference semantics (subsumes.rs:10-49, simplify.rs:338-420,567-591,
+ * formula/util.rs:45-77), not its job order: the result is equisatisfiable and every model of it extends to a model of
+ * the input.  out_clause_off / out_lits: the reduced CNF as CSR (capacity 2*nc+1024 / 3*nlits+4096); out_estack: the
+ * eliminated-clause records; counts[16]: [0] kept clauses [1] kept literals [2] eliminated vars [3] subsumed clauses
+ * [4] strengthened literals [5] outer iterations [6] BVE rounds [7] subsume/strengthen rounds [8] stack words
+ * [9] overflow [10] empty clause derived (UNSAT) [11] kernel launches. */
+int b200sat_engine_preprocess_instance(b200sat_engine *e, uint32_t inst, uint32_t grow, int cl_lim, uint32_t max_outer,
+                                       uint32_t *out_clause_off, uint32_t *out_lits, uint32_t *out_estack,
+                                       uint32_t counts[16], float *kernel_ms, void *stream);
+/* ElimClauses::extend_model (elim_clauses.rs:43-63) ON THE DEVICE over the stack the last preprocess_instance left there */
+int b200sat_engine_k4_extend_model(b200sat_engine *e, uint8_t *model, uint32_t n_vars, void *stream);
+
 /* Progress rows of the reference's search table (search.rs:289-301: printed whenever the learnt-clause limit is bumped),
  * recorded on the device for every instance solved with B200SAT_F_COUNT_TRAFFIC while rows > 0.  One row = 8 doubles:
  * conflicts, free decision vars, original clauses, their literals, learnt limit, learnts, literals per learnt, progress %. */

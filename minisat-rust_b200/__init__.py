@@ -125,7 +125,7 @@ ABI_SYMBOLS = (
     "b200sat_engine_bcp_replay", "b200sat_engine_set_var_flags", "b200sat_engine_set_assumptions",
     "b200sat_engine_resume", "b200sat_engine_resume_async", "b200sat_engine_set_import_cap",
     "b200sat_engine_ring_open_local_peer", "b200sat_engine_set_progress_rows", "b200sat_engine_download_progress",
-    "b200sat_engine_set_rescue",
+    "b200sat_engine_set_rescue", "b200sat_engine_preprocess_instance", "b200sat_engine_k4_extend_model",
 )
 PF_SHARE, PF_IGNORE_DONE, PF_SHARE_LBD2, PF_KEEP_RING = 1, 2, 4, 8
 
@@ -180,6 +180,9 @@ def lib():
     L.b200sat_engine_set_progress_rows.argtypes = [vp, C.c_uint32]
     L.b200sat_engine_download_progress.argtypes = [vp, C.c_uint32, C.POINTER(C.c_double), C.c_uint32, u32p]
     L.b200sat_engine_set_rescue.argtypes = [vp, C.c_int]
+    L.b200sat_engine_preprocess_instance.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, u32p, u32p, u32p, u32p,
+                                                     C.POINTER(C.c_float), vp]
+    L.b200sat_engine_k4_extend_model.argtypes = [vp, u8p, C.c_uint32, vp]
     L.b200sat_engine_set_import_cap.argtypes = [vp, C.c_uint32]
     L.b200sat_engine_ring_open_local_peer.argtypes = [vp, C.c_uint32, vp]
     L.b200sat_engine_set_slice.argtypes = [vp, C.c_uint32]
@@ -397,6 +400,28 @@ class Engine:
         n = C.c_uint32()
         _check(lib().b200sat_engine_download_progress(self._e, inst, out.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(n)))
         return out[:n.value]
+
+    def preprocess_instance(self, inst, n_clauses, n_lits, grow=0, cl_lim=20, max_outer=64, stream=None):
+        """K4 as one preprocessor (subsumption + strengthening + BVE interleaved, one cooperative kernel) ->
+        dict(clause_off, lits, estack, kept, kept_lits, eliminated, subsumed, strengthened, outer, bve_rounds, ss_rounds,
+        launches, unsat, kernel_ms)"""
+        NC, NL = 2 * n_clauses + 1024, 3 * n_lits + 4096
+        off = np.zeros(NC + 2, np.uint32); li = np.zeros(NL + 2, np.uint32); es = np.zeros(NL + 2, np.uint32)
+        cnt = np.zeros(16, np.uint32); ms = C.c_float()
+        u32p = C.POINTER(C.c_uint32)
+        _check(lib().b200sat_engine_preprocess_instance(self._e, inst, grow, cl_lim, max_outer, off.ctypes.data_as(u32p),
+                                                        li.ctypes.data_as(u32p), es.ctypes.data_as(u32p), cnt.ctypes.data_as(u32p),
+                                                        C.byref(ms), stream))
+        kept, kl = int(cnt[0]), int(cnt[1])
+        return dict(clause_off=off[:kept + 1].copy(), lits=li[:kl].copy(), estack=es[:int(cnt[8])].copy(), kept=kept, kept_lits=kl,
+                    eliminated=int(cnt[2]), subsumed=int(cnt[3]), strengthened=int(cnt[4]), outer=int(cnt[5]), bve_rounds=int(cnt[6]),
+                    ss_rounds=int(cnt[7]), launches=int(cnt[11]), unsat=bool(cnt[10]), kernel_ms=float(ms.value))
+
+    def k4_extend_model(self, model, stream=None):
+        """elim_clauses.rs:43-63 on the device over the stack of the last preprocess_instance; model: uint8[n_vars] in/out"""
+        m = np.ascontiguousarray(model, dtype=np.uint8).copy()
+        _check(lib().b200sat_engine_k4_extend_model(self._e, m.ctypes.data_as(C.POINTER(C.c_uint8)), len(m), stream))
+        return m
 
     def set_rescue(self, on=True):
         """free-running mode: idle warps help instances that are still running (NOT the reference trace for those)"""

@@ -166,6 +166,8 @@ struct b200sat_engine {
     u8 *d_verified = nullptr;
     size_t cap_verified = 0;
     u32 *d_pp = nullptr;          /* scratch of the K4 preprocessing kernels */
+    u32 *k4_estack = nullptr;     /* eliminated-clause stack of the last preprocess_instance (inside d_pp) */
+    u32 k4_estack_words = 0, k4_nvars = 0;
     size_t cap_pp = 0;
     u32 model_stride = 0;
     /* work */
@@ -268,7 +270,7 @@ extern "C" b200sat_engine *b200sat_engine_create(int device) {
     e->smem_optin = prop.sharedMemPerBlockOptin;
     memset(&e->info, 0, sizeof e->info);
     memset(&e->resident_L, 0, sizeof e->resident_L);
-    if (cudaMalloc((void **)&e->d_queue, 256) != cudaSuccess || cudaMallocHost((void **)&e->h_pinned, 256) != cudaSuccess ||
+    if (cudaMalloc((void **)&e->d_queue, 256) != cudaSuccess || cudaMallocHost((void **)&e->h_pinned, 1024) != cudaSuccess ||
         cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
         cudaEventCreate(&e->ev2) != cudaSuccess || cudaEventCreate(&e->ev3) != cudaSuccess ||
         cudaMallocHost((void **)&e->h_interrupt, 64) != cudaSuccess ||
@@ -1023,6 +1025,79 @@ extern "C" int b200sat_engine_bve_instance(b200sat_engine *e, uint32_t inst, uin
     }
     if (out_lits && kept_lits) CK(cudaMemcpy(out_lits, d_out_lits, (size_t)kept_lits * 4, cudaMemcpyDeviceToHost));
     if (out_estack && ewords) CK(cudaMemcpy(out_estack, d_estack, (size_t)ewords * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" size_t b200sat_k4_words(size_t nc, size_t nvars, size_t nlits);
+extern "C" int b200sat_k4_launch(const u32 *d_coff, const u32 *d_lits, u32 cb, u32 nc, u32 nvars, u32 nlits, u32 lit_base, u32 *mem,
+                                 u32 grow, int cl_lim, u32 max_outer, u32 *d_out_coff, u32 *d_out_lits, u32 **d_estack_out,
+                                 u32 *h_counts, int num_sms, cudaStream_t stream);
+extern "C" int b200sat_k4_extend_model_launch(const u32 *d_estack, u32 n_words, u8 *d_model, u32 n_vars, cudaStream_t stream);
+
+/* K4 as ONE preprocessor (csrc/preprocess_coop.cu): subsumption + strengthening + BVE of instance `inst` of the resident
+ * batch, interleaved to a fixpoint inside one cooperative kernel.  counts[16]: [0] kept clauses [1] kept literals
+ * [2] eliminated vars [3] subsumed clauses [4] strengthened literals [5] outer iterations [6] BVE rounds
+ * [7] subsume/strengthen rounds [8] eliminated-clause stack words [9] overflow [10] empty clause derived (UNSAT)
+ * [11] kernel launches.  The eliminated-clause stack stays on the device for b200sat_engine_k4_extend_model. */
+extern "C" int b200sat_engine_preprocess_instance(b200sat_engine *e, uint32_t inst, uint32_t grow, int cl_lim, uint32_t max_outer,
+                                                  uint32_t *out_clause_off, uint32_t *out_lits, uint32_t *out_estack, uint32_t counts[16],
+                                                  float *kernel_ms, void *stream_) {
+    if (!e || inst >= e->n_inst) return set_err(B200SAT_E_ARG, "bad instance index");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(cudaSetDevice(e->device));
+    u32 io[2], lo[2];
+    CK(cudaMemcpy(io, e->d_ioff + inst, 8, cudaMemcpyDeviceToHost));
+    const u32 cb = io[0], nc = io[1] - io[0];
+    if (counts) for (int i = 0; i < 16; i++) counts[i] = 0;
+    if (nc == 0) return 0;
+    CK(cudaMemcpy(&lo[0], e->d_coff + cb, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&lo[1], e->d_coff + cb + nc, 4, cudaMemcpyDeviceToHost));
+    const u32 nlits = lo[1] - lo[0], nvars = e->shape.max_vars;
+    const size_t NC = 2 * (size_t)nc + 1024, NL = 3 * (size_t)nlits + 4096;
+    int rc;
+    const size_t kw = b200sat_k4_words(nc, nvars, nlits);
+    if ((rc = ensure(e->d_pp, e->cap_pp, kw + NC + 2 + NL + 64))) return rc;
+    u32 *mem = e->d_pp;
+    u32 *d_out_coff = mem + kw;
+    u32 *d_out_lits = d_out_coff + NC + 2;
+    u32 *d_estack = nullptr;
+    u32 *hc = e->h_pinned + 64; /* 32 pinned words */
+    CK(cudaEventRecord(e->ev0, stream));
+    rc = b200sat_k4_launch(e->d_coff, e->d_lits, cb, nc, nvars, nlits, lo[0], mem, grow, cl_lim, max_outer ? max_outer : 64, d_out_coff,
+                           d_out_lits, &d_estack, hc, e->num_sms, stream);
+    if (rc == -3) return set_err(B200SAT_E_CUDA, "cooperative launch not available");
+    if (rc) return set_err(B200SAT_E_CUDA, std::string("k4 preprocess launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    CK(cudaEventRecord(e->ev1, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, e->ev0, e->ev1));
+    const u32 kept = hc[13], kept_lits = hc[14], ewords = hc[12];
+    if (counts) {
+        counts[0] = kept; counts[1] = kept_lits; counts[2] = hc[2]; counts[3] = hc[5]; counts[4] = hc[6]; counts[5] = hc[7];
+        counts[6] = hc[8]; counts[7] = hc[9]; counts[8] = ewords; counts[9] = hc[3]; counts[10] = hc[4]; counts[11] = 3;
+    }
+    e->k4_estack = d_estack; e->k4_estack_words = ewords; e->k4_nvars = nvars;
+    if (hc[3]) return set_err(B200SAT_E_MEM, "k4: clause store overflow");
+    if (out_clause_off) {
+        CK(cudaMemcpy(out_clause_off, d_out_coff, (size_t)kept * 4, cudaMemcpyDeviceToHost));
+        out_clause_off[kept] = kept_lits;
+    }
+    if (out_lits && kept_lits) CK(cudaMemcpy(out_lits, d_out_lits, (size_t)kept_lits * 4, cudaMemcpyDeviceToHost));
+    if (out_estack && ewords) CK(cudaMemcpy(out_estack, d_estack, (size_t)ewords * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+/* ElimClauses::extend_model (elim_clauses.rs:43-63) on the device, over the stack the last preprocess_instance left
+ * there: model bytes in / out (1 true, 0 false, 2 undefined) */
+extern "C" int b200sat_engine_k4_extend_model(b200sat_engine *e, uint8_t *model, uint32_t n_vars, void *stream_) {
+    if (!e || !model) return set_err(B200SAT_E_ARG, "null argument");
+    if (!e->k4_estack) return set_err(B200SAT_E_ARG, "no eliminated-clause stack resident (call preprocess_instance first)");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(cudaSetDevice(e->device));
+    int rc;
+    if ((rc = ensure(e->d_verified, e->cap_verified, (size_t)n_vars + 16))) return rc;
+    CK(cudaMemcpyAsync(e->d_verified, model, n_vars, cudaMemcpyHostToDevice, stream));
+    if (b200sat_k4_extend_model_launch(e->k4_estack, e->k4_estack_words, e->d_verified, n_vars, stream)) return set_err(B200SAT_E_CUDA, "extend_model launch failed");
+    CK(cudaMemcpyAsync(model, e->d_verified, n_vars, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
     return 0;
 }
 
