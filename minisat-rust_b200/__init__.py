@@ -632,14 +632,14 @@ def extend_model_k4(model, records):
     def is_true(l):
         m = model[l >> 1]
         return m != 2 and (m == 1) == ((l & 1) == 0)
+    for v in range(len(model)):     # free variables take `false` before the walk (the reference's search assigns every variable)
+        if model[v] == 2:
+            model[v] = 0
     for rnd, var, unit, cls in sorted(records, key=lambda r: -r[0]):
         model[var] = 0 if (unit & 1) else 1
         for c in cls:
             if not any(is_true(l) for l in c):
                 model[c[0] >> 1] = 0 if (c[0] & 1) else 1
-    for v in range(len(model)):
-        if model[v] == 2:
-            model[v] = 0
     return model
 
 

@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256) k4_preprocess(K4State S) {
                 }
                 const bool save_neg = npos > nneg;
                 const u32 ks = save_neg ? nneg : npos;
-                u32 rec = 4;
+                u32 rec = 5;
                 for (u32 i = 0; i < ks; i++) rec += 1 + S.len[save_neg ? sd[63 - i] : sd[i]];
                 u32 cid0 = 0, l0 = 0, e0 = 0, okres = 1;
                 if (lane == 0) {
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) k4_preprocess(K4State S) {
                     }
                     rr += __popc(okm); ro += tot;
                 }
-                if (lane == 0) { /* eliminated-clause record: [var, unit lit, round, k, (len, lits...) * k] of the smaller side */
+                if (lane == 0) { /* eliminated-clause record: [var, unit lit, round, k, (len, lits...) * k, record words] of the smaller side */
                     u32 *e = S.estack + e0;
                     e[0] = v; e[1] = save_neg ? 2 * v : 2 * v + 1; e[2] = outer * 4096 + r; e[3] = ks;
                     u32 w = 4;
@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(256) k4_preprocess(K4State S) {
                         const u32 first = w;
                         for (u32 k = 0; k < n; k++) { e[w] = S.wl[S.wo[c] + k]; if ((e[w] >> 1) == v) { const u32 tmp = e[first]; e[first] = e[w]; e[w] = tmp; } w++; }
                     }
+                    e[w] = w + 1;   /* back link: the stack is walked from its top */
                     S.eliminated[v] = 1;
                     atomicAdd(&S.ctl[C_NELIM], 1u);
                 }
@@ -365,23 +366,27 @@ __global__ void k4_compact(K4State S, u32 *out_coff, u32 *out_lits) {
     for (u32 k = 0; k < S.len[c]; k++) out_lits[o + k] = S.wl[S.wo[c] + k];
 }
 
-/* elim_clauses.rs:43-63 on the device: walk the records backwards; model bytes 0 false / 1 true / 2 undefined */
+/* elim_clauses.rs:43-63 on the device: walk the records from the top of the stack; model bytes 0 false / 1 true / 2 undefined.
+ * Per record the reference's stack holds the saved clauses and then the unit, so walking down the unit comes first: the
+ * eliminated variable takes the unit's value whatever the reduced formula's model said about it (it no longer occurs
+ * there), and every saved clause that is then unsatisfied flips it to its own literal. */
 __global__ void k4_extend_model(const u32 *estack, u32 n_words, u8 *model, u32 n_vars) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    /* records are variable-length and only forward-linked: collect their starts first (in place of a stack walk) */
-    u32 n_rec = 0;
-    for (u32 p = 0; p < n_words;) { u32 ks = estack[p + 3]; u32 q = p + 4; for (u32 i = 0; i < ks; i++) q += 1 + estack[q]; p = q; n_rec++; }
-    for (u32 r = n_rec; r-- > 0;) {
-        u32 p = 0;
-        for (u32 i = 0; i < r; i++) { u32 ks = estack[p + 3]; u32 q = p + 4; for (u32 k = 0; k < ks; k++) q += 1 + estack[q]; p = q; }
+    /* a variable the reduced formula no longer mentions is free: it takes `false` BEFORE the walk (the reference's search
+     * assigns every variable), so that a saved clause is judged on the values the final model has */
+    for (u32 v = threadIdx.x; v < n_vars; v += blockDim.x) if (model[v] == 2) model[v] = 0;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    for (u32 top = n_words; top > 0;) {
+        const u32 total = estack[top - 1];
+        if (total < 5 || total > top) return;   /* malformed stack: leave the model as it is */
+        const u32 p = top - total;
+        top = p;
         const u32 unit = estack[p + 1], ks = estack[p + 3];
-        /* stack order of the reference: clauses pushed first, the unit last -> walking backwards the unit comes first */
-        { const u32 v = unit >> 1; if (v < n_vars && model[v] == 2) model[v] = (unit & 1) ? 0 : 1; }
-        u32 q = p + 4;
-        /* the saved clauses of this variable, last pushed first */
+        { const u32 v = unit >> 1; if (v < n_vars) model[v] = (unit & 1) ? 0 : 1; }
         u32 starts[64];
+        u32 q = p + 4;
         for (u32 i = 0; i < ks && i < 64; i++) { starts[i] = q; q += 1 + estack[q]; }
-        for (u32 i = ks; i-- > 0;) {
+        for (u32 i = ks < 64 ? ks : 64; i-- > 0;) {   /* the saved clauses of this variable, last pushed first */
             const u32 s = starts[i], n = estack[s];
             bool sat = false;
             for (u32 k = 0; k < n; k++) {
@@ -455,6 +460,6 @@ extern "C" int b200sat_k4_launch(const u32 *d_coff, const u32 *d_lits, u32 cb, u
 }
 
 extern "C" int b200sat_k4_extend_model_launch(const u32 *d_estack, u32 n_words, u8 *d_model, u32 n_vars, cudaStream_t stream) {
-    k4_extend_model<<<1, 32, 0, stream>>>(d_estack, n_words, d_model, n_vars);
+    k4_extend_model<<<1, 256, 0, stream>>>(d_estack, n_words, d_model, n_vars);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

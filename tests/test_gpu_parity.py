@@ -834,3 +834,64 @@ def test_straggler_rescue_keeps_verdicts_and_models(pkg, po):
         assert (again["stats"] == ref["stats"]).all() and ((again["attempts"] & 0x100) == 0).all()
     finally:
         e.close()
+
+
+def _extend_model_host(estack, model):
+    """elim_clauses.rs:43-63 on the host, over K4's eliminated-clause records [var, unit, round, k, (len, lits..)*k, words]"""
+    recs, p = [], 0
+    while p < len(estack):
+        ks = int(estack[p + 3]); q = p + 4; cls = []
+        for _ in range(ks):
+            n = int(estack[q]); cls.append([int(x) for x in estack[q + 1:q + 1 + n]]); q += 1 + n
+        assert int(estack[q]) == q + 1 - p
+        recs.append((int(estack[p + 1]), cls)); p = q + 1
+    m = model.copy()
+    m[m == 2] = 0       # free variables take `false` before the walk, as on the device
+    def sat(cl):
+        return any(m[l >> 1] != 2 and (m[l >> 1] != 0) != ((l & 1) != 0) for l in cl)
+    for unit, cls in reversed(recs):
+        m[unit >> 1] = 0 if (unit & 1) else 1
+        for cl in reversed(cls):
+            if not sat(cl):
+                m[cl[0] >> 1] = 0 if (cl[0] & 1) else 1
+    return m
+
+
+def test_k4_one_preprocessor(pkg, po):
+    """K4 as ONE preprocessor (csrc/preprocess_coop.cu): subsumption + strengthening + BVE interleaved to a fixpoint in one
+    cooperative kernel.  S* parity: the reduced formula has the original's verdict, every model of it,
+    extended ON THE DEVICE through the eliminated-clause stack, satisfies the ORIGINAL formula (and equals the host
+    extension); clause / eliminated-var counts are reported beside the oracle's."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "corpus_hard.npz"))
+    rows = []
+    e = pkg.Engine(0)
+    try:
+        for i, name in enumerate(g["names"]):
+            cb, ce = int(g["inst_clause_off"][i]), int(g["inst_clause_off"][i + 1])
+            off = g["clause_off"][cb:ce + 1].astype(np.int64)
+            lits = g["lits"][off[0]:off[-1]].astype(np.uint32)
+            off = (off - off[0]).astype(np.uint32)
+            ioff, coff, li = batch_of([(off, lits)])
+            e.upload(ioff, coff, li)
+            r = e.preprocess_instance(0, len(off) - 1, len(lits))
+            assert not r["unsat"] and r["launches"] <= 20
+            nv = int(lits.max() >> 1) + 1
+            o, om = po.solve_csr(off, lits, kind=po.CORE)
+            red, rm = po.solve_csr(r["clause_off"], r["lits"] if len(r["lits"]) else np.zeros(1, np.uint32), kind=po.CORE)
+            assert red.verdict == o.verdict, name
+            if red.verdict == 1:
+                m0 = np.full(nv, 2, np.uint8); m0[:len(rm)] = rm
+                dev = e.k4_extend_model(m0)
+                host = _extend_model_host(r["estack"], m0)
+                assert (dev == host).all(), name
+                full = dev.copy(); full[full == 2] = 0
+                assert po.check_model(off, lits, full), name
+            oc = [int(x) for x in g["rows"][i]]     # oracle SimpSolver preprocessing: n_vars, ingest, clauses left, eliminated vars, ...
+            rows.append((str(name), len(off) - 1, r["kept"], oc[2], r["eliminated"], oc[3], r["outer"], r["bve_rounds"], r["ss_rounds"],
+                         r["launches"], r["kernel_ms"]))
+    finally:
+        e.close()
+    print("\nK4 one preprocessor: instance | clauses in | clauses left (K4 / oracle) | eliminated vars (K4 / oracle) | outer, BVE, subsume rounds | launches | ms")
+    for row in rows:
+        print("  %-28s %7d | %7d / %7d | %6d / %6d | %2d %4d %4d | %2d | %8.2f" % row)
