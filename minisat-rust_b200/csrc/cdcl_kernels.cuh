@@ -39,7 +39,9 @@ kernel_fn b200sat_pick_replay_c1(int tier_nv, size_t *smem_per_warp, size_t *sav
 #endif
 
 #ifndef B200SAT_SEARCH_BLOCKS
-#define B200SAT_SEARCH_BLOCKS 32 /* resident one-warp blocks per SM the search kernel is compiled for: 64 registers per thread */
+#define B200SAT_SEARCH_BLOCKS 24 /* resident one-warp blocks per SM the search kernels are compiled for: 80 registers per
+                                  * thread, no spills.  Measured (profiles/r02_ab_d.log): same throughput as 32 blocks at 64
+                                  * registers on a saturated GPU, 2 % faster when the n=250 tier (21 blocks by shared memory) runs */
 #endif
 
 namespace b200sat {
@@ -48,6 +50,19 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
+}
+
+/* The block's shared-memory base, held in a register pair.  Left to itself the compiler rebuilds the shared-window
+ * address (S2UR SR_CgaCtaId + UMOV + ULEA) in front of every fixed-offset LDS / STS of the var block: 127 static sites,
+ * 3.3 % of the executed instructions of the search kernel and an S2UR latency on every scalar access.  The empty asm
+ * hides the constant, the assumption keeps the accesses LDS / STS (measured: -7 % run time, profiles/r02_ab_d.log). */
+template <class T> __device__ __forceinline__ T *smem_base(unsigned char *raw) {
+    T *p = reinterpret_cast<T *>(raw);
+#ifndef B200SAT_EMU
+    asm volatile("" : "+l"(p));
+    __builtin_assume(__isShared(p));
+#endif
+    return p;
 }
 
 template <class WS> __device__ __forceinline__ void bind_item(WS &S, const KParams &P, u32 w) {
@@ -85,14 +100,14 @@ template <int NV, bool COUNT, bool SIMP> __global__ void __launch_bounds__(64, 8
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSolver<VarsS<NV, SIMP>, COUNT> S(P, lane);
-    S.V.s = reinterpret_cast<SmemVars<NV, SIMP> *>(smem_raw) + warp;
+    S.V.s = smem_base<SmemVars<NV, SIMP>>(smem_raw) + warp;
     ingest_loop<SIMP>(S, P);
 }
 template <bool COUNT, bool SIMP> __global__ void __launch_bounds__(64, 8) ingest_glob(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSolver<VarsG, COUNT> S(P, lane);
-    S.V.s = reinterpret_cast<SmemSmall *>(smem_raw) + warp;
+    S.V.s = smem_base<SmemSmall>(smem_raw) + warp;
     ingest_loop<SIMP>(S, P);
 }
 #elif B200SAT_KERNEL_TU_PHASE == 2
@@ -119,16 +134,16 @@ template <class WS> __device__ __forceinline__ void replay_loop(WS &S, const KPa
         __syncwarp();
     }
 }
-template <int NV, bool COUNT> __global__ void __launch_bounds__(32, B200SAT_SEARCH_BLOCKS) replay_smem(const __grid_constant__ KParams P) {
+template <int NV, bool COUNT> __global__ void __launch_bounds__(32, 32) replay_smem(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSolver<VarsS<NV, false>, COUNT, false> S(P, threadIdx.x);
-    S.V.s = reinterpret_cast<SmemVars<NV, false> *>(smem_raw);
+    S.V.s = smem_base<SmemVars<NV, false>>(smem_raw);
     replay_loop(S, P);
 }
 template <bool COUNT> __global__ void __launch_bounds__(32, 16) replay_glob(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSolver<VarsG, COUNT, false> S(P, threadIdx.x);
-    S.V.s = reinterpret_cast<SmemSmall *>(smem_raw);
+    S.V.s = smem_base<SmemSmall>(smem_raw);
     replay_loop(S, P);
 }
 #else
@@ -257,13 +272,13 @@ template <class WS> __device__ __forceinline__ void search_loop_rescue(WS &S, co
 template <int NV> __global__ void __launch_bounds__(32, B200SAT_SEARCH_BLOCKS) rescue_smem(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSolver<VarsS<NV, false>, false, true> S(P, threadIdx.x);
-    S.V.s = reinterpret_cast<SmemVars<NV, false> *>(smem_raw);
+    S.V.s = smem_base<SmemVars<NV, false>>(smem_raw);
     search_loop_rescue(S, P);
 }
 __global__ void __launch_bounds__(32, 16) rescue_glob(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSolver<VarsG, false, true> S(P, threadIdx.x);
-    S.V.s = reinterpret_cast<SmemSmall *>(smem_raw);
+    S.V.s = smem_base<SmemSmall>(smem_raw);
     search_loop_rescue(S, P);
 }
 #else
@@ -272,13 +287,13 @@ __global__ void __launch_bounds__(32, 16) rescue_glob(const __grid_constant__ KP
 template <int NV, bool COUNT, bool PF> __global__ void __launch_bounds__(32, B200SAT_SEARCH_BLOCKS) search_smem(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSolver<VarsS<NV, false>, COUNT, PF> S(P, threadIdx.x);
-    S.V.s = reinterpret_cast<SmemVars<NV, false> *>(smem_raw);
+    S.V.s = smem_base<SmemVars<NV, false>>(smem_raw);
     search_loop_ring(S, P);
 }
 template <bool COUNT, bool PF> __global__ void __launch_bounds__(32, 16) search_glob(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSolver<VarsG, COUNT, PF> S(P, threadIdx.x);
-    S.V.s = reinterpret_cast<SmemSmall *>(smem_raw);
+    S.V.s = smem_base<SmemSmall>(smem_raw);
     search_loop_ring(S, P);
 }
 #endif

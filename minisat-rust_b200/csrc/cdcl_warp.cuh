@@ -1415,7 +1415,7 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
             const u32 p = V.trail()[qh];
             qh++;
             const u32 not_p = p ^ 1;
-            const u32 word = V.wstart()[p];
+            u32 word = V.wstart()[p];
             const u32 n = V.wlen()[p];
             const bool dirty = (word & W_DIRTY) != 0;
             uint2 *ws = wpool + (word >> W_SHIFT);
@@ -1481,6 +1481,10 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
                     const bool commit = pend && lane < stop;
                     const bool mv = commit && out == OUT_MOVE;
                     const bool keep = commit && !mv;
+                    /* lanes that move to the same list; issued here so that the match (the longest-latency warp
+                     * instruction of the loop) overlaps the stores below instead of stalling the append */
+                    const u32 tgt = lk ^ 1;
+                    const u32 peers = __match_any_sync(FULL_MASK, mv ? tgt : (0x80000000u | lane));
                     const u32 keepmask = __ballot_sync(FULL_MASK, keep);
                     if (keep) ws[j + __popc(keepmask & lt)] = make_uint2(w.x, out == OUT_KEEPW ? w.y : first);
                     j += __popc(keepmask);
@@ -1517,8 +1521,6 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
                     }
                     if (movemask) {
                         /* ordered parallel append: lanes with the same target list keep their lane order */
-                        const u32 tgt = lk ^ 1;
-                        const u32 peers = __match_any_sync(FULL_MASK, mv ? tgt : (0x80000000u | lane));
                         u32 tword = 0, tlen = 0;
                         bool over = false;
                         if (mv) {
@@ -1532,7 +1534,8 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
                         if (__ballot_sync(FULL_MASK, over)) {
                             qhead = qh; trail_n = tn;
                             if (!push_watch_multi(movemask, mv, tgt, w.x, first)) return CREF_UNDEF;
-                            ws = wpool + (V.wstart()[p] >> W_SHIFT); /* the pool may have been compacted */
+                            word = V.wstart()[p]; /* the pool may have been compacted */
+                            ws = wpool + (word >> W_SHIFT);
                         } else { /* every lane has read its list length before the ballot above completed */
                             if (mv) {
                                 wpool[(tword >> W_SHIFT) + tlen + __popc(peers & lt)] = make_uint2(w.x, first);
@@ -1567,11 +1570,10 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
                 if (live) ws[j + __popc(m & lt)] = w;
                 j += __popc(m);
             }
-            __syncwarp();
-            if (lane == 0) {
-                if (j != n) V.wlen()[p] = (idx_t)j;
-                if (dirty) V.wstart()[p] = V.wstart()[p] & ~W_DIRTY;
-            }
+            /* every lane stores the same words (one predicated STS each instead of a lane-0 branch region); nobody
+             * reads them before the barrier below */
+            V.wlen()[p] = (idx_t)j;
+            if (dirty) V.wstart()[p] = word & ~W_DIRTY;
             __syncwarp();
             if (confl != CREF_UNDEF) break;
         }

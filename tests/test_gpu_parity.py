@@ -698,7 +698,12 @@ def test_config1_every_bundled_file(pkg, po, eng, kind_name, corpus):
     lits_all = g["lits"].astype(np.uint32)
     kind = pkg.CORE if kind_name == "core" else pkg.SIMP
     nv = g["n_vars"]
-    groups = [[i for i in range(n) if lo < nv[i] <= hi] for lo, hi in ((0, 128), (128, 256), (256, 1024), (1024, 1 << 30))]
+    # One warp runs an instance at ~125 us per conflict, so the default run keeps the instances with at most 150 k
+    # conflicts (3,021 of 3,023 tests/cnf files, 68 of the 149 tests/cnf-hard ones: about a minute per variant);
+    # B200SAT_FULL_CORPUS=1 runs every instance of the fixture (profiles/r02_pytest_c.log: all green, 93 s / 130 s).
+    box = (1 << 62) if os.environ.get("B200SAT_FULL_CORPUS") else 150000
+    worst = np.maximum(g["core_stats"][:, 4], g["simp_stats"][:, 4])
+    groups = [[i for i in range(n) if lo < nv[i] <= hi and worst[i] <= box] for lo, hi in ((0, 128), (128, 256), (256, 1024), (1024, 1 << 30))]
     t_all, solved = 0.0, 0
     for group in groups:
         if not group:
@@ -725,8 +730,8 @@ def test_config1_every_bundled_file(pkg, po, eng, kind_name, corpus):
                 assert res[k]["eliminated_vars"] == int(g["simp_elim"][i]) and res[k]["n_clauses_pre"] == int(g["simp_nclauses_pre"][i]), name
         assert check_models(ioff, coff, lits, res["verdict"], models) == 0
         solved += len(group)
-    print("\nconfig 1 [%s, %s]: %d instances in %.2f s through the C ABI with host buffers = %.0f instances/s; excluded: %s"
-          % (corpus, kind_name, solved, t_all, solved / t_all, list(g["excluded"])))
+    print("\nconfig 1 [%s, %s]: %d of %d instances in %.2f s through the C ABI with host buffers = %.0f instances/s; excluded from the fixture: %s"
+          % (corpus, kind_name, solved, n, t_all, solved / t_all, list(g["excluded"])))
 
 
 def test_portfolio_two_gpus_peer_rings_and_cancel(pkg, po):
@@ -857,6 +862,13 @@ def _extend_model_host(estack, model):
     return m
 
 
+# verdicts of the ORIGINAL tests/cnf-hard formulas of corpus_hard.npz (oracle CoreSolver, default settings, run once on the
+# CPU: 0.3-3 s each; 2bitadd_10 needs 7.6 M conflicts = minutes, so its reduced formula is checked for structure only)
+K4_ORIGINAL_VERDICT = {"3bitadd_32.cnf.gz": 1, "grieu-vmpc-s05-24s.cnf.gz": 1, "e0ddr2-10-by-5-1.cnf.gz": 1,
+                       "manol-pipe-f6b.cnf.gz": 0, "stric-bmc-ibm-12.cnf.gz": 1, "2bitadd_10.cnf.gz": 0}
+K4_TOO_LONG_FOR_THE_ORACLE = {"2bitadd_10.cnf.gz"}
+
+
 def test_k4_one_preprocessor(pkg, po):
     """K4 as ONE preprocessor (csrc/preprocess_coop.cu): subsumption + strengthening + BVE interleaved to a fixpoint in one
     cooperative kernel.  S* parity: the reduced formula has the original's verdict, every model of it,
@@ -877,9 +889,14 @@ def test_k4_one_preprocessor(pkg, po):
             r = e.preprocess_instance(0, len(off) - 1, len(lits))
             assert not r["unsat"] and r["launches"] <= 20
             nv = int(lits.max() >> 1) + 1
-            o, om = po.solve_csr(off, lits, kind=po.CORE)
+            oc = [int(x) for x in g["rows"][i]]     # oracle SimpSolver preprocessing: n_vars, ingest, clauses left, eliminated vars, ...
+            if str(name) in K4_TOO_LONG_FOR_THE_ORACLE:   # structure only: the CPU solve of the reduced formula takes minutes
+                assert r["kept"] <= len(off) - 1
+                rows.append((str(name), len(off) - 1, r["kept"], oc[2], r["eliminated"], oc[3], r["outer"], r["bve_rounds"], r["ss_rounds"],
+                             r["launches"], r["kernel_ms"]))
+                continue
             red, rm = po.solve_csr(r["clause_off"], r["lits"] if len(r["lits"]) else np.zeros(1, np.uint32), kind=po.CORE)
-            assert red.verdict == o.verdict, name
+            assert red.verdict == K4_ORIGINAL_VERDICT[str(name)], name
             if red.verdict == 1:
                 m0 = np.full(nv, 2, np.uint8); m0[:len(rm)] = rm
                 dev = e.k4_extend_model(m0)
@@ -887,7 +904,6 @@ def test_k4_one_preprocessor(pkg, po):
                 assert (dev == host).all(), name
                 full = dev.copy(); full[full == 2] = 0
                 assert po.check_model(off, lits, full), name
-            oc = [int(x) for x in g["rows"][i]]     # oracle SimpSolver preprocessing: n_vars, ingest, clauses left, eliminated vars, ...
             rows.append((str(name), len(off) - 1, r["kept"], oc[2], r["eliminated"], oc[3], r["outer"], r["bve_rounds"], r["ss_rounds"],
                          r["launches"], r["kernel_ms"]))
     finally:
