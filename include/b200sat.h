@@ -245,6 +245,12 @@ int b200sat_engine_set_slice(b200sat_engine *e, uint32_t slice_conflicts);
 enum { B200SAT_VAR_UPOL_SET = 1, B200SAT_VAR_UPOL_VAL = 2 /* user polarity = sign: 1 picks the negative literal */,
        B200SAT_VAR_NOT_DECISION = 4 };
 int b200sat_engine_set_var_flags(b200sat_engine *e, const uint8_t *flags, const uint32_t *inst_var_off);
+/* With var flags set: clause_nvars[c] = how many vars the caller had created when it added clause c (global clause index
+ * of the resident batch) -- for callers that interleave new_var with add_clause, as the reference's own DIMACS loader
+ * does (dimacs.rs:146-167).  SimpSolver's elimination order depends on the interleaving (elim_queue.rs:26-76); CoreSolver
+ * is indifferent to it.  NULL = every var was created before the first clause (sat.rs:31-32 call order).  Call after
+ * set_var_flags; an upload resets it.  The b200sat_add_clause / b200sat_new_var handle records it by itself. */
+int b200sat_engine_set_clause_nvars(b200sat_engine *e, const uint32_t *clause_nvars);
 /* assumptions of the following solve calls (Solver::solve_limited's &[Lit], sat.rs:34; search.rs:216-232), applied to
  * every instance of the batch; n = 0 clears them.  A false assumption ends the search UNSAT, as in the reference
  * (search.rs:431-435 drops analyze_final's result). */

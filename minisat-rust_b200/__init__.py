@@ -122,7 +122,7 @@ ABI_SYMBOLS = (
     "b200sat_engine_ring_open_peer", "b200sat_portfolio_solve", "b200sat_engine_download_replicas",
     "b200sat_engine_verify_models", "b200sat_engine_subsume_instance", "b200sat_engine_simplify_instance", "b200sat_engine_bve_instance", "b200sat_read_dimacs", "b200sat_free_buffer", "b200sat_write_result",
     "b200sat_engine_set_slice", "b200sat_engine_set_budget", "b200sat_engine_interrupt",
-    "b200sat_engine_bcp_replay", "b200sat_engine_set_var_flags", "b200sat_engine_set_assumptions",
+    "b200sat_engine_bcp_replay", "b200sat_engine_set_var_flags", "b200sat_engine_set_clause_nvars", "b200sat_engine_set_assumptions",
     "b200sat_engine_resume", "b200sat_engine_resume_async", "b200sat_engine_set_import_cap",
     "b200sat_engine_ring_open_local_peer", "b200sat_engine_set_progress_rows", "b200sat_engine_download_progress",
     "b200sat_engine_set_rescue", "b200sat_engine_preprocess_instance", "b200sat_engine_k4_extend_model",
@@ -174,6 +174,7 @@ def lib():
     L.b200sat_engine_launch_info.argtypes = [vp, C.POINTER(LaunchInfo)]
     L.b200sat_engine_bcp_replay.argtypes = [vp, C.POINTER(Settings), C.c_int, C.POINTER(ReplayInfo), vp]
     L.b200sat_engine_set_var_flags.argtypes = [vp, u8p, u32p]
+    L.b200sat_engine_set_clause_nvars.argtypes = [vp, u32p]
     L.b200sat_engine_set_assumptions.argtypes = [vp, u32p, C.c_uint32]
     L.b200sat_engine_resume.argtypes = [vp, vp]
     L.b200sat_engine_resume_async.argtypes = [vp, vp]
@@ -378,6 +379,15 @@ class Engine:
         f = np.ascontiguousarray(flags, dtype=np.uint8)
         o, op = _u32(inst_var_off)
         _check(lib().b200sat_engine_set_var_flags(self._e, f.ctypes.data_as(C.POINTER(C.c_uint8)), op))
+
+    def set_clause_nvars(self, clause_nvars):
+        """vars that existed when each clause of the resident batch was added (new_var interleaved with add_clause);
+        None = every var created before the first clause.  Needs set_var_flags."""
+        if clause_nvars is None:
+            _check(lib().b200sat_engine_set_clause_nvars(self._e, None))
+            return
+        a, ap = _u32(clause_nvars)
+        _check(lib().b200sat_engine_set_clause_nvars(self._e, ap))
 
     def set_assumptions(self, lits):
         a, ap = _u32(lits if lits is not None and len(lits) else np.zeros(1, np.uint32))

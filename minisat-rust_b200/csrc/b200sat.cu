@@ -194,6 +194,9 @@ struct b200sat_engine {
     u32 *d_var_off = nullptr;
     size_t cap_var_off = 0;
     bool have_var_flags = false;
+    u32 *d_clause_nvars = nullptr; /* vars that existed when each clause was added (optional, with the var flags) */
+    size_t cap_clause_nvars = 0;
+    bool have_clause_nvars = false;
     u32 *d_assumps = nullptr;     /* assumptions of the following solve calls */
     size_t cap_assumps = 0;
     u32 n_assumps = 0;
@@ -302,7 +305,7 @@ extern "C" void b200sat_engine_destroy(b200sat_engine *e) {
     if (e->h_interrupt) cudaFreeHost(e->h_interrupt);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     cudaFree(e->d_ring);
-    cudaFree(e->d_trace); cudaFree(e->d_progress); cudaFree(e->d_pristine); cudaFree(e->d_run_table); cudaFree(e->d_rrings); cudaFree(e->d_parked); cudaFree(e->d_var_flags); cudaFree(e->d_var_off); cudaFree(e->d_assumps);
+    cudaFree(e->d_trace); cudaFree(e->d_progress); cudaFree(e->d_pristine); cudaFree(e->d_run_table); cudaFree(e->d_rrings); cudaFree(e->d_parked); cudaFree(e->d_var_flags); cudaFree(e->d_clause_nvars); cudaFree(e->d_var_off); cudaFree(e->d_assumps);
     delete e;
 }
 
@@ -315,6 +318,19 @@ extern "C" int b200sat_engine_configure(b200sat_engine *e, int warps_per_block, 
 
 static int alloc_outputs(b200sat_engine *e);
 /* Solver::new_var(upol, dvar) records for the resident batch (sat.rs:31; decision_heuristic.rs:70-102,181-192) */
+/* With var flags set: clause_nvars[c] = how many vars the caller had created when it added clause c of the resident
+ * batch (global clause index).  SimpSolver's elimination order depends on it (elim_queue.rs:26-76).  null clears. */
+extern "C" int b200sat_engine_set_clause_nvars(b200sat_engine *e, const uint32_t *clause_nvars) {
+    if (!e) return set_err(B200SAT_E_ARG, "null engine");
+    if (!clause_nvars) { e->have_clause_nvars = false; return 0; }
+    if (e->n_clauses == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    int rc;
+    if ((rc = ensure(e->d_clause_nvars, e->cap_clause_nvars, (size_t)e->n_clauses))) return rc;
+    CK(cudaMemcpy(e->d_clause_nvars, clause_nvars, (size_t)e->n_clauses * 4, cudaMemcpyHostToDevice));
+    e->have_clause_nvars = true;
+    return 0;
+}
 extern "C" int b200sat_engine_set_var_flags(b200sat_engine *e, const uint8_t *flags, const uint32_t *inst_var_off) {
     if (!e) return set_err(B200SAT_E_ARG, "null engine");
     CK(cudaSetDevice(e->device));
@@ -441,7 +457,7 @@ static int device_shape(b200sat_engine *e, cudaStream_t stream) {
 
 extern "C" int b200sat_engine_upload(b200sat_engine *e, const b200sat_batch *b, void *stream_) {
     if (!e || !b) return set_err(B200SAT_E_ARG, "null argument");
-    e->have_var_flags = false; e->resident_items = 0;
+    e->have_var_flags = false; e->have_clause_nvars = false; e->resident_items = 0;
     cudaStream_t stream = (cudaStream_t)stream_;
     CK(cudaSetDevice(e->device));
     const u32 n = b->n_inst;
@@ -495,7 +511,7 @@ extern "C" int b200sat_engine_generate_ksat(b200sat_engine *e, uint64_t seed_bas
                                             uint32_t n_clauses, uint32_t k, void *stream_) {
     if (!e) return set_err(B200SAT_E_ARG, "null engine");
     if (k == 0 || k > n_vars) return set_err(B200SAT_E_ARG, "k must be in 1..n_vars");
-    e->have_var_flags = false; e->resident_items = 0;
+    e->have_var_flags = false; e->have_clause_nvars = false; e->resident_items = 0;
     if ((u64)n_inst * n_clauses * k > 0xFFFFFFF0ull) return set_err(B200SAT_E_ARG, "batch exceeds 2^32 literals");
     cudaStream_t stream = (cudaStream_t)stream_;
     CK(cudaSetDevice(e->device));
@@ -610,7 +626,7 @@ static void fill_params(b200sat_engine *e, KParams &P, const Layout &L) {
     P.trace_buf = e->trace_cap ? e->d_trace : nullptr; P.trace_cap = e->trace_cap;
     P.parked = e->d_parked;
     if (e->progress_rows && e->d_progress && !pd.portfolio) { P.progress_buf = e->d_progress; P.progress_cap = e->progress_rows; }
-    if (e->have_var_flags && !pd.portfolio) { P.var_flags = e->d_var_flags; P.inst_var_off = e->d_var_off; }
+    if (e->have_var_flags && !pd.portfolio) { P.var_flags = e->d_var_flags; P.inst_var_off = e->d_var_off; P.clause_nvars = e->have_clause_nvars ? e->d_clause_nvars : nullptr; }
     P.assumps = e->d_assumps; P.n_assumps = e->n_assumps;
 }
 
@@ -1405,6 +1421,7 @@ struct b200sat_solver {
     std::vector<u8> dvar;
     std::vector<u32> clause_off{0};
     std::vector<u32> lits;
+    std::vector<u32> clause_nvars;   /* n_vars at each add_clause */
     size_t n_clauses_known = 0;
     b200sat_stats stats;
     b200sat_engine *eng = nullptr;
@@ -1444,6 +1461,7 @@ extern "C" int b200sat_add_clause(b200sat_solver *h, const uint32_t *lits, size_
     for (size_t i = 1; i < ps.size(); i++) if (ps[i] == (ps[i - 1] ^ 1)) taut = true;
     h->lits.insert(h->lits.end(), lits, lits + n);
     h->clause_off.push_back((u32)h->lits.size());
+    h->clause_nvars.push_back(h->n_vars);
     h->resident = false; /* the next solve ingests the whole clause list again */
     if (!taut) {
         if (ps.empty()) { h->ok = false; return 0; }
@@ -1490,6 +1508,7 @@ static int solver_ingest(b200sat_solver *h, int flags, const b200sat_budget *b, 
         vf[v] = (u8)((h->upol[v] ? (VARF_UPOL_SET | (h->upol[v] == 3 ? VARF_UPOL_VAL : 0)) : 0) | (h->dvar[v] ? 0 : VARF_NOT_DECISION));
     u32 voff[2] = {0, h->n_vars};
     if ((rc = b200sat_engine_set_var_flags(h->eng, vf.data(), voff))) return rc;
+    if ((rc = b200sat_engine_set_clause_nvars(h->eng, h->clause_nvars.empty() ? nullptr : h->clause_nvars.data()))) return rc;
     if ((rc = b200sat_engine_set_budget(h->eng, b ? b->conflict_budget : -1, b ? b->propagation_budget : -1))) return rc;
     if ((rc = b200sat_engine_solve_async(h->eng, &h->st, h->kind, flags, nullptr))) return rc;
     if ((rc = solver_wait(h, b))) return rc;

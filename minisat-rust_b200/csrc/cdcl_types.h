@@ -166,6 +166,9 @@ struct KParams {
      * var_flags[inst_var_off[i] + v]: VARF_* bits; inst_var_off[i + 1] - inst_var_off[i] = number of vars created */
     const u8 *var_flags;
     const u32 *inst_var_off;
+    /* optional, with var_flags: clause_nvars[c] = vars that existed when clause c was added (new_var calls interleaved
+     * with add_clause, as the reference's own DIMACS loader does); null = every var was created before the first clause */
+    const u32 *clause_nvars;
     const u32 *assumps;       /* assumptions of solve_limited (sat.rs:34), shared by every instance of the batch */
     u32 n_assumps;
     u8 *parked;               /* [item] 1: the item's state is resident and resumable (PH_READY), 0: not */

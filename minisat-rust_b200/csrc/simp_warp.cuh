@@ -1252,14 +1252,18 @@ DEVNI SimpPhaseOut simp_phase(const KParams *Pp, VT V, u8 *slab, const b200sat_s
     if (lane == 0) {
         S.sc().extra_clause_field = 1;   /* Simplificator::on simplify.rs:546-549 */
         S.sc().remove_satisfied = 0;
-        /* a caller of the trait creates every var before it adds clauses (sat.rs:31-32) */
-        if (P.var_flags) while (Z.n_created < S.nvars) Z.init_var(Z.n_created);
+        /* Var creation order matters here (the elimination heap is updated by every occurrence, elim_queue.rs:26-76).
+         * A caller of the trait that creates every var first (sat.rs:31-32): var_flags without clause_nvars.  A caller
+         * that interleaves new_var with add_clause: clause_nvars[c] vars exist when clause c arrives. */
+        if (P.var_flags && !P.clause_nvars) while (Z.n_created < S.nvars) Z.init_var(Z.n_created);
         /* ingest: dimacs.rs:146-167 order -- vars are created lazily, interleaved with the clauses */
         for (u32 c = cb; c < ce && !Z.failed(); c++) {
             u32 b = P.clause_off[c], e = P.clause_off[c + 1];
+            if (P.var_flags && P.clause_nvars) { const u32 want = P.clause_nvars[c] < S.nvars ? P.clause_nvars[c] : S.nvars; while (Z.n_created < want) Z.init_var(Z.n_created); }
             for (u32 k = b; k < e; k++) while ((P.lits[k] >> 1) + 1 > Z.n_created) Z.init_var(Z.n_created);
             if (!Z.add_clause(P.lits + b, e - b)) ok = 0; /* SimpSolver::add_clause: no `ok` check before (minisat.rs:146-158) */
         }
+        if (P.var_flags) while (Z.n_created < S.nvars && !Z.failed()) Z.init_var(Z.n_created); /* vars created after the last clause */
         o.n_ingest = S.sc().num_clauses;
         o.n_pre = o.n_ingest;
         bad = Z.failed() ? 1 : 0;

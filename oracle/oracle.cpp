@@ -1451,6 +1451,8 @@ uint32_t oracle_get_progress(double *out, uint32_t cap_rows) {
 }
 static std::vector<uint8_t> g_var_flags;   /* bit0 upol set, bit1 upol value, bit2 not a decision var */
 static std::vector<Lit> g_assumptions;
+static std::vector<uint32_t> g_clause_nvars;   /* with g_var_flags: vars that existed when clause c was added */
+void oracle_set_clause_nvars(const uint32_t *nv, uint32_t n) { g_clause_nvars.assign(nv, nv + (nv ? n : 0)); }
 void oracle_set_var_flags(const uint8_t *flags, uint32_t n) { g_var_flags.assign(flags, flags + (flags ? n : 0)); }
 void oracle_set_assumptions(const uint32_t *lits, uint32_t n) { g_assumptions.assign(lits, lits + (lits ? n : 0)); }
 static int64_t g_conflict_budget = -1, g_propagation_budget = -1;
@@ -1467,17 +1469,24 @@ int oracle_solve_csr(const uint32_t *clause_off, const uint32_t *lits, uint32_t 
     Solver solver(*s, kind);
     std::vector<Lit> tmp;
     if ((flags & ORACLE_F_NO_PRE) && kind == ORACLE_SIMP) solver.preprocess();   /* lib.rs:36-41 */
-    /* the trait's own call order (sat.rs:31-32): every var created with its (upol, dvar) before the clauses are added */
-    for (size_t v = 0; v < g_var_flags.size(); v++) {
-        uint8_t f = g_var_flags[v];
-        solver.new_var((f & 1) ? ((f & 2) ? 1 : 0) : -1, !(f & 4));
-    }
+    /* new_var(upol, dvar) records: either the trait's own call order (sat.rs:31-32: every var before the clauses), or,
+     * with a per-clause watermark, new_var interleaved with add_clause the way the caller issued them */
+    auto create_flagged = [&](size_t upto) {
+        while (solver.n_vars() < upto && solver.n_vars() < g_var_flags.size()) {
+            uint8_t f = g_var_flags[solver.n_vars()];
+            solver.new_var((f & 1) ? ((f & 2) ? 1 : 0) : -1, !(f & 4));
+        }
+    };
+    const bool interleaved = !g_var_flags.empty() && g_clause_nvars.size() >= n_clauses;
+    if (!interleaved) create_flagged(g_var_flags.size());
     for (uint32_t c = 0; c < n_clauses; c++) {                             /* Subst::add_clause dimacs.rs:146-167 */
         uint32_t b = clause_off[c], e = clause_off[c + 1];
+        if (interleaved) create_flagged(g_clause_nvars[c]);
         for (uint32_t k = b; k < e; k++)
             while (lit_var(lits[k]) + 1 > solver.n_vars()) solver.new_var(-1, true);
         solver.add_clause(lits + b, e - b);
     }
+    create_flagged(g_var_flags.size());
     out->n_vars = (uint32_t)solver.n_vars();
     out->n_clauses_ingest = (uint32_t)solver.n_clauses();
     auto t1 = std::chrono::steady_clock::now();

@@ -128,6 +128,8 @@ void oracle_set_budget(int64_t conflict_budget, int64_t propagation_budget, int 
  * (bit0 upol set, bit1 upol value = sign, bit2 not a decision var) before any clause is added, as a caller of the
  * trait does (sat.rs:31-32); n = 0 restores the DIMACS behaviour (lazy creation, (None, true)). */
 void oracle_set_var_flags(const uint8_t *flags, uint32_t n);
+/* with var flags: clause_nvars[c] = vars created before clause c was added (interleaved new_var / add_clause) */
+void oracle_set_clause_nvars(const uint32_t *clause_nvars, uint32_t n);
 /* assumptions (&[Lit]) of the NEXT solve_limited calls; n = 0 clears them (search.rs:216-232,431-435) */
 void oracle_set_assumptions(const uint32_t *lits, uint32_t n);
 

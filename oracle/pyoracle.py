@@ -141,6 +141,7 @@ def lib():
         L.oracle_get_progress.argtypes = [C.POINTER(C.c_double), C.c_uint32]
         L.oracle_get_progress.restype = C.c_uint32
         L.oracle_set_var_flags.argtypes = [C.POINTER(C.c_uint8), C.c_uint32]
+        L.oracle_set_clause_nvars.argtypes = [C.POINTER(C.c_uint32), C.c_uint32]
         L.oracle_set_assumptions.argtypes = [C.POINTER(C.c_uint32), C.c_uint32]
         _lib = L
     return _lib
@@ -222,6 +223,15 @@ def set_var_flags(flags=None):
         return
     f = np.ascontiguousarray(flags, dtype=np.uint8)
     lib().oracle_set_var_flags(f.ctypes.data_as(C.POINTER(C.c_uint8)), len(f))
+
+
+def set_clause_nvars(clause_nvars=None):
+    """with var flags: vars that existed when each clause was added (new_var interleaved with add_clause); None clears"""
+    if clause_nvars is None or len(clause_nvars) == 0:
+        lib().oracle_set_clause_nvars(None, 0)
+        return
+    a = np.ascontiguousarray(clause_nvars, dtype=np.uint32)
+    lib().oracle_set_clause_nvars(a.ctypes.data_as(C.POINTER(C.c_uint32)), len(a))
 
 
 def set_assumptions(lits=None):

@@ -271,11 +271,12 @@ int emu_portfolio(const uint32_t *clause_off, const uint32_t *lits, uint32_t n_c
 
 /* optional inputs of the following emu_solve_batch calls: new_var(upol, dvar) records and assumptions */
 static const uint8_t *g_var_flags = nullptr;
-static const uint32_t *g_inst_var_off = nullptr, *g_assumps = nullptr;
+static const uint32_t *g_inst_var_off = nullptr, *g_assumps = nullptr, *g_clause_nvars = nullptr;
 static uint32_t g_n_assumps = 0;
 void emu_set_extras(const uint8_t *var_flags, const uint32_t *inst_var_off, const uint32_t *assumps, uint32_t n_assumps) {
     g_var_flags = var_flags; g_inst_var_off = inst_var_off; g_assumps = assumps; g_n_assumps = n_assumps;
 }
+void emu_set_clause_nvars(const uint32_t *clause_nvars) { g_clause_nvars = clause_nvars; }
 
 /* tier_nv: 128/256/1024 = shared-memory tier, 0 = global tier, -1 = auto.
  * sched_seed: 0 = lanes run in ascending order, else adversarial ordering.
@@ -327,7 +328,7 @@ int emu_solve_batch(const uint32_t *inst_clause_off, const uint32_t *clause_off,
         j.P.slabs = (u8 *)slab.data(); j.P.L = L; j.P.st = *st; j.P.kind = kind; j.P.flags = flags;
         j.P.attempt = attempt + 1;
         j.P.qctl = qctl; j.P.slice_conflicts = slice_conflicts;
-        j.P.var_flags = g_var_flags; j.P.inst_var_off = g_inst_var_off; j.P.assumps = g_assumps; j.P.n_assumps = g_n_assumps;
+        j.P.var_flags = g_var_flags; j.P.inst_var_off = g_inst_var_off; j.P.clause_nvars = g_var_flags ? g_clause_nvars : nullptr; j.P.assumps = g_assumps; j.P.n_assumps = g_n_assumps;
         j.smem = smem.data(); j.tier_nv = tier_nv;
         j.count = (flags & B200SAT_F_COUNT_TRAFFIC) != 0;
         std::vector<u32> again;

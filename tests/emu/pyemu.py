@@ -60,6 +60,7 @@ def lib():
                                     C.POINTER(Result), C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32]
         L.emu_portfolio.restype = C.c_int
         L.emu_set_extras.argtypes = [C.POINTER(C.c_uint8), u32p, u32p, C.c_uint32]
+        L.emu_set_clause_nvars.argtypes = [u32p]
         L.emu_bcp_replay.argtypes = [u32p, u32p, u32p, C.c_uint32, C.c_void_p, C.c_int, C.c_uint32, C.c_uint64,
                                      C.POINTER(C.c_uint64)]
         L.emu_bcp_replay.restype = C.c_int
@@ -75,7 +76,7 @@ def _u32(a):
 def solve_batch(inst_clause_off, clause_off, lits, settings, kind=0, flags=1 | 4 | 8 | 16, tier_nv=-1,
                 arena_words=0, wpool_entries=0, sched_seed=0, model_stride=0, slice_conflicts=0,
                 conflict_budget=-1, propagation_budget=-1, resume_rounds=0, want_suspends=False,
-                var_flags=None, inst_var_off=None, assumptions=None):
+                var_flags=None, inst_var_off=None, assumptions=None, clause_nvars=None):
     """settings: any ctypes struct with the b200sat_settings layout (e.g. oracle Settings).
     slice_conflicts > 0 parks and resumes every instance each time it used that many conflicts."""
     ioff, ioffp = _u32(inst_clause_off)
@@ -97,10 +98,15 @@ def solve_batch(inst_clause_off, clause_off, lits, settings, kind=0, flags=1 | 4
         if assumptions is not None and len(assumptions):
             asm, asp = _u32(assumptions)
         lib().emu_set_extras(vfp, vop, asp, 0 if asm is None else len(asm))
+    cnv = None
+    if clause_nvars is not None:
+        cnv, cnvp = _u32(clause_nvars)
+        lib().emu_set_clause_nvars(cnvp)
     rc = lib().emu_solve_batch(ioffp, offp, lip, n, C.addressof(settings), kind, flags, tier_nv,
                                arena_words, wpool_entries, sched_seed, res, mp, model_stride, slice_conflicts,
                                conflict_budget, propagation_budget, resume_rounds)
     lib().emu_set_extras(None, None, None, 0)
+    lib().emu_set_clause_nvars(None)
     if rc < 0:
         raise RuntimeError("emulator: solver kind not compiled in")
     if want_suspends:

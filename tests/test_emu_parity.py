@@ -313,6 +313,39 @@ def test_new_var_flags_and_assumptions(po, emu, kind):
         assert e[0].eliminated_vars == o.eliminated_vars
 
 
+def test_new_var_interleaved_with_add_clause(po, emu):
+    """new_var calls interleaved with add_clause (the reference's DIMACS loader, dimacs.rs:146-167, and any caller that
+    creates vars on demand): SimpSolver's elimination heap sees every occurrence as it arrives (elim_queue.rs:26-76), so
+    the interleaving changes the preprocessing result.  The per-clause watermark (clause_nvars) reproduces it: with
+    the lazy watermark the flagged run equals the plain fixture run, and on 2bitcomp_5 the up-front order differs."""
+    g = load_golden()
+    i = list(g["names"]).index("2bitcomp_5.cnf.gz")
+    off, lits = golden_instance(g, i)
+    nv = int(g["n_vars"][i])
+    ioff = np.array([0, len(off) - 1], np.uint32)
+    vf = np.zeros(nv, np.uint8)
+    lazy, seen = [], 0
+    for c in range(len(off) - 1):
+        seen = max(seen, int(lits[off[c]:off[c + 1]].max() >> 1) + 1)
+        lazy.append(seen)
+    st = po.default_settings()
+    outs = {}
+    for tag, cnv in (("upfront", None), ("lazy", np.array(lazy, np.uint32)), ("early", np.minimum(np.array(lazy, np.uint32) + 7, nv))):
+        po.set_var_flags(vf); po.set_clause_nvars(cnv)
+        try:
+            o, _ = po.solve_csr(off, lits, kind=po.SIMP)
+        finally:
+            po.set_var_flags(); po.set_clause_nvars()
+        e, _ = emu.solve_batch(ioff, off, lits, st, kind=po.SIMP, flags=FLAGS, model_stride=nv, sched_seed=3,
+                               var_flags=vf, inst_var_off=np.array([0, nv], np.uint32), clause_nvars=cnv)
+        assert e[0].status == 0 and e[0].verdict == o.verdict, tag
+        assert list(e[0].stats) == list(o.stats) and e[0].trace_hash == o.trace_hash, tag
+        assert e[0].eliminated_vars == o.eliminated_vars and e[0].n_clauses_pre == o.n_clauses_pre, tag
+        outs[tag] = (o.n_clauses_pre, list(o.stats))
+    assert outs["lazy"][0] == int(g["simp_nclauses_pre"][i]) and outs["lazy"][1] == [int(x) for x in g["simp_stats"][i]]
+    assert outs["upfront"] != outs["lazy"]
+
+
 def test_no_pre_simp_solver_is_a_core_solver_with_a_seeded_simplify_guard(po, emu):
     """--no-pre (lib.rs:36-41): SimpSolver::preprocess runs on the EMPTY formula before parsing; the simplifier is off
     afterwards but SimplifyGuard holds (Some(0), 0), so try_simplify fires at different moments than in a fresh
