@@ -343,7 +343,8 @@ def main():
                 # NOT measured in this run (ncu cannot run inside the bench): the committed `ncu --set full` capture of
                 # this exact workload and kernel; `traffic_static` says where it came from
                 traffic = float(tj["dram_bytes_per_launch"])
-                traffic_src = {"static": True, "capture": tj.get("capture"), "kernel": tj.get("kernel"), "commit": tj.get("commit")}
+                traffic_src = {"static": True, "capture": tj.get("capture"), "kernel": tj.get("kernel"), "commit": tj.get("commit"),
+                               "issue": tj.get("issue")}
         except Exception:
             pass
         value = world * B * a.steps / (dev_ms * 1e-3)
@@ -383,7 +384,14 @@ def main():
                 "algorithmic_bytes": bcp["bcp_bytes"], "propagations": bcp["propagations"],
                 "propagations_per_sec": bcp["propagations"] / bsec if bsec > 0 else None,
                 "instances": bcp["instances"], "replay_mismatches": bcp["mismatches"], "dram_bytes": None,
-                "note": "dram_bytes: see profiles/ (ncu capture of replay_smem); mismatches must be 0"}
+                "note": "mismatches must be 0"}
+            try:   # committed ncu capture of replay_smem on this exact workload (static, like `traffic`)
+                kj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("bcp_only")
+                if kj and a.solver == "core" and n == 100 and B == 10000:
+                    line["roofline"]["bcp_only"]["dram_bytes"] = float(kj["dram_bytes_per_launch"])
+                    line["roofline"]["bcp_only"]["dram_bytes_static"] = {"static": True, "capture": kj.get("capture")}
+            except Exception:
+                pass
             assert bcp["mismatches"] == 0, "bcp_replay left the recorded trace"
         if c3 is not None:
             ms3 = max(x[0] for x in c3)
