@@ -75,11 +75,32 @@ _use_native = False
 _native_flags = ""
 
 
+def _cpu_signature():
+    try:
+        model, flags = "", ""
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name") and not model:
+                model = ln.split(":", 1)[1].strip()
+            elif ln.startswith("flags") and not flags:
+                flags = " ".join(sorted(ln.split(":", 1)[1].split()))
+            if model and flags:
+                break
+        import hashlib
+        return model + " " + hashlib.sha1(flags.encode()).hexdigest()[:16]
+    except Exception:
+        return "unknown"
+
+
 def build_native():
     """CPU-baseline build for THIS machine: -O3 -march=native -flto (mirrors the reference's opt-level=3, lto=true,
     Cargo.toml:28-31).  Kept apart from the portable liboracle.so that travels with the repo."""
     src = os.path.join(_HERE, "oracle.cpp")
-    if os.path.exists(_NATIVE_PATH) and os.path.getmtime(_NATIVE_PATH) >= os.path.getmtime(src):
+    # a -march=native library is only valid on the CPU it was built on: the build records the host's CPU signature and
+    # a copy that travelled to another machine is rebuilt there
+    sig = _cpu_signature()
+    sig_path = _NATIVE_PATH + ".cpu"
+    if (os.path.exists(_NATIVE_PATH) and os.path.getmtime(_NATIVE_PATH) >= os.path.getmtime(src)
+            and os.path.exists(sig_path) and open(sig_path).read() == sig):
         return _NATIVE_PATH
     os.makedirs(os.path.dirname(_NATIVE_PATH), exist_ok=True)
     global _native_flags
@@ -89,6 +110,7 @@ def build_native():
         if subprocess.run(cmd, capture_output=True).returncode == 0:
             _native_flags = "-O3 -march=native" + (" -flto" if lto else " (single translation unit; -flto unavailable in this image)")
             open(_NATIVE_PATH + ".flags", "w").write(_native_flags)
+            open(sig_path, "w").write(sig)
             return _NATIVE_PATH
     raise RuntimeError("native oracle build failed")
 
