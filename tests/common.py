@@ -94,3 +94,13 @@ HAND_TRACES = {
     "H4_luby_restart": ([[1, 3, 2], [1, 3, -2]], 0, {"restart_first": 1.0}, 1, [1, 2, 5, 0, 1, 6, 2, 0], [0, 1, 1], 0, 2),
     "H5_simp_elimination": ([[1, 2]], 1, {}, 1, [1, 1, 1, 0, 0, 0, 0, 0], [1, 0], 2, 0),
 }
+
+# H6 / H7 of tests/golden/hand_traces.md: solve_limited(budget, assumptions) semantics, derived by hand from the Rust source.
+# name -> (clauses, assumptions (Lit encoding), (conflict_budget, propagation_budget),
+#          first call (verdict, stats), second call without budget (verdict, stats, model) or None)
+HAND_TRACES_CALLS = {
+    "H6_false_assumption": ([[1, 2], [-1, 2]], [3], (-1, -1), (0, [1, 1, 0, 0, 1, 2, 1, 0]), None),
+    "H7_conflict_budget_then_resume": ([[1, 3, 2], [1, 3, -2]], [], (1, -1), (2, [1, 1, 2, 0, 1, 3, 2, 0]),
+                                       (1, [2, 2, 5, 0, 1, 6, 2, 0], [0, 1, 1])),
+}
+

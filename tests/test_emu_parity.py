@@ -282,6 +282,25 @@ def test_hand_traces_device_source(po, emu):
             assert [int(x) for x in models[0][:nv]] == model, name
 
 
+def test_hand_traces_call_semantics_device_source(po, emu):
+    """H6 / H7 of tests/golden/hand_traces.md (false assumption; conflict budget -> Interrupted -> second solve_limited)
+    against the device source under the emulator."""
+    from common import HAND_TRACES_CALLS
+    for name, (clauses, assumps, (cb, pb), first, second) in HAND_TRACES_CALLS.items():
+        ioff, coff, lits = batch_of([csr_of(clauses)])
+        nv = max(abs(x) for c in clauses for x in c)
+        for rounds, want in ((0, first), (1, second)):
+            if want is None:
+                continue
+            res, models = emu.solve_batch(ioff, coff, lits, po.default_settings(), kind=0, flags=FLAGS, model_stride=nv, sched_seed=17,
+                                          conflict_budget=cb, propagation_budget=pb, resume_rounds=rounds,
+                                          assumptions=assumps if assumps else None)
+            assert res[0].status == 0 and res[0].verdict == want[0], (name, rounds)
+            assert list(res[0].stats) == want[1], (name, rounds, list(res[0].stats))
+            if len(want) > 2:
+                assert [int(x) for x in models[0][:nv]] == want[2], name
+
+
 @pytest.mark.parametrize("kind", [0, 1])
 def test_new_var_flags_and_assumptions(po, emu, kind):
     """Solver::new_var(upol, dvar) (decision_heuristic.rs:70-102,181-192) and solve_limited's assumptions

@@ -911,3 +911,28 @@ def test_k4_one_preprocessor(pkg, po):
     print("\nK4 one preprocessor: instance | clauses in | clauses left (K4 / oracle) | eliminated vars (K4 / oracle) | outer, BVE, subsume rounds | launches | ms")
     for row in rows:
         print("  %-28s %7d | %7d / %7d | %6d / %6d | %2d %4d %4d | %2d | %8.2f" % row)
+
+
+def test_hand_traces_call_semantics_gpu(pkg):
+    """H6 / H7 of tests/golden/hand_traces.md through the trait mirror of the C ABI (b200sat_new_var / add_clause /
+    preprocess / solve_limited with a budget and assumptions): a false assumption ends UNSAT; a conflict budget of 1
+    returns Interrupted with the handle still usable, the second solve_limited finishes the search."""
+    from common import HAND_TRACES_CALLS
+    for name, (clauses, assumps, (cb, pb), first, second) in HAND_TRACES_CALLS.items():
+        nv = max(abs(x) for c in clauses for x in c)
+        s = pkg.CoreSolver()
+        for _ in range(nv):
+            s.new_var(None, True)
+        for c in clauses:
+            assert s.add_clause([((abs(x) - 1) << 1) | (1 if x < 0 else 0) for x in c])
+        assert s.preprocess()
+        r = s.solve_limited(budget=(cb, pb) if (cb >= 0 or pb >= 0) else None, assumptions=assumps)
+        assert r.kind == first[0] and [r.stats[k] for k in pkg.STAT_NAMES] == first[1], (name, r.kind, r.stats)
+        if second is not None:
+            r = s.solve_limited(assumptions=assumps)
+            assert r.kind == second[0] and [r.stats[k] for k in pkg.STAT_NAMES] == second[1], (name, r.kind, r.stats)
+            model = [2] * nv
+            for l in r.model:
+                model[pkg.lit_var(l)] = 0 if pkg.lit_sign(l) else 1
+            assert model == second[2], name
+

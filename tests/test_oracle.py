@@ -138,3 +138,23 @@ def test_hand_traces(po):
         assert r.eliminated_vars == elim and r.n_clauses_pre == ncl, name
         if model is not None:
             assert [int(x) for x in m] == model, name
+
+
+def test_hand_traces_call_semantics(po):
+    """H6 / H7 of tests/golden/hand_traces.md: a false assumption, a conflict budget with Interrupted and a second
+    solve_limited -- constants derived by hand from the Rust source pin the oracle's round-2 additions."""
+    from common import HAND_TRACES_CALLS, csr_of
+    for name, (clauses, assumps, (cb, pb), first, second) in HAND_TRACES_CALLS.items():
+        off, lits = csr_of(clauses)
+        for rounds, want in ((0, first), (1, second)):
+            if want is None:
+                continue
+            po.set_assumptions(assumps); po.set_budget(cb, pb, rounds)
+            try:
+                r, m = po.solve_csr(off, lits, kind=po.CORE)
+            finally:
+                po.set_assumptions(); po.set_budget()
+            assert r.verdict == want[0] and list(r.stats) == want[1], (name, rounds, r.verdict, list(r.stats))
+            if len(want) > 2:
+                assert [int(x) for x in m] == want[2], name
+
