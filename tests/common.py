@@ -93,6 +93,8 @@ HAND_TRACES = {
     "H3_binary_learnt": ([[1, 3, 2], [1, 3, -2]], 0, {}, 1, [1, 1, 4, 0, 1, 4, 2, 0], [0, 1, 1], 0, 2),
     "H4_luby_restart": ([[1, 3, 2], [1, 3, -2]], 0, {"restart_first": 1.0}, 1, [1, 2, 5, 0, 1, 6, 2, 0], [0, 1, 1], 0, 2),
     "H5_simp_elimination": ([[1, 2]], 1, {}, 1, [1, 1, 1, 0, 0, 0, 0, 0], [1, 0], 2, 0),
+    "H8_simp_subsume_strengthen_unit": ([[1, 2], [1, 2, 3], [-1, 2]], 1, {}, 1, [1, 1, 1, 0, 0, 1, 0, 0], [0, 1, 0], 2, 0),
+    "H9_simp_resolvent_and_heap_order": ([[1, 2], [-1, 3], [-2, -3], [2, 3]], 1, {}, 1, [1, 1, 1, 0, 0, 0, 0, 0], [0, 1, 0], 3, 0),
 }
 
 # H6 / H7 of tests/golden/hand_traces.md: solve_limited(budget, assumptions) semantics, derived by hand from the Rust source.
