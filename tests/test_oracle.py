@@ -158,3 +158,24 @@ def test_hand_traces_call_semantics(po):
             if len(want) > 2:
                 assert [int(x) for x in m] == want[2], name
 
+
+def test_hand_trace_document_and_fixture_agree():
+    """The constants asserted by the hand-trace tests are the ones written in tests/golden/hand_traces.md (the derivation
+    is the source of truth; common.py must not drift from it)."""
+    import os, re
+    from common import HAND_TRACES, HAND_TRACES_CALLS
+    text = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hand_traces.md")).read()
+    doc = {}
+    for sec in re.split(r"\n## ", text)[1:]:
+        m = re.match(r"(H\d+)", sec)
+        if m:
+            doc[m.group(1)] = [[int(x) for x in t.split(",")] for t in re.findall(r"[Ss]tats `\[([0-9, ]+)\]`", sec)]
+    for name, t in HAND_TRACES.items():
+        key = name.split("_")[0]
+        assert key in doc and t[4] in doc[key], (name, t[4], doc.get(key))
+    for name, (_, _, _, first, second) in HAND_TRACES_CALLS.items():
+        key = name.split("_")[0]
+        assert first[1] in doc[key], name
+        if second is not None:
+            assert second[1] in doc[key], name
+
