@@ -141,6 +141,11 @@ int      b200sat_solve_limited(b200sat_solver *h, const b200sat_budget *b,
                                uint8_t *model, size_t model_cap);
 /* Solver::stats (sat.rs:35; search.rs:590-601) */
 void     b200sat_get_stats(const b200sat_solver *h, b200sat_stats *out);
+/* the progress estimate carried by the last SolveRes::Interrupted of this handle (sat.rs:24); 0 before any */
+double   b200sat_progress_estimate(const b200sat_solver *h);
+/* sizeof of the structs that cross this boundary, for bindings that mirror them by hand:
+ * out[0] = b200sat_result, out[1] = b200sat_settings, out[2] = b200sat_stats, out[3] = b200sat_launch_info */
+void     b200sat_abi_sizes(uint32_t out[4]);
 
 /* ------------------------------------------------------------------ batch (new: no reference analogue)
  * Many independent solvers advanced by one persistent kernel, one warp per
@@ -168,6 +173,8 @@ typedef struct b200sat_result {
     uint64_t trace_hash;       /* FNV-1a over conflicts when B200SAT_F_TRACE_HASH       */
     uint32_t exported;         /* portfolio: clauses this replica appended to its ring  */
     uint32_t imported;         /* portfolio: clauses this replica took from the rings   */
+    double   progress;         /* B200SAT_INTERRUPTED by a budget / interrupt: the f64 of SolveRes::Interrupted(progress, _),
+                                  search/util.rs:5-14, taken before the trail is undone (search.rs:473-477); else 0 */
 } b200sat_result;
 
 typedef struct b200sat_engine b200sat_engine;

@@ -68,7 +68,7 @@ class Result(C.Structure):
         ("n_clauses_ingest", C.c_uint32), ("n_clauses_pre", C.c_uint32), ("eliminated_vars", C.c_uint32),
         ("pre_ok", C.c_uint32), ("attempts", C.c_uint32),
         ("stats", C.c_uint64 * 8), ("traffic", C.c_uint64 * 8), ("trace_hash", C.c_uint64),
-        ("exported", C.c_uint32), ("imported", C.c_uint32),
+        ("exported", C.c_uint32), ("imported", C.c_uint32), ("progress", C.c_double),
     ]
 
     def stats_dict(self):
@@ -79,7 +79,7 @@ RESULT_DTYPE = np.dtype([
     ("verdict", np.int32), ("status", np.int32), ("n_vars", np.uint32), ("n_clauses_ingest", np.uint32),
     ("n_clauses_pre", np.uint32), ("eliminated_vars", np.uint32), ("pre_ok", np.uint32), ("attempts", np.uint32),
     ("stats", np.uint64, (8,)), ("traffic", np.uint64, (8,)), ("trace_hash", np.uint64),
-    ("exported", np.uint32), ("imported", np.uint32)])
+    ("exported", np.uint32), ("imported", np.uint32), ("progress", np.float64)])
 assert RESULT_DTYPE.itemsize == C.sizeof(Result)
 
 
@@ -113,6 +113,7 @@ ABI_SYMBOLS = (
     "b200sat_default_settings", "b200sat_last_error", "b200sat_device_count",
     "b200sat_new", "b200sat_free", "b200sat_n_vars", "b200sat_n_clauses", "b200sat_new_var",
     "b200sat_add_clause", "b200sat_preprocess", "b200sat_solve_limited", "b200sat_get_stats",
+    "b200sat_progress_estimate", "b200sat_abi_sizes",
     "b200sat_engine_create", "b200sat_engine_destroy", "b200sat_engine_upload",
     "b200sat_engine_generate_ksat", "b200sat_engine_solve", "b200sat_engine_download",
     "b200sat_engine_batch_dims", "b200sat_engine_download_batch", "b200sat_engine_configure",
@@ -161,6 +162,10 @@ def lib():
     L.b200sat_solve_limited.argtypes = [vp, C.POINTER(Budget), u32p, C.c_size_t, u8p, C.c_size_t]
     L.b200sat_solve_limited.restype = C.c_int
     L.b200sat_get_stats.argtypes = [vp, C.POINTER(StatsStruct)]
+    L.b200sat_progress_estimate.argtypes = [vp]
+    L.b200sat_progress_estimate.restype = C.c_double
+    L.b200sat_abi_sizes.argtypes = [C.POINTER(C.c_uint32)]
+    L.b200sat_abi_sizes.restype = None
     L.b200sat_engine_create.argtypes = [C.c_int]
     L.b200sat_engine_create.restype = vp
     L.b200sat_engine_destroy.argtypes = [vp]
@@ -214,6 +219,12 @@ def lib():
     L.b200sat_free_buffer.argtypes = [vp]
     L.b200sat_free_buffer.restype = None
     L.b200sat_write_result.argtypes = [C.c_char_p, C.c_int, u8p, C.c_uint32]
+    # the hand-written mirrors below must have the library's struct sizes: fail loudly instead of reading garbage
+    sizes = (C.c_uint32 * 4)()
+    L.b200sat_abi_sizes(sizes)
+    mine = (C.sizeof(Result), C.sizeof(Settings), C.sizeof(StatsStruct), C.sizeof(LaunchInfo))
+    if tuple(sizes) != mine:
+        raise EngineError(E_ARG, "libb200sat.so struct sizes %s != binding %s (stale build?)" % (tuple(sizes), mine))
     _lib = L
     return L
 
@@ -255,8 +266,8 @@ class Stats(dict):
 
 class SolveRes:
     """sat.rs:21-25: UnSAT(stats) | SAT(model, stats) | Interrupted(progress, solver)"""
-    def __init__(self, kind, stats, model=None):
-        self.kind, self.stats, self.model = kind, stats, model
+    def __init__(self, kind, stats, model=None, progress=0.0):
+        self.kind, self.stats, self.model, self.progress = kind, stats, model, progress
 
     def is_sat(self):
         return self.kind == SAT
@@ -324,7 +335,7 @@ class Solver:
             # model as Vec<Lit> in var order (minisat.rs:68,235-239)
             lits = [mk_lit(v, model[v] == 0) for v in range(n) if model[v] != 2]
             return SolveRes(SAT, st, lits)
-        return SolveRes(rc, st)
+        return SolveRes(rc, st, progress=float(lib().b200sat_progress_estimate(self._h)) if rc == INTERRUPTED else 0.0)
 
     def stats(self):
         s = StatsStruct()

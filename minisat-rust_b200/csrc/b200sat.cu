@@ -1424,6 +1424,7 @@ struct b200sat_solver {
     std::vector<u32> clause_nvars;   /* n_vars at each add_clause */
     size_t n_clauses_known = 0;
     b200sat_stats stats;
+    double progress = 0.0;           /* of the last SolveRes::Interrupted */
     b200sat_engine *eng = nullptr;
 };
 
@@ -1561,6 +1562,7 @@ extern "C" int b200sat_solve_limited(b200sat_solver *h, const b200sat_budget *b,
     h->n_clauses_known = r.n_clauses_pre;
     if (r.verdict == B200SAT_INTERRUPTED) { /* SolveRes::Interrupted(progress, solver): the handle stays usable */
         h->resident = true;
+        h->progress = r.progress;
         return B200SAT_INTERRUPTED;
     }
     h->spent = true;
@@ -1575,4 +1577,9 @@ extern "C" int b200sat_solve_limited(b200sat_solver *h, const b200sat_budget *b,
 
 extern "C" void b200sat_get_stats(const b200sat_solver *h, b200sat_stats *out) {
     if (h && out) *out = h->stats;
+}
+extern "C" double b200sat_progress_estimate(const b200sat_solver *h) { return h ? h->progress : 0.0; }
+extern "C" void b200sat_abi_sizes(uint32_t out[4]) {
+    out[0] = (uint32_t)sizeof(b200sat_result); out[1] = (uint32_t)sizeof(b200sat_settings);
+    out[2] = (uint32_t)sizeof(b200sat_stats); out[3] = (uint32_t)sizeof(b200sat_launch_info);
 }

@@ -2374,6 +2374,7 @@ template <class VT, bool COUNT, bool PF = false> struct WarpSolver {
             r->trace_hash = s.trace_hash;
             r->exported = s.exported;
             r->imported = s.imported;
+            r->progress = (s.status == ST_OK && verdict == B200SAT_INTERRUPTED) ? s.progress : 0.0;
         }
         if (P.models && s.status == ST_OK && verdict == B200SAT_SAT) { /* formula/util.rs:35-41 */
             u8 *m = P.models + (size_t)res_index * P.model_stride;

@@ -1529,6 +1529,7 @@ int oracle_solve_csr(const uint32_t *clause_off, const uint32_t *lits, uint32_t 
     out->traffic[4] = T.moves; out->traffic[5] = T.implied; out->traffic[6] = T.an_words; out->traffic[7] = T.learnt_words;
     out->trace_hash = solver.search.trace_hash;
     out->seconds = std::chrono::duration<double>(t2 - t1).count();
+    out->progress = verdict == ORACLE_INTERRUPTED && !(flags & ORACLE_F_NO_SOLVE) ? solver.search.progress : 0.0;
     if (verdict == ORACLE_SAT && model_out) {
         uint32_t n = std::min<uint32_t>(model_cap, (uint32_t)model.size());
         memcpy(model_out, model.data(), n);

@@ -82,6 +82,7 @@ typedef struct oracle_result {
                                  6 analysis words read, 7 learnt words written            */
     uint64_t trace_hash;      /* FNV-1a over (bt level, learnt lits) of every conflict    */
     double   seconds;         /* wall time of preprocess + solve                          */
+    double   progress;        /* ORACLE_INTERRUPTED: the f64 of SolveRes::Interrupted (search/util.rs:5-14), else 0 */
 } oracle_result;
 
 void oracle_default_settings(oracle_settings *s);

@@ -43,7 +43,7 @@ class Result(C.Structure):
         ("verdict", C.c_int32), ("n_vars", C.c_uint32), ("n_clauses_ingest", C.c_uint32),
         ("n_clauses_pre", C.c_uint32), ("eliminated_vars", C.c_uint32), ("pre_ok", C.c_uint32),
         ("stats", C.c_uint64 * 8), ("traffic", C.c_uint64 * 8), ("trace_hash", C.c_uint64),
-        ("seconds", C.c_double),
+        ("seconds", C.c_double), ("progress", C.c_double),
     ]
 
     def stats_dict(self):

@@ -34,7 +34,7 @@ class Result(C.Structure):
         ("n_clauses_ingest", C.c_uint32), ("n_clauses_pre", C.c_uint32), ("eliminated_vars", C.c_uint32),
         ("pre_ok", C.c_uint32), ("attempts", C.c_uint32),
         ("stats", C.c_uint64 * 8), ("traffic", C.c_uint64 * 8), ("trace_hash", C.c_uint64),
-        ("exported", C.c_uint32), ("imported", C.c_uint32),
+        ("exported", C.c_uint32), ("imported", C.c_uint32), ("progress", C.c_double),
     ]
 
 

@@ -232,6 +232,8 @@ def test_budget_interrupts_and_the_solver_resumes(po, emu, kind):
         for o, e in zip(ores, eres):
             assert e.status == 0 and e.verdict == o.verdict and list(e.stats) == list(o.stats)
             assert e.trace_hash == o.trace_hash
+            assert e.progress == o.progress      # the f64 of SolveRes::Interrupted (search/util.rs:5-14); 0 unless interrupted
+            assert o.verdict == po.INTERRUPTED or o.progress == 0.0
             n_int += o.verdict == po.INTERRUPTED
         assert n_int >= 3
         # ... and resumed without a budget: same as the oracle's second solve_limited call
@@ -285,7 +287,7 @@ def test_hand_traces_device_source(po, emu):
 def test_hand_traces_call_semantics_device_source(po, emu):
     """H6 / H7 of tests/golden/hand_traces.md (false assumption; conflict budget -> Interrupted -> second solve_limited)
     against the device source under the emulator."""
-    from common import HAND_TRACES_CALLS
+    from common import HAND_TRACES_CALLS, HAND_TRACES_PROGRESS
     for name, (clauses, assumps, (cb, pb), first, second) in HAND_TRACES_CALLS.items():
         ioff, coff, lits = batch_of([csr_of(clauses)])
         nv = max(abs(x) for c in clauses for x in c)
@@ -299,6 +301,8 @@ def test_hand_traces_call_semantics_device_source(po, emu):
             assert list(res[0].stats) == want[1], (name, rounds, list(res[0].stats))
             if len(want) > 2:
                 assert [int(x) for x in models[0][:nv]] == want[2], name
+            if rounds == 0 and name in HAND_TRACES_PROGRESS:
+                assert res[0].progress == HAND_TRACES_PROGRESS[name], (name, res[0].progress)
 
 
 @pytest.mark.parametrize("kind", [0, 1])

@@ -674,6 +674,7 @@ def test_trait_semantics_through_the_handle(pkg, po, kind_name):
         r1 = s.solve_limited(budget=(3, -1), assumptions=assumps)
         assert r1.kind == o1.verdict and [r1.stats[k] for k in pkg.STAT_NAMES] == list(o1.stats), trial
         if o1.verdict == pkg.INTERRUPTED:
+            assert r1.progress == o1.progress, (trial, r1.progress, o1.progress)   # SolveRes::Interrupted(progress, _)
             r2 = s.solve_limited(assumptions=assumps)
             assert r2.kind == o2.verdict and [r2.stats[k] for k in pkg.STAT_NAMES] == list(o2.stats), trial
             assert r2.stats["solves"] == 2
@@ -917,7 +918,7 @@ def test_hand_traces_call_semantics_gpu(pkg):
     """H6 / H7 of tests/golden/hand_traces.md through the trait mirror of the C ABI (b200sat_new_var / add_clause /
     preprocess / solve_limited with a budget and assumptions): a false assumption ends UNSAT; a conflict budget of 1
     returns Interrupted with the handle still usable, the second solve_limited finishes the search."""
-    from common import HAND_TRACES_CALLS
+    from common import HAND_TRACES_CALLS, HAND_TRACES_PROGRESS
     for name, (clauses, assumps, (cb, pb), first, second) in HAND_TRACES_CALLS.items():
         nv = max(abs(x) for c in clauses for x in c)
         s = pkg.CoreSolver()
@@ -928,6 +929,8 @@ def test_hand_traces_call_semantics_gpu(pkg):
         assert s.preprocess()
         r = s.solve_limited(budget=(cb, pb) if (cb >= 0 or pb >= 0) else None, assumptions=assumps)
         assert r.kind == first[0] and [r.stats[k] for k in pkg.STAT_NAMES] == first[1], (name, r.kind, r.stats)
+        if name in HAND_TRACES_PROGRESS:      # the f64 of SolveRes::Interrupted(progress, solver)
+            assert abs(r.progress - HAND_TRACES_PROGRESS[name]) < 1e-15, (name, r.progress)
         if second is not None:
             r = s.solve_limited(assumptions=assumps)
             assert r.kind == second[0] and [r.stats[k] for k in pkg.STAT_NAMES] == second[1], (name, r.kind, r.stats)

@@ -143,7 +143,7 @@ def test_hand_traces(po):
 def test_hand_traces_call_semantics(po):
     """H6 / H7 of tests/golden/hand_traces.md: a false assumption, a conflict budget with Interrupted and a second
     solve_limited -- constants derived by hand from the Rust source pin the oracle's round-2 additions."""
-    from common import HAND_TRACES_CALLS, csr_of
+    from common import HAND_TRACES_CALLS, HAND_TRACES_PROGRESS, csr_of
     for name, (clauses, assumps, (cb, pb), first, second) in HAND_TRACES_CALLS.items():
         off, lits = csr_of(clauses)
         for rounds, want in ((0, first), (1, second)):
@@ -157,6 +157,8 @@ def test_hand_traces_call_semantics(po):
             assert r.verdict == want[0] and list(r.stats) == want[1], (name, rounds, r.verdict, list(r.stats))
             if len(want) > 2:
                 assert [int(x) for x in m] == want[2], name
+            if rounds == 0 and name in HAND_TRACES_PROGRESS:
+                assert r.progress == HAND_TRACES_PROGRESS[name], (name, r.progress)
 
 
 def test_hand_trace_document_and_fixture_agree():
