@@ -98,6 +98,8 @@ HAND_TRACES = {
     "H10_deep_minimisation": ([[1, 2], [1, 3, 4], [-2, -3, 4]], 0, {}, 1, [1, 1, 4, 0, 1, 5, 2, 1], [0, 1, 1, 1], 0, 3),
     "H11_random_decisions": ([[1, 2, 3]], 0, {"random_var_freq": 1.0}, 1, [1, 1, 3, 1, 0, 3, 0, 0], [0, 1, 0], 0, 1),
     "H12_reduce_db_removes_the_learnt": ([[1, 2, 3, 4], [1, -2, 3, 4]], 0, {"restart_first": 1.0}, 1, [1, 2, 7, 0, 1, 8, 3, 0], [0, 1, 1, 0], 0, 2),
+    "H13_basic_minimisation": ([[1, 2], [1, 3, 4], [-2, -3, 4]], 0, {"ccmin_mode": 1}, 1, [1, 1, 4, 0, 1, 5, 2, 1], [0, 1, 1, 1], 0, 3),
+    "H14_no_minimisation": ([[1, 2], [1, 3, 4], [-2, -3, 4]], 0, {"ccmin_mode": 0}, 1, [1, 1, 4, 0, 1, 5, 3, 0], [0, 1, 1, 1], 0, 3),
 }
 
 # H6 / H7 of tests/golden/hand_traces.md: solve_limited(budget, assumptions) semantics, derived by hand from the Rust source.
