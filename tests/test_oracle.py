@@ -170,7 +170,7 @@ def test_hand_trace_document_and_fixture_agree():
     doc = {}
     for sec in re.split(r"\n## ", text)[1:]:
         stats = [[int(x) for x in t.split(",")] for t in re.findall(r"[Ss]tats `\[([0-9, ]+)\]`", sec)]
-        for key in re.findall(r"H\d+", sec.split("\n", 1)[0]):     # a heading may cover several cases ("H13, H14")
+        for key in re.findall(r"H\d+", sec.split("\n", 1)[0].split("\u2014")[0]):   # "H13, H14 \u2014 ...": the cases in front of the dash
             doc[key] = stats
     for name, t in HAND_TRACES.items():
         key = name.split("_")[0]
