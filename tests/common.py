@@ -109,7 +109,10 @@ HAND_TRACES_CALLS = {
     "H6_false_assumption": ([[1, 2], [-1, 2]], [3], (-1, -1), (0, [1, 1, 0, 0, 1, 2, 1, 0]), None),
     "H7_conflict_budget_then_resume": ([[1, 3, 2], [1, 3, -2]], [], (1, -1), (2, [1, 1, 2, 0, 1, 3, 2, 0]),
                                        (1, [2, 2, 5, 0, 1, 6, 2, 0], [0, 1, 1])),
+    "H15_propagation_budget_then_resume": ([[1, 3, 2], [1, 3, -2]], [], (-1, 1), (2, [1, 1, 1, 0, 0, 1, 0, 0]),
+                                           (1, [2, 2, 5, 0, 1, 5, 2, 0], [1, 1, 0])),
 }
 # the f64 carried by SolveRes::Interrupted after the FIRST call (search/util.rs:5-14; derivation in hand_traces.md H7)
-HAND_TRACES_PROGRESS = {"H7_conflict_budget_then_resume": ((1.0 / 3.0) * (1.0 / 3.0)) * 2.0}
+HAND_TRACES_PROGRESS = {"H7_conflict_budget_then_resume": ((1.0 / 3.0) * (1.0 / 3.0)) * 2.0,
+                        "H15_propagation_budget_then_resume": ((1.0 / 3.0) * (1.0 / 3.0)) * 1.0}
 
